@@ -1,0 +1,366 @@
+/*
+ * ref_harness.cpp -- C entry points around the UNMODIFIED reference library
+ * (TEST INFRASTRUCTURE; linked into oracle/_ref/libsaena_ref.so by
+ * oracle/Makefile, never into the product).
+ *
+ * It drives the reference exactly as experiments/Poisson.cpp does
+ * (/root/reference/experiments/Poisson.cpp:81-246: laplacian3D -> assemble ->
+ * rhs -> amg::set_matrix -> amg::set_rhs -> amg::solve_pCG) on one MPI rank,
+ * and exposes
+ *   - the finished hierarchy (the arrays saena_matrix::set_off_on_diagonal,
+ *     prolong_matrix::findLocalRemote and restrict_matrix::transposeP built),
+ *     so tests can hand the same hierarchy to the CUDA path and to the C oracle;
+ *   - the reference's own hot-path functions (matvec, chebyshev, jacobi,
+ *     residual, R/P matvec, vcycle, solve_pCG with a residual history taken by
+ *     ref_shim/ref_hooks.h) as the parity oracle;
+ *   - the reference CPU solve as the bench's cpu_baseline ("kind": "reference").
+ */
+#define SAENA_REF_HARNESS_TU
+#include "ref_shim/ref_hooks.h"
+
+#include "saena.hpp"
+#include "saena_object.h"
+#include "saena_matrix.h"
+#include "grid.h"
+#include "aux_functions2.h"
+
+#include <cstdio>
+#include <cstring>
+#include <unistd.h>
+#include <fcntl.h>
+#include <vector>
+
+// ---------------------------------------------------------------- residual history
+static std::vector<double> g_rr;
+extern "C" void saena_ref_record_rr(double rr) { g_rr.push_back(rr); }
+
+namespace {
+
+struct Handle {
+    saena::matrix *A = nullptr;
+    saena::vector *rhs = nullptr;
+    saena::options *opts = nullptr;
+    saena::amg *solver = nullptr;
+    bool vcycle_mem = false;
+};
+
+// The reference prints its setup report unconditionally; keep test logs readable.
+struct QuietStdout {
+    int saved = -1;
+    explicit QuietStdout(bool on) {
+        if (!on) return;
+        fflush(stdout);
+        saved = dup(1);
+        int devnull = open("/dev/null", O_WRONLY);
+        dup2(devnull, 1);
+        close(devnull);
+    }
+    ~QuietStdout() {
+        if (saved < 0) return;
+        fflush(stdout);
+        dup2(saved, 1);
+        close(saved);
+    }
+};
+
+void ensure_mpi() {
+    int inited = 0;
+    MPI_Initialized(&inited);
+    if (!inited) MPI_Init(nullptr, nullptr);
+}
+
+saena_object *obj(Handle *h) { return h->solver->get_object(); }
+
+void finish_setup(Handle *h, saena::vector *rhs, bool quiet) {
+    QuietStdout q(quiet);
+    h->solver = new saena::amg();
+    h->solver->set_scale(false);  // Poisson.cpp:41,193
+    h->solver->set_matrix(h->A, h->opts);
+    h->solver->set_rhs(*rhs);
+}
+
+}  // namespace
+
+extern "C" {
+
+struct sref_opts {
+    int max_iter;
+    double tol;
+    const char *smoother;
+    int pre, post;
+    const char *psmoother;
+    float conn_str;
+    int dynamic_levels, max_level, float_level;
+    double filter_thre, filter_max;
+    int filter_start, filter_rate;
+};
+
+static saena::options *make_opts(const sref_opts *o) {
+    return new saena::options(o->max_iter, o->tol, o->smoother, o->pre, o->post, o->psmoother, o->conn_str,
+                              o->dynamic_levels != 0, o->max_level, o->float_level, o->filter_thre,
+                              o->filter_max, o->filter_start, o->filter_rate, false, 0.1f, 5000);
+}
+
+// 3D 7-point Poisson, exactly the driver sequence of experiments/Poisson.cpp.
+void *sref_poisson_new(int mx, const sref_opts *o, int quiet) {
+    ensure_mpi();
+    MPI_Comm comm = MPI_COMM_WORLD;
+    Handle *h = new Handle();
+    {
+        QuietStdout q(quiet != 0);
+        h->A = new saena::matrix(comm);
+        saena::laplacian3D(h->A, mx, mx, mx);
+        h->A->set_remove_boundary(true);
+        h->A->assemble(false);
+    }
+    value_t *rhs_std = nullptr;
+    index_t orig_sz = saena::laplacian3D_set_rhs(rhs_std, mx, mx, mx, comm);
+    index_t my_split = 0;
+    saena::find_split(orig_sz, my_split, comm);
+    h->rhs = new saena::vector(comm);
+    h->rhs->set(&rhs_std[0], orig_sz, my_split);
+    h->rhs->assemble();
+    h->opts = make_opts(o);
+    finish_setup(h, h->rhs, quiet != 0);
+    saena_free(rhs_std);
+    return h;
+}
+
+// Generic square matrix from COO triplets (global ids) + dense rhs; boundary removal off.
+void *sref_coo_new(int n, long nnz, const int *row, const int *col, const double *val, const double *rhs,
+                   const sref_opts *o, int quiet) {
+    ensure_mpi();
+    MPI_Comm comm = MPI_COMM_WORLD;
+    Handle *h = new Handle();
+    {
+        QuietStdout q(quiet != 0);
+        h->A = new saena::matrix(comm);
+        for (long i = 0; i < nnz; ++i) h->A->set(row[i], col[i], val[i]);
+        h->A->set_remove_boundary(false);
+        h->A->assemble(false);
+    }
+    h->rhs = new saena::vector(comm);
+    h->rhs->set(rhs, n, 0);
+    h->rhs->assemble();
+    h->opts = make_opts(o);
+    finish_setup(h, h->rhs, quiet != 0);
+    return h;
+}
+
+void sref_free(void *hv) {
+    Handle *h = (Handle *)hv;
+    if (!h) return;
+    if (h->vcycle_mem) obj(h)->free_vcycle_memory();
+    h->solver->destroy();
+    h->A->destroy();
+    delete h->solver;
+    delete h->rhs;
+    delete h->opts;
+    delete h->A;
+    delete h;
+}
+
+// number of grids = max_level + 1; operators P/R/Ac exist on levels < max_level
+int sref_max_level(void *hv) { return obj((Handle *)hv)->max_level; }
+
+struct sref_level_info {
+    int M, Mbig, Nbig;
+    long nnz_l, nnz_local, nnz_remote;
+    int col_remote_size, vIndexSize, recvSize, numRecvProc, numSendProc;
+    int use_double, active;
+    double eig_max;
+};
+
+static saena_matrix *level_A(Handle *h, int l) { return obj(h)->grids[l].A; }
+
+// kind: 0 = A_l, 1 = P_l (fine rows x coarse cols), 2 = R_l (coarse rows x fine cols)
+int sref_level_info_get(void *hv, int l, int kind, sref_level_info *out) {
+    Handle *h = (Handle *)hv;
+    memset(out, 0, sizeof(*out));
+    if (l < 0 || l > obj(h)->max_level) return 1;
+    Grid &g = obj(h)->grids[l];
+    if (kind == 0) {
+        saena_matrix *A = g.A;
+        out->M = A->M; out->Mbig = A->Mbig; out->Nbig = A->Mbig;
+        out->nnz_l = A->nnz_l; out->nnz_local = A->nnz_l_local; out->nnz_remote = A->nnz_l_remote;
+        out->col_remote_size = A->col_remote_size; out->vIndexSize = A->vIndexSize; out->recvSize = A->recvSize;
+        out->numRecvProc = A->numRecvProc; out->numSendProc = A->numSendProc;
+        out->use_double = A->use_double; out->active = A->active; out->eig_max = A->eig_max_of_invdiagXA;
+    } else if (l >= obj(h)->max_level) {
+        return 1;
+    } else if (kind == 1) {
+        prolong_matrix &P = g.P;
+        out->M = P.M; out->Mbig = P.Mbig; out->Nbig = P.Nbig;
+        out->nnz_l = P.nnz_l; out->nnz_local = P.nnz_l_local; out->nnz_remote = P.nnz_l_remote;
+        out->col_remote_size = P.col_remote_size; out->vIndexSize = P.vIndexSize; out->recvSize = P.recvSize;
+        out->numRecvProc = P.numRecvProc; out->numSendProc = P.numSendProc;
+        out->use_double = P.use_double; out->active = g.active;
+    } else {
+        restrict_matrix &R = g.R;
+        out->M = R.M; out->Mbig = R.Mbig; out->Nbig = R.Nbig;
+        out->nnz_l = R.nnz_l; out->nnz_local = R.nnz_l_local; out->nnz_remote = R.nnz_l_remote;
+        out->col_remote_size = R.col_remote_size; out->vIndexSize = R.vIndexSize; out->recvSize = R.recvSize;
+        out->numRecvProc = R.numRecvProc; out->numSendProc = R.numSendProc;
+        out->use_double = R.use_double; out->active = g.active;
+    }
+    return 0;
+}
+
+// field ids for sref_array
+enum { F_NNZ_PER_ROW_LOCAL = 0, F_COL_LOCAL = 1, F_VAL_LOCAL = 2, F_INV_DIAG = 3, F_SPLIT = 4, F_SPLIT_NEW = 5,
+       F_ROW_REMOTE = 6, F_VAL_REMOTE = 7, F_NNZ_PER_COL_REMOTE = 8, F_ENTRY_ROW = 9, F_ENTRY_COL = 10,
+       F_ENTRY_VAL = 11 };
+
+// Copies one layout array of an operator into `dst` (if non-null) and returns its element count.
+long sref_array(void *hv, int l, int kind, int field, void *dst) {
+    Handle *h = (Handle *)hv;
+    Grid &g = obj(h)->grids[l];
+#define COPY_VEC(v) do { if (dst && !(v).empty()) memcpy(dst, (v).data(), (v).size() * sizeof((v)[0])); \
+                         return (long)(v).size(); } while (0)
+#define COPY_PTR(p, n) do { if (dst && (n) > 0) memcpy(dst, (p), (size_t)(n) * sizeof((p)[0])); return (long)(n); } while (0)
+#define COPY_ENTRY(vec, member, T) do { if (dst) { T *d = (T *)dst; for (size_t i = 0; i < (vec).size(); ++i) \
+                         d[i] = (T)(vec)[i].member; } return (long)(vec).size(); } while (0)
+    if (kind == 0) {
+        saena_matrix *A = g.A;
+        switch (field) {
+            case F_NNZ_PER_ROW_LOCAL: COPY_VEC(A->nnzPerRow_local);
+            case F_COL_LOCAL: COPY_PTR(A->col_local, A->nnz_l_local);
+            case F_VAL_LOCAL: COPY_PTR(A->val_local, A->nnz_l_local);
+            case F_INV_DIAG: COPY_PTR(A->inv_diag, A->M);
+            case F_SPLIT: COPY_VEC(A->split);
+            case F_ROW_REMOTE: COPY_PTR(A->row_remote, A->nnz_l_remote);
+            case F_VAL_REMOTE: COPY_PTR(A->val_remote, A->nnz_l_remote);
+            case F_NNZ_PER_COL_REMOTE: COPY_VEC(A->nnzPerCol_remote);
+            case F_ENTRY_ROW: COPY_ENTRY(A->entry, row, int);
+            case F_ENTRY_COL: COPY_ENTRY(A->entry, col, int);
+            case F_ENTRY_VAL: COPY_ENTRY(A->entry, val, double);
+            default: return -1;
+        }
+    } else if (kind == 1) {
+        prolong_matrix &P = g.P;
+        switch (field) {
+            case F_NNZ_PER_ROW_LOCAL: COPY_VEC(P.nnzPerRow_local);
+            case F_COL_LOCAL: COPY_VEC(P.col_local);
+            case F_VAL_LOCAL: COPY_VEC(P.val_local);
+            case F_SPLIT: COPY_VEC(P.split);
+            case F_SPLIT_NEW: COPY_VEC(P.splitNew);
+            case F_ROW_REMOTE: COPY_VEC(P.row_remote);
+            case F_VAL_REMOTE: COPY_VEC(P.val_remote);
+            case F_NNZ_PER_COL_REMOTE: COPY_VEC(P.nnzPerCol_remote);
+            case F_ENTRY_ROW: COPY_ENTRY(P.entry, row, int);
+            case F_ENTRY_COL: COPY_ENTRY(P.entry, col, int);
+            case F_ENTRY_VAL: COPY_ENTRY(P.entry, val, double);
+            default: return -1;
+        }
+    } else {
+        restrict_matrix &R = g.R;
+        switch (field) {
+            case F_NNZ_PER_ROW_LOCAL: COPY_VEC(R.nnzPerRow_local);
+            case F_COL_LOCAL: COPY_VEC(R.col_local);
+            case F_VAL_LOCAL: COPY_VEC(R.val_local);
+            case F_SPLIT: COPY_VEC(R.split);
+            case F_SPLIT_NEW: COPY_VEC(R.splitNew);
+            case F_ROW_REMOTE: COPY_VEC(R.row_remote);
+            case F_VAL_REMOTE: COPY_VEC(R.val_remote);
+            case F_NNZ_PER_COL_REMOTE: COPY_VEC(R.nnzPerCol_remote);
+            case F_ENTRY_ROW: COPY_ENTRY(R.entry, row, int);
+            case F_ENTRY_COL: COPY_ENTRY(R.entry, col, int);
+            case F_ENTRY_VAL: COPY_ENTRY(R.entry, val, double);
+            default: return -1;
+        }
+    }
+#undef COPY_VEC
+#undef COPY_PTR
+#undef COPY_ENTRY
+}
+
+// solver parameters the reference ended up with
+void sref_params(void *hv, int *pre, int *post, int *max_iter, double *tol, int *smoother_is_cheb) {
+    saena_object *o = obj((Handle *)hv);
+    *pre = o->preSmooth; *post = o->postSmooth; *max_iter = o->solver_max_iter; *tol = o->solver_tol;
+    *smoother_is_cheb = (o->smoother == "chebyshev");
+}
+
+// grids[0].rhs (repartitioned, boundary rows removed), length grids[0].A->M
+void sref_rhs(void *hv, double *out) {
+    saena_object *o = obj((Handle *)hv);
+    memcpy(out, o->grids[0].rhs, sizeof(double) * (size_t)o->grids[0].A->M);
+}
+
+// ---- the reference's own hot-path functions ----
+void sref_matvec(void *hv, int l, int kind, const double *v, double *w) {
+    Grid &g = obj((Handle *)hv)->grids[l];
+    if (kind == 0) g.A->matvec(v, w);
+    else if (kind == 1) g.P.matvec(v, w);
+    else g.R.matvec(v, w);
+}
+
+void sref_residual(void *hv, int l, const double *u, const double *rhs, double *res) {
+    obj((Handle *)hv)->grids[l].A->residual(u, rhs, res);
+}
+
+// smoother: 0 = jacobi, 1 = chebyshev (saena_object.tpp:85-96 dispatch)
+void sref_smooth(void *hv, int l, int smoother, int iters, double *u, const double *rhs) {
+    saena_matrix *A = level_A((Handle *)hv, l);
+    if (smoother == 1) A->chebyshev(iters, u, rhs);
+    else A->jacobi(iters, u, rhs);
+}
+
+double sref_dot(void *hv, const double *a, const double *b, int n) {
+    double d = 0;
+    dotProduct(a, b, n, &d, level_A((Handle *)hv, 0)->comm);
+    return d;
+}
+
+// One V-cycle starting at grid `l` with the solver's current smoother settings.
+void sref_vcycle(void *hv, int l, int pre, int post, int smoother, double *u, double *rhs) {
+    Handle *h = (Handle *)hv;
+    saena_object *o = obj(h);
+    if (!h->vcycle_mem) { o->alloc_vcycle_memory(); h->vcycle_mem = true; }
+    o->preSmooth = pre; o->postSmooth = post; o->smoother = smoother ? "chebyshev" : "jacobi";
+    o->vcycle(&o->grids[l], u, rhs);
+}
+
+// Coarsest-level direct solve as the reference does it (SuperLU_DIST pdgssvx).
+void sref_coarsest_solve(void *hv, double *u, double *rhs) {
+    saena_object *o = obj((Handle *)hv);
+    o->solve_coarsest_SuperLU(o->grids[o->max_level].A, u, rhs);
+}
+
+// saena::amg::solve_pCG; returns the reported iteration count (i+1) and the
+// history sqrt(<r,r>) [0] = initial, [k] = after iteration k.
+int sref_solve_pcg(void *hv, int max_iter, double tol, int smoother, int pre, int post, double *u_out,
+                   double *hist, int hist_cap, int *hist_len, int quiet) {
+    Handle *h = (Handle *)hv;
+    if (h->vcycle_mem) { obj(h)->free_vcycle_memory(); h->vcycle_mem = false; }
+    h->opts->set_solve_params(max_iter, tol, smoother ? "chebyshev" : "jacobi", pre, post);
+    g_rr.clear();
+    value_t *u = nullptr;
+    {
+        QuietStdout q(quiet != 0);
+        h->solver->solve_pCG(u, h->opts, false);
+    }
+    const int M = obj(h)->grids[0].A->M;
+    if (u_out) memcpy(u_out, u, sizeof(double) * (size_t)M);
+    saena_free(u);
+    int n = (int)g_rr.size();
+    *hist_len = n;
+    for (int i = 0; i < n && i < hist_cap; ++i) hist[i] = sqrt(g_rr[i]);
+    return n - 1;  // one <r,r> before the loop, one per executed iteration
+}
+
+// Wall-clock seconds of `reps` reference solve_pCG calls (cpu_baseline).
+double sref_time_solve_pcg(void *hv, int reps) {
+    Handle *h = (Handle *)hv;
+    if (h->vcycle_mem) { obj(h)->free_vcycle_memory(); h->vcycle_mem = false; }
+    QuietStdout q(true);
+    double t0 = MPI_Wtime();
+    for (int i = 0; i < reps; ++i) {
+        value_t *u = nullptr;
+        h->solver->solve_pCG(u, h->opts, false);
+        saena_free(u);
+    }
+    return MPI_Wtime() - t0;
+}
+
+}  // extern "C"
