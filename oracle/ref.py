@@ -1,0 +1,227 @@
+"""ctypes bridge to oracle/_ref/libsaena_ref.so -- the UNMODIFIED reference compiled by
+oracle/Makefile (TEST INFRASTRUCTURE: importable only from tests/, bench.py's cpu_baseline /
+--impl reference legs and __graft_entry__.smoke()).
+
+It runs the reference's own host setup (one MPI rank) and returns the finished hierarchy in
+`saena_b200.hierarchy` containers, and calls the reference's own hot-path functions as the
+parity oracle.  See oracle/ref_harness.cpp for the C side and the reference lines it drives.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from saena_b200.hierarchy import (F64, I32, KIND_A, KIND_P, KIND_R, Hierarchy, Level, Operator)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libsaena_ref.so")
+
+# field ids of sref_array (ref_harness.cpp)
+F_NNZ_PER_ROW_LOCAL, F_COL_LOCAL, F_VAL_LOCAL, F_INV_DIAG, F_SPLIT, F_SPLIT_NEW = range(6)
+F_ROW_REMOTE, F_VAL_REMOTE, F_NNZ_PER_COL_REMOTE, F_ENTRY_ROW, F_ENTRY_COL, F_ENTRY_VAL = range(6, 12)
+
+
+class _Opts(ctypes.Structure):
+    _fields_ = [("max_iter", ctypes.c_int), ("tol", ctypes.c_double), ("smoother", ctypes.c_char_p),
+                ("pre", ctypes.c_int), ("post", ctypes.c_int), ("psmoother", ctypes.c_char_p),
+                ("conn_str", ctypes.c_float), ("dynamic_levels", ctypes.c_int), ("max_level", ctypes.c_int),
+                ("float_level", ctypes.c_int), ("filter_thre", ctypes.c_double), ("filter_max", ctypes.c_double),
+                ("filter_start", ctypes.c_int), ("filter_rate", ctypes.c_int)]
+
+
+class _LevelInfo(ctypes.Structure):
+    _fields_ = [("M", ctypes.c_int), ("Mbig", ctypes.c_int), ("Nbig", ctypes.c_int),
+                ("nnz_l", ctypes.c_long), ("nnz_local", ctypes.c_long), ("nnz_remote", ctypes.c_long),
+                ("col_remote_size", ctypes.c_int), ("vIndexSize", ctypes.c_int), ("recvSize", ctypes.c_int),
+                ("numRecvProc", ctypes.c_int), ("numSendProc", ctypes.c_int),
+                ("use_double", ctypes.c_int), ("active", ctypes.c_int), ("eig_max", ctypes.c_double)]
+
+
+@dataclass
+class RefOptions:
+    """The options of /root/reference/data/options006_poisson.xml (the Poisson driver's file)."""
+    max_iter: int = 50
+    tol: float = 1e-8
+    smoother: str = "chebyshev"
+    pre: int = 3
+    post: int = 3
+    psmoother: str = "jacobi"
+    conn_str: float = 0.2
+    dynamic_levels: bool = True
+    max_level: int = 20
+    float_level: int = 0
+    filter_thre: float = 1e-12
+    filter_max: float = 1e-9
+    filter_start: int = 1
+    filter_rate: int = 1
+
+    def _c(self) -> _Opts:
+        return _Opts(self.max_iter, self.tol, self.smoother.encode(), self.pre, self.post, self.psmoother.encode(),
+                     self.conn_str, int(self.dynamic_levels), self.max_level, self.float_level, self.filter_thre,
+                     self.filter_max, self.filter_start, self.filter_rate)
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError(f"{LIB_PATH} missing: run `make -C oracle ref` where /root/reference exists")
+        L = ctypes.CDLL(LIB_PATH)
+        L.sref_poisson_new.restype = ctypes.c_void_p
+        L.sref_coo_new.restype = ctypes.c_void_p
+        L.sref_array.restype = ctypes.c_long
+        L.sref_dot.restype = ctypes.c_double
+        L.sref_time_solve_pcg.restype = ctypes.c_double
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class RefSolver:
+    """A reference `saena::amg` after set_matrix + set_rhs (one MPI rank)."""
+
+    def __init__(self, handle, opts: RefOptions):
+        self._h = ctypes.c_void_p(handle)
+        self.opts = opts
+
+    @classmethod
+    def poisson(cls, mx: int, opts: RefOptions | None = None, quiet: bool = True) -> "RefSolver":
+        opts = opts or RefOptions()
+        c = opts._c()
+        return cls(lib().sref_poisson_new(int(mx), ctypes.byref(c), int(quiet)), opts)
+
+    @classmethod
+    def from_coo(cls, n, row, col, val, rhs, opts: RefOptions | None = None, quiet: bool = True) -> "RefSolver":
+        opts = opts or RefOptions()
+        c = opts._c()
+        row, col = np.ascontiguousarray(row, I32), np.ascontiguousarray(col, I32)
+        val, rhs = np.ascontiguousarray(val, F64), np.ascontiguousarray(rhs, F64)
+        return cls(lib().sref_coo_new(int(n), ctypes.c_long(len(val)), _p(row), _p(col), _p(val), _p(rhs),
+                                      ctypes.byref(c), int(quiet)), opts)
+
+    def close(self):
+        if self._h:
+            lib().sref_free(self._h)
+            self._h = None
+
+    # ---- hierarchy extraction ----
+    @property
+    def max_level(self) -> int:
+        return lib().sref_max_level(self._h)
+
+    def _info(self, l, kind) -> _LevelInfo:
+        info = _LevelInfo()
+        rc = lib().sref_level_info_get(self._h, l, kind, ctypes.byref(info))
+        assert rc == 0
+        return info
+
+    def _arr(self, l, kind, field, dtype):
+        n = lib().sref_array(self._h, l, kind, field, None)
+        assert n >= 0
+        out = np.zeros(n, dtype)
+        if n:
+            lib().sref_array(self._h, l, kind, field, _p(out))
+        return out
+
+    def _operator(self, l, kind) -> Operator:
+        info = self._info(l, kind)
+        assert info.nnz_remote == 0, "one-rank reference: no remote part expected"
+        return Operator(kind=kind, level=l, M=info.M, Mbig=info.Mbig, Nbig=info.Nbig, row_offset=0, col_offset=0,
+                        n_local_cols=info.Nbig,
+                        nnzPerRow_local=self._arr(l, kind, F_NNZ_PER_ROW_LOCAL, I32),
+                        col_local=self._arr(l, kind, F_COL_LOCAL, I32),
+                        val_local=self._arr(l, kind, F_VAL_LOCAL, F64),
+                        use_double=bool(info.use_double))
+
+    def hierarchy(self) -> Hierarchy:
+        ml = self.max_level
+        levels = []
+        for l in range(ml + 1):
+            info = self._info(l, KIND_A)
+            lv = Level(level=l, A=self._operator(l, KIND_A), inv_diag=self._arr(l, KIND_A, F_INV_DIAG, F64),
+                       eig_max=float(info.eig_max), active=bool(info.active))
+            if l < ml:
+                lv.P = self._operator(l, KIND_P)
+                lv.R = self._operator(l, KIND_R)
+                lv.M_coarse_old = lv.R.M
+                lv.M_coarse = lv.R.M
+            levels.append(lv)
+        h = Hierarchy(levels=levels, coarse_n=levels[-1].A.Mbig,
+                      coarse_row=self._arr(ml, KIND_A, F_ENTRY_ROW, I32),
+                      coarse_col=self._arr(ml, KIND_A, F_ENTRY_COL, I32),
+                      coarse_val=self._arr(ml, KIND_A, F_ENTRY_VAL, F64))
+        return h
+
+    def rhs(self) -> np.ndarray:
+        out = np.zeros(self._info(0, KIND_A).M, F64)
+        lib().sref_rhs(self._h, _p(out))
+        return out
+
+    # ---- the reference's own hot-path functions ----
+    def matvec(self, l, kind, v) -> np.ndarray:
+        v = np.ascontiguousarray(v, F64)
+        w = np.zeros(self._info(l, kind).M, F64)
+        lib().sref_matvec(self._h, l, kind, _p(v), _p(w))
+        return w
+
+    def residual(self, l, u, rhs) -> np.ndarray:
+        u, rhs = np.ascontiguousarray(u, F64), np.ascontiguousarray(rhs, F64)
+        res = np.zeros_like(u)
+        lib().sref_residual(self._h, l, _p(u), _p(rhs), _p(res))
+        return res
+
+    def smooth(self, l, smoother: str, iters: int, u, rhs) -> np.ndarray:
+        u = np.array(u, F64, copy=True)
+        rhs = np.ascontiguousarray(rhs, F64)
+        lib().sref_smooth(self._h, l, int(smoother == "chebyshev"), int(iters), _p(u), _p(rhs))
+        return u
+
+    def dot(self, a, b) -> float:
+        a, b = np.ascontiguousarray(a, F64), np.ascontiguousarray(b, F64)
+        return float(lib().sref_dot(self._h, _p(a), _p(b), len(a)))
+
+    def vcycle(self, l, u, rhs, pre=3, post=3, smoother="chebyshev") -> np.ndarray:
+        u = np.array(u, F64, copy=True)
+        rhs = np.array(rhs, F64, copy=True)
+        lib().sref_vcycle(self._h, l, pre, post, int(smoother == "chebyshev"), _p(u), _p(rhs))
+        return u
+
+    def coarsest_solve(self, rhs) -> np.ndarray:
+        rhs = np.array(rhs, F64, copy=True)
+        u = np.zeros_like(rhs)
+        lib().sref_coarsest_solve(self._h, _p(u), _p(rhs))
+        return u
+
+    def solve_pcg(self, max_iter=None, tol=None, smoother=None, pre=None, post=None):
+        """-> (u, iterations as reported by the reference (i+1), residual-norm history)"""
+        o = self.opts
+        max_iter = o.max_iter if max_iter is None else max_iter
+        tol = o.tol if tol is None else tol
+        smoother = o.smoother if smoother is None else smoother
+        pre = o.pre if pre is None else pre
+        post = o.post if post is None else post
+        u = np.zeros(self._info(0, KIND_A).M, F64)
+        hist = np.zeros(max_iter + 2, F64)
+        n = ctypes.c_int(0)
+        lib().sref_solve_pcg(self._h, int(max_iter), ctypes.c_double(tol), int(smoother == "chebyshev"), int(pre),
+                             int(post), _p(u), _p(hist), len(hist), ctypes.byref(n), 1)
+        hist = hist[:n.value]
+        # the loop leaves with i == number of completed iterations - 1 on a break, and the
+        # reference reports i+1 (saena_object_solve.cpp:2678-2682)
+        return u, len(hist) - 1, hist
+
+    def time_solve_pcg(self, reps: int) -> float:
+        return float(lib().sref_time_solve_pcg(self._h, int(reps)))
