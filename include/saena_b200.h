@@ -1,0 +1,153 @@
+/*
+ * saena_b200.h -- C ABI of the B200-native AMG solve phase (the drop-in boundary).
+ *
+ * The reference (paralab/Saena) has no FFI layer: its boundary is the C++ pImpl
+ * API of include/saena.hpp whose solve methods forward into saena_object
+ * (/root/reference/src/saena.cpp:745-799).  This header is what a replacement
+ * of those forwarders binds (see INTEGRATION.md for the adaptor): the finished
+ * hierarchy that saena_object::setup left in `grids` is uploaded once, then
+ * solve_pCG / solve / the per-operator hooks run on the GPU.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no C++/torch types.  Host pointers unless a
+ *    parameter is named *_dev.
+ *  - every function returns 0 on success, non-zero on failure and never calls
+ *    exit(); saena_b200_last_error() gives the message.  (The reference's
+ *    convention is print-and-terminate; the adaptor maps
+ *    non-zero to that.)
+ *  - one context per process/GPU (= one MPI rank of the reference).  With
+ *    nranks > 1 all calls that touch a distributed level are collective and
+ *    must be made in the same order on every rank (as the reference's are).
+ *  - FP64 values, int32 row/column indices (Saena's value_t / index_t,
+ *    include/data_struct.h:36-38); nnz counts are 64-bit (nnz_t).
+ *  - there is no CPU fallback: if no CUDA device is usable, init fails.
+ */
+#ifndef SAENA_B200_H
+#define SAENA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct saena_b200_ctx saena_b200_ctx;
+
+#define SAENA_B200_NCCL_ID_BYTES 128
+
+enum { SAENA_B200_KIND_A = 0, SAENA_B200_KIND_P = 1, SAENA_B200_KIND_R = 2 };
+enum { SAENA_B200_JACOBI = 0, SAENA_B200_CHEBYSHEV = 1 };
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+
+/* Rank 0 creates the NCCL id and shares the 128 bytes with the other ranks by any means (the
+ * reference's ranks share MPI_COMM_WORLD, experiments/Poisson.cpp:18-22). */
+int saena_b200_nccl_unique_id(void *id_out);
+
+/* nccl_id may be NULL when nranks == 1 (no communicator is created). */
+int saena_b200_init(saena_b200_ctx **ctx_out, int device_id, int rank, int nranks, const void *nccl_id);
+int saena_b200_destroy(saena_b200_ctx *ctx);
+const char *saena_b200_last_error(const saena_b200_ctx *ctx); /* ctx may be NULL: error of a failed init */
+
+/* ---- hierarchy upload (once per setup) ---------------------------------------------------
+ * The descriptor carries the arrays of one operator exactly as the reference's setup built
+ * them: saena_matrix::set_off_on_diagonal (src/saena_matrix_setup.cpp:793-1098),
+ * prolong_matrix::findLocalRemote (src/prolong_matrix.cpp:18-378),
+ * restrict_matrix::transposeP (src/restrict_matrix.cpp:229-494); field names are the
+ * reference's member names (include/saena_matrix.h:105-149).                              */
+typedef struct saena_b200_operator_desc {
+    int32_t kind;                    /* SAENA_B200_KIND_* */
+    int32_t level;                   /* grids[level] */
+    int32_t M;                       /* local rows */
+    int32_t n_local_cols;            /* length of the local input vector */
+    int32_t col_offset;              /* split[rank] of the column partition: kernels index v - col_offset */
+    int32_t use_double;              /* 0: ghost values travel as float (matvec_sparse_float) */
+    int64_t nnz_local;
+    const int32_t *nnzPerRow_local;  /* [M] */
+    const int32_t *col_local;        /* [nnz_local] GLOBAL ids, row-major */
+    const double *val_local;         /* [nnz_local] */
+    int64_t nnz_remote;
+    int32_t col_remote_size;         /* == recvSize */
+    const int32_t *row_remote;       /* [nnz_remote] local row, column-major grouped by owner */
+    const double *val_remote;        /* [nnz_remote] */
+    const int32_t *nnzPerCol_remote; /* [col_remote_size] */
+    int32_t vIndexSize;
+    const int32_t *vIndex;           /* [vIndexSize] local ids whose values are sent */
+    int32_t numSendProc;
+    const int32_t *sendProcRank;     /* [numSendProc] */
+    const int32_t *sendProcCount;    /* [numSendProc] */
+    const int32_t *vdispls;          /* [nranks] start of each receiver's slice in the send buffer */
+    int32_t numRecvProc;
+    const int32_t *recvProcRank;     /* [numRecvProc] */
+    const int32_t *recvProcCount;    /* [numRecvProc] */
+    const int32_t *rdispls;          /* [nranks] start of each sender's slice in the ghost buffer */
+} saena_b200_operator_desc;
+
+int saena_b200_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *desc);
+
+/* (peer, offset, count) of Grid::repart_u's plan (src/grid.cpp:3-163): offset is into the
+ * old-partition vector for sends and into the new-partition vector for receives. */
+typedef struct saena_b200_block {
+    int32_t peer, offset, count;
+} saena_b200_block;
+
+/* Per-level data next to A_l: inv_diag and eig_max_of_invdiagXA (saena_matrix.h:151,183) and
+ * the plan that moves R's output (Ac.M_old entries) onto the coarse grid's partition (Ac.M). */
+int saena_b200_upload_level_aux(saena_b200_ctx *ctx, int level, const double *inv_diag, double eig_max,
+                                int M_coarse_old, int M_coarse, int n_send, const saena_b200_block *send,
+                                int n_recv, const saena_b200_block *recv);
+
+/* Coarsest operator as global COO (what setup_SuperLU passes on, saena_object_solve.cpp:282-308).
+ * It is LU-factored on the host once and kept on the device as a dense factor; the rank that
+ * owns the coarsest level's rows applies it (the others pass n = 0). */
+int saena_b200_upload_coarsest(saena_b200_ctx *ctx, int n, int64_t nnz, const int32_t *row, const int32_t *col,
+                               const double *val);
+
+/* Seal the hierarchy: allocates the per-level work vectors (Grid::allocate_mem, grid.cpp:165-172)
+ * and picks each operator's kernel mapping from its nnz/row. */
+int saena_b200_finalize(saena_b200_ctx *ctx);
+
+/* ---- solvers -----------------------------------------------------------------------------
+ * rhs / u are this rank's block (grids[0].A->M entries).  u is overwritten (zero initial
+ * guess, as the reference does: saena_object_solve.cpp:2482).  `iters` receives the count
+ * the reference prints ("stopped at iteration", i+1).  hist[0] = ||r0||, hist[k] = ||r_k||.  */
+int saena_b200_solve_pcg(saena_b200_ctx *ctx, const double *rhs, double *u, int max_iter, double tol,
+                         int smoother, int pre, int post, int *iters, double *hist, int hist_cap,
+                         int *hist_len);                                      /* saena_object::solve_pCG */
+int saena_b200_solve_vcycle(saena_b200_ctx *ctx, const double *rhs, double *u, int max_iter, double tol,
+                            int smoother, int pre, int post, int *iters, double *hist, int hist_cap,
+                            int *hist_len);                                   /* saena_object::solve */
+int saena_b200_solve_cg(saena_b200_ctx *ctx, const double *rhs, double *u, int max_iter, double tol, int *iters,
+                        double *hist, int hist_cap, int *hist_len);           /* saena_object::solve_CG */
+
+/* Same solve with rhs / u already resident in device memory (no host copies). */
+int saena_b200_solve_pcg_dev(saena_b200_ctx *ctx, const double *rhs_dev, double *u_dev, int max_iter, double tol,
+                             int smoother, int pre, int post, int *iters, double *hist, int hist_cap,
+                             int *hist_len);
+
+/* ---- per-operator hooks (saena::matrix::matvec and the parity tests) --------------------- */
+int saena_b200_matvec(saena_b200_ctx *ctx, int level, int kind, const double *v, double *w);
+int saena_b200_residual(saena_b200_ctx *ctx, int level, const double *u, const double *rhs, double *res);
+int saena_b200_smooth(saena_b200_ctx *ctx, int level, int smoother, int iters, double *u, const double *rhs);
+int saena_b200_vcycle(saena_b200_ctx *ctx, int level, int smoother, int pre, int post, double *u,
+                      const double *rhs);
+int saena_b200_coarsest_solve(saena_b200_ctx *ctx, const double *rhs, double *u);
+int saena_b200_dot(saena_b200_ctx *ctx, const double *a, const double *b, int n, double *out);
+
+/* ---- measurement ---------------------------------------------------------------------------
+ * Device-resident timing loops for bench.py: `reps` applications of one operator / smoother
+ * sweep with CUDA events on the launching stream; returns average milliseconds per launch. */
+int saena_b200_time_matvec(saena_b200_ctx *ctx, int level, int kind, int reps, int flush_l2, float *ms_out);
+int saena_b200_time_smooth_sweep(saena_b200_ctx *ctx, int level, int smoother, int reps, int flush_l2,
+                                 float *ms_out);
+/* kernels launched by this context since init (bench.py's gpu_launches) */
+int64_t saena_b200_launch_count(const saena_b200_ctx *ctx);
+/* 0: heuristic; >0: force the lanes-per-row of one operator's SpMV mapping (tuning/profiling) */
+int saena_b200_set_mapping(saena_b200_ctx *ctx, int level, int kind, int mapping);
+/* algorithmic bytes of one application of an operator (SURVEY.md 8d formula), for the roofline */
+int64_t saena_b200_operator_bytes(const saena_b200_ctx *ctx, int level, int kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,599 @@
+// api.cu -- the extern "C" entry points declared in include/saena_b200.h.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.h"
+
+thread_local std::string g_sb_init_error;
+int sb_prepare_operator(saena_b200_ctx *ctx, DevOperator &op);
+
+extern "C" {
+
+const char *saena_b200_last_error(const saena_b200_ctx *ctx) {
+    return ctx ? ctx->error.c_str() : g_sb_init_error.c_str();
+}
+
+int saena_b200_nccl_unique_id(void *id_out) { return sb_nccl_unique_id(id_out, g_sb_init_error); }
+
+static int init_body(saena_b200_ctx *ctx, const void *nccl_id) {
+    int ndev = 0;
+    SB_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) SB_FAIL("no CUDA device: this library has no CPU path");
+    if (ctx->device < 0 || ctx->device >= ndev) SB_FAIL("init: device_id out of range");
+    SB_CUDA(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    SB_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->sm_count = prop.multiProcessorCount;
+    SB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    SB_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    SB_CUDA(cudaEventCreateWithFlags(&ctx->ev_packed, cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreate(&ctx->ev_t0));
+    SB_CUDA(cudaEventCreate(&ctx->ev_t1));
+    SB_CUDA(cudaMalloc((void **)&ctx->red_partials, sizeof(double) * RED_MAX_BLOCKS * 4));
+    SB_CUDA(cudaMalloc((void **)&ctx->red_counter, sizeof(unsigned int)));
+    SB_CUDA(cudaMemset(ctx->red_counter, 0, sizeof(unsigned int)));
+    SB_CUDA(cudaMalloc((void **)&ctx->scalars, sizeof(double) * S_COUNT));
+    SB_CUDA(cudaMemset(ctx->scalars, 0, sizeof(double) * S_COUNT));
+    SB_CUDA(cudaMallocHost((void **)&ctx->scalars_host, sizeof(double) * S_COUNT));
+    SB_TRY(sb_nccl_init(ctx, nccl_id));
+    return 0;
+}
+
+int saena_b200_init(saena_b200_ctx **ctx_out, int device_id, int rank, int nranks, const void *nccl_id) {
+    *ctx_out = nullptr;
+    if (nranks < 1 || rank < 0 || rank >= nranks) {
+        g_sb_init_error = "init: bad rank / nranks";
+        return 1;
+    }
+    saena_b200_ctx *ctx = new saena_b200_ctx();
+    ctx->device = device_id;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    if (init_body(ctx, nccl_id)) {
+        g_sb_init_error = ctx->error;
+        delete ctx;
+        return 1;
+    }
+    *ctx_out = ctx;
+    return 0;
+}
+
+static void free_level_work(DevLevel &lv, bool owns_rhs) {
+    cudaFree(lv.u[0]); cudaFree(lv.u[1]); cudaFree(lv.d); cudaFree(lv.res); cudaFree(lv.xfer_old);
+    if (owns_rhs) cudaFree(lv.rhs);
+    lv.u[0] = lv.u[1] = lv.d = lv.res = lv.xfer_old = lv.rhs = nullptr;
+}
+
+int saena_b200_destroy(saena_b200_ctx *ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->comm_stream);
+    for (size_t l = 0; l < ctx->levels.size(); ++l) {
+        DevLevel &lv = ctx->levels[l];
+        sb_free_operator(lv.A); sb_free_operator(lv.P); sb_free_operator(lv.R);
+        cudaFree(lv.inv_diag);
+        free_level_work(lv, l > 0);
+    }
+    cudaFree(ctx->coarse_A); cudaFree(ctx->coarse_Ainv); cudaFree(ctx->coarse_tmp);
+    cudaFree(ctx->red_partials); cudaFree(ctx->red_counter); cudaFree(ctx->scalars);
+    cudaFreeHost(ctx->scalars_host);
+    cudaFree(ctx->pcg_r); cudaFree(ctx->pcg_p); cudaFree(ctx->pcg_h); cudaFree(ctx->pcg_u); cudaFree(ctx->pcg_rhs);
+    for (int i = 0; i < 4; ++i) cudaFree(ctx->stage[i]);
+    cudaFree(ctx->flush_buf);
+    sb_nccl_destroy(ctx);
+    cudaEventDestroy(ctx->ev_packed); cudaEventDestroy(ctx->ev_halo);
+    cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->comm_stream);
+    delete ctx;
+    return 0;
+}
+
+int saena_b200_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *desc) {
+    if (!ctx || !desc) return 1;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    return sb_upload_operator(ctx, desc);
+}
+
+int saena_b200_upload_level_aux(saena_b200_ctx *ctx, int level, const double *inv_diag, double eig_max,
+                                int M_coarse_old, int M_coarse, int n_send, const saena_b200_block *send,
+                                int n_recv, const saena_b200_block *recv) {
+    if (!ctx) return 1;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    if (level < 0 || level >= (int)ctx->levels.size() || !ctx->levels[level].A.present)
+        SB_FAIL("upload_level_aux: upload A of this level first");
+    DevLevel &lv = ctx->levels[level];
+    cudaFree(lv.inv_diag);
+    lv.inv_diag = nullptr;
+    SB_CUDA(cudaMalloc((void **)&lv.inv_diag, sizeof(double) * std::max(lv.M, 1)));
+    if (lv.M) SB_CUDA(cudaMemcpy(lv.inv_diag, inv_diag, sizeof(double) * lv.M, cudaMemcpyHostToDevice));
+    lv.eig_max = eig_max;
+    lv.M_coarse_old = M_coarse_old;
+    lv.M_coarse = M_coarse;
+    lv.repart.send.assign(send, send + n_send);
+    lv.repart.recv.assign(recv, recv + n_recv);
+    for (const auto &b : lv.repart.send)
+        if (b.peer < 0 || b.peer >= ctx->nranks || b.offset < 0 || b.offset + b.count > M_coarse_old)
+            SB_FAIL("upload_level_aux: send block out of range");
+    for (const auto &b : lv.repart.recv)
+        if (b.peer < 0 || b.peer >= ctx->nranks || b.offset < 0 || b.offset + b.count > M_coarse)
+            SB_FAIL("upload_level_aux: recv block out of range");
+    lv.aux_set = true;
+    ctx->finalized = false;
+    return 0;
+}
+
+// Dense LU with partial pivoting on the host, then the explicit inverse; the device applies
+// Ainv with one refinement step against A (vector_ops.cu).  Stands in for SuperLU_DIST's
+// factor + pdgssvx solve (saena_object_solve.cpp:117-419, :793-958).
+int saena_b200_upload_coarsest(saena_b200_ctx *ctx, int n, int64_t nnz, const int32_t *row, const int32_t *col,
+                               const double *val) {
+    if (!ctx) return 1;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    cudaFree(ctx->coarse_A); cudaFree(ctx->coarse_Ainv); cudaFree(ctx->coarse_tmp);
+    ctx->coarse_A = ctx->coarse_Ainv = ctx->coarse_tmp = nullptr;
+    ctx->coarse_n = n;
+    if (n == 0) return 0;
+    if (n < 0 || n > 4096) SB_FAIL("upload_coarsest: coarsest level must have 1..4096 rows");
+    std::vector<double> A((size_t)n * n, 0.0);
+    for (int64_t k = 0; k < nnz; ++k) {
+        if (row[k] < 0 || row[k] >= n || col[k] < 0 || col[k] >= n) SB_FAIL("upload_coarsest: index out of range");
+        A[(size_t)row[k] * n + col[k]] += val[k];
+    }
+    std::vector<double> LU(A), inv((size_t)n * n, 0.0);
+    std::vector<int> piv(n);
+    for (int k = 0; k < n; ++k) {
+        int p = k;
+        double best = fabs(LU[(size_t)k * n + k]);
+        for (int i = k + 1; i < n; ++i)
+            if (fabs(LU[(size_t)i * n + k]) > best) { best = fabs(LU[(size_t)i * n + k]); p = i; }
+        if (best == 0.0) SB_FAIL("upload_coarsest: coarsest operator is singular");
+        piv[k] = p;
+        if (p != k)
+            for (int j = 0; j < n; ++j) std::swap(LU[(size_t)k * n + j], LU[(size_t)p * n + j]);
+        const double dkk = LU[(size_t)k * n + k];
+        for (int i = k + 1; i < n; ++i) {
+            const double lik = LU[(size_t)i * n + k] / dkk;
+            LU[(size_t)i * n + k] = lik;
+            if (lik != 0.0)
+                for (int j = k + 1; j < n; ++j) LU[(size_t)i * n + j] -= lik * LU[(size_t)k * n + j];
+        }
+    }
+    std::vector<double> c(n);
+    for (int e = 0; e < n; ++e) {  // column e of the inverse
+        std::fill(c.begin(), c.end(), 0.0);
+        c[e] = 1.0;
+        for (int k = 0; k < n; ++k)
+            if (piv[k] != k) std::swap(c[k], c[piv[k]]);
+        for (int i = 0; i < n; ++i) {
+            double s = c[i];
+            for (int j = 0; j < i; ++j) s -= LU[(size_t)i * n + j] * c[j];
+            c[i] = s;
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double s = c[i];
+            for (int j = i + 1; j < n; ++j) s -= LU[(size_t)i * n + j] * c[j];
+            c[i] = s / LU[(size_t)i * n + i];
+        }
+        for (int i = 0; i < n; ++i) inv[(size_t)i * n + e] = c[i];
+    }
+    SB_CUDA(cudaMalloc((void **)&ctx->coarse_A, sizeof(double) * n * n));
+    SB_CUDA(cudaMalloc((void **)&ctx->coarse_Ainv, sizeof(double) * n * n));
+    SB_CUDA(cudaMalloc((void **)&ctx->coarse_tmp, sizeof(double) * 2 * n));
+    SB_CUDA(cudaMemcpy(ctx->coarse_A, A.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(ctx->coarse_Ainv, inv.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int alloc_d(saena_b200_ctx *ctx, double **p, size_t n) {
+    *p = nullptr;
+    SB_CUDA(cudaMalloc((void **)p, sizeof(double) * std::max<size_t>(n, 1)));
+    SB_CUDA(cudaMemset(*p, 0, sizeof(double) * std::max<size_t>(n, 1)));
+    return 0;
+}
+
+int saena_b200_finalize(saena_b200_ctx *ctx) {
+    if (!ctx) return 1;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    const int L = (int)ctx->levels.size();
+    if (L == 0) SB_FAIL("finalize: no level uploaded");
+    for (int l = 0; l < L; ++l) {
+        DevLevel &lv = ctx->levels[l];
+        if (!lv.A.present) SB_FAIL("finalize: a level has no A");
+        if (!lv.aux_set) SB_FAIL("finalize: upload_level_aux missing for a level");
+        if (l < L - 1) {
+            if (!lv.P.present || !lv.R.present) SB_FAIL("finalize: P/R missing on a non-coarsest level");
+            DevLevel &cl = ctx->levels[l + 1];
+            if (lv.P.M != lv.M || lv.R.n_local_cols != lv.M) SB_FAIL("finalize: P rows / R columns != A rows");
+            if (lv.R.M != lv.M_coarse_old || lv.P.n_local_cols != lv.M_coarse_old)
+                SB_FAIL("finalize: R rows / P columns != M_coarse_old");
+            if (cl.M != lv.M_coarse) SB_FAIL("finalize: coarse A rows != M_coarse");
+            if (lv.repart.identity() && lv.M_coarse_old != lv.M_coarse)
+                SB_FAIL("finalize: partitions differ but no repartition plan was given");
+        }
+        free_level_work(lv, l > 0);
+        SB_TRY(alloc_d(ctx, &lv.u[0], lv.M));
+        SB_TRY(alloc_d(ctx, &lv.u[1], lv.M));
+        SB_TRY(alloc_d(ctx, &lv.d, lv.M));
+        SB_TRY(alloc_d(ctx, &lv.res, lv.M));
+        if (l > 0) SB_TRY(alloc_d(ctx, &lv.rhs, lv.M));
+        if (l < L - 1 && !lv.repart.identity()) SB_TRY(alloc_d(ctx, &lv.xfer_old, lv.M_coarse_old));
+        lv.cur = 0;
+        SB_TRY(sb_prepare_operator(ctx, lv.A));
+        SB_TRY(sb_prepare_operator(ctx, lv.P));
+        SB_TRY(sb_prepare_operator(ctx, lv.R));
+    }
+    if (ctx->levels[L - 1].M > 0 && ctx->coarse_n != ctx->levels[L - 1].M && L > 0) {
+        // the rank that owns the coarsest rows must hold the whole coarsest operator
+        SB_FAIL("finalize: coarsest factor missing or its size differs from the coarsest level's rows");
+    }
+    const int n0 = ctx->levels[0].M;
+    cudaFree(ctx->pcg_r); cudaFree(ctx->pcg_p); cudaFree(ctx->pcg_h); cudaFree(ctx->pcg_u); cudaFree(ctx->pcg_rhs);
+    SB_TRY(alloc_d(ctx, &ctx->pcg_r, n0));
+    SB_TRY(alloc_d(ctx, &ctx->pcg_p, n0));
+    SB_TRY(alloc_d(ctx, &ctx->pcg_h, n0));
+    SB_TRY(alloc_d(ctx, &ctx->pcg_u, n0));
+    SB_TRY(alloc_d(ctx, &ctx->pcg_rhs, n0));
+    ctx->pcg_cap = n0;
+    ctx->finalized = true;
+    return 0;
+}
+
+#define SB_ENTER()                                                        \
+    if (!ctx) return 1;                                                   \
+    SB_CUDA(cudaSetDevice(ctx->device));                                  \
+    if (!ctx->finalized) SB_FAIL("call saena_b200_finalize first")
+
+static int stage_buf(saena_b200_ctx *ctx, int i, size_t n) {
+    if (ctx->stage_cap[i] < n) {
+        cudaFree(ctx->stage[i]);
+        ctx->stage[i] = nullptr;
+        ctx->stage_cap[i] = 0;
+        SB_CUDA(cudaMalloc((void **)&ctx->stage[i], sizeof(double) * std::max<size_t>(n, 1)));
+        ctx->stage_cap[i] = n;
+    }
+    return 0;
+}
+static int h2d(saena_b200_ctx *ctx, double *dst, const double *src, size_t n) {
+    if (n) SB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+static int d2h(saena_b200_ctx *ctx, double *dst, const double *src, size_t n) {
+    if (n) SB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static DevOperator *get_op(saena_b200_ctx *ctx, int level, int kind) {
+    if (level < 0 || level >= (int)ctx->levels.size()) return nullptr;
+    DevLevel &lv = ctx->levels[level];
+    DevOperator *op = kind == SAENA_B200_KIND_A ? &lv.A : (kind == SAENA_B200_KIND_P ? &lv.P : &lv.R);
+    return op->present ? op : nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Krylov drivers (device-resident vectors; one host read of <r,r> per iteration for the stop test)
+// ---------------------------------------------------------------------------------------------
+static void push_hist(double v, double *hist, int cap, int &n) {
+    if (hist && n < cap) hist[n] = sqrt(v);
+    ++n;
+}
+
+static int pcg_device(saena_b200_ctx *ctx, const double *rhs, double *u, int max_iter, double tol, int smoother,
+                      int pre, int post, int *iters, double *hist, int hist_cap, int *hist_len) {
+    DevLevel &l0 = ctx->levels[0];
+    const int n = l0.M;
+    const int max_level = (int)ctx->levels.size() - 1;
+    double *r = ctx->pcg_r, *p = ctx->pcg_p, *h = ctx->pcg_h;
+    int nh = 0;
+    // u = 0 (:2482); r = A u - rhs = -rhs (:2496); init_dot = <r,r> (:2501)
+    SB_TRY(sb_fill_zero(ctx, u, n));
+    SB_TRY(sb_negate_copy(ctx, n, rhs, r));
+    SB_TRY(sb_dot(ctx, r, r, n, S_RR));
+    SB_TRY(sb_read_scalars(ctx));
+    const double init_dot = ctx->scalars_host[S_RR];
+    double current_dot = init_dot;
+    push_hist(init_dot, hist, hist_cap, nh);
+    int i = 0;
+    if (max_level == 0) {
+        // :2507-2521 direct solver only: u = A^-1 rhs
+        l0.cur = 0;
+        SB_TRY(sb_vcycle(ctx, 0, smoother, pre, post, rhs, true));
+        if (n) SB_CUDA(cudaMemcpyAsync(u, l0.u[l0.cur], sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        EpiArgs e{};
+        e.rhs = rhs;
+        e.out = r;
+        SB_TRY(sb_apply(ctx, l0.A, u, EPI_RESIDUAL, e));
+        SB_TRY(sb_dot(ctx, r, r, n, S_RR));
+        SB_TRY(sb_read_scalars(ctx));
+        push_hist(ctx->scalars_host[S_RR], hist, hist_cap, nh);
+        *iters = 1;
+        *hist_len = nh;
+        return 0;
+    }
+    // rho = 0; vcycle(rho, r) (:2535-2537); rho lives in level 0's iterate buffers
+    SB_TRY(sb_vcycle(ctx, 0, smoother, pre, post, r, true));
+    // p = rho (:2554)
+    if (n) SB_CUDA(cudaMemcpyAsync(p, l0.u[l0.cur], sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    const double THRSHLD = init_dot * tol * tol;  // :2558
+    SB_TRY(sb_dot(ctx, r, l0.u[l0.cur], n, S_RHO_RES));  // first <r,rho> (:2580)
+    for (i = 0; i < max_iter; i++) {
+        EpiArgs e{};
+        e.out = h;
+        SB_TRY(sb_apply(ctx, l0.A, p, EPI_PLAIN, e));  // h = A p (:2571)
+        SB_TRY(sb_dot(ctx, p, h, n, S_PDOTH));         // :2581
+        SB_TRY(sb_pcg_update(ctx, n, u, r, p, h));     // :2588-2603
+        SB_TRY(sb_read_scalars(ctx));
+        current_dot = ctx->scalars_host[S_RR];
+        push_hist(current_dot, hist, hist_cap, nh);
+        if (!(current_dot >= THRSHLD)) break;          // :2620 (NaN also stops)
+        SB_TRY(sb_vcycle(ctx, 0, smoother, pre, post, r, true));  // :2640-2641
+        SB_TRY(sb_dot(ctx, r, l0.u[l0.cur], n, S_BETA_NUM));      // :2655
+        SB_TRY(sb_pcg_p_update(ctx, n, p, l0.u[l0.cur]));          // :2662-2667
+    }
+    if (i == max_iter) i--;  // :2673-2674
+    *iters = i + 1;          // :2678-2682
+    *hist_len = nh;
+    (void)current_dot;
+    return 0;
+}
+
+int saena_b200_solve_pcg_dev(saena_b200_ctx *ctx, const double *rhs_dev, double *u_dev, int max_iter, double tol,
+                             int smoother, int pre, int post, int *iters, double *hist, int hist_cap,
+                             int *hist_len) {
+    SB_ENTER();
+    SB_TRY(pcg_device(ctx, rhs_dev, u_dev, max_iter, tol, smoother, pre, post, iters, hist, hist_cap, hist_len));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int saena_b200_solve_pcg(saena_b200_ctx *ctx, const double *rhs, double *u, int max_iter, double tol, int smoother,
+                         int pre, int post, int *iters, double *hist, int hist_cap, int *hist_len) {
+    SB_ENTER();
+    const int n = ctx->levels[0].M;
+    SB_TRY(h2d(ctx, ctx->pcg_rhs, rhs, n));
+    SB_TRY(pcg_device(ctx, ctx->pcg_rhs, ctx->pcg_u, max_iter, tol, smoother, pre, post, iters, hist, hist_cap,
+                      hist_len));
+    SB_TRY(d2h(ctx, u, ctx->pcg_u, n));
+    return 0;
+}
+
+int saena_b200_solve_vcycle(saena_b200_ctx *ctx, const double *rhs, double *u, int max_iter, double tol,
+                            int smoother, int pre, int post, int *iters, double *hist, int hist_cap,
+                            int *hist_len) {
+    SB_ENTER();
+    DevLevel &l0 = ctx->levels[0];
+    const int n = l0.M;
+    double *r = ctx->pcg_r;
+    int nh = 0;
+    SB_TRY(h2d(ctx, ctx->pcg_rhs, rhs, n));
+    const double *b = ctx->pcg_rhs;
+    l0.cur = 0;
+    SB_TRY(sb_fill_zero(ctx, l0.u[0], n));
+    SB_TRY(sb_negate_copy(ctx, n, b, r));
+    SB_TRY(sb_dot(ctx, r, r, n, S_RR));
+    SB_TRY(sb_read_scalars(ctx));
+    const double init_dot = ctx->scalars_host[S_RR];
+    push_hist(init_dot, hist, hist_cap, nh);
+    const double THRSHLD = init_dot * tol * tol;
+    int i = 0;
+    for (; i < max_iter; ++i) {
+        SB_TRY(sb_vcycle(ctx, 0, smoother, pre, post, b, i == 0));  // u carries over between cycles
+        EpiArgs e{};
+        e.rhs = b;
+        e.out = r;
+        SB_TRY(sb_apply(ctx, l0.A, l0.u[l0.cur], EPI_RESIDUAL, e));
+        SB_TRY(sb_dot(ctx, r, r, n, S_RR));
+        SB_TRY(sb_read_scalars(ctx));
+        push_hist(ctx->scalars_host[S_RR], hist, hist_cap, nh);
+        if (!(ctx->scalars_host[S_RR] >= THRSHLD)) break;
+    }
+    if (i == max_iter) --i;
+    *iters = i + 1;
+    *hist_len = nh;
+    SB_TRY(d2h(ctx, u, l0.u[l0.cur], n));
+    return 0;
+}
+
+// Unpreconditioned CG (saena_object_solve.cpp:2119-2386, sign convention r = A u - rhs,
+// u -= alpha p).  The reference's pointer aliasing bug at :2311 is not replicated.
+int saena_b200_solve_cg(saena_b200_ctx *ctx, const double *rhs, double *u, int max_iter, double tol, int *iters,
+                        double *hist, int hist_cap, int *hist_len) {
+    SB_ENTER();
+    DevLevel &l0 = ctx->levels[0];
+    const int n = l0.M;
+    double *r = ctx->pcg_r, *p = ctx->pcg_p, *h = ctx->pcg_h, *x = ctx->pcg_u;
+    int nh = 0;
+    SB_TRY(h2d(ctx, ctx->pcg_rhs, rhs, n));
+    SB_TRY(sb_fill_zero(ctx, x, n));
+    SB_TRY(sb_negate_copy(ctx, n, ctx->pcg_rhs, r));
+    SB_TRY(sb_dot(ctx, r, r, n, S_RHO_RES));  // <r,r> plays rho_res
+    SB_TRY(sb_read_scalars(ctx));
+    const double init_dot = ctx->scalars_host[S_RHO_RES];
+    push_hist(init_dot, hist, hist_cap, nh);
+    if (n) SB_CUDA(cudaMemcpyAsync(p, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    const double THRSHLD = init_dot * tol * tol;
+    int i = 0;
+    for (; i < max_iter; ++i) {
+        EpiArgs e{};
+        e.out = h;
+        SB_TRY(sb_apply(ctx, l0.A, p, EPI_PLAIN, e));
+        SB_TRY(sb_dot(ctx, p, h, n, S_PDOTH));
+        SB_TRY(sb_pcg_update(ctx, n, x, r, p, h));  // alpha = <r,r>/<p,Ap>; writes S_RR
+        SB_TRY(sb_read_scalars(ctx));
+        push_hist(ctx->scalars_host[S_RR], hist, hist_cap, nh);
+        if (!(ctx->scalars_host[S_RR] >= THRSHLD)) break;
+        SB_TRY(sb_cg_p_update(ctx, n, p, r, S_RR, S_RHO_RES));  // beta = <r,r>_new / <r,r>_old
+        SB_CUDA(cudaMemcpyAsync(ctx->scalars + S_RHO_RES, ctx->scalars + S_RR, sizeof(double),
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (i == max_iter) --i;
+    *iters = i + 1;
+    *hist_len = nh;
+    SB_TRY(d2h(ctx, u, x, n));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-operator hooks
+// ---------------------------------------------------------------------------------------------
+int saena_b200_matvec(saena_b200_ctx *ctx, int level, int kind, const double *v, double *w) {
+    SB_ENTER();
+    DevOperator *op = get_op(ctx, level, kind);
+    if (!op) SB_FAIL("matvec: no such operator");
+    SB_TRY(stage_buf(ctx, 0, op->n_local_cols));
+    SB_TRY(stage_buf(ctx, 1, op->M));
+    SB_TRY(h2d(ctx, ctx->stage[0], v, op->n_local_cols));
+    EpiArgs e{};
+    e.out = ctx->stage[1];
+    SB_TRY(sb_apply(ctx, *op, ctx->stage[0], EPI_PLAIN, e));
+    SB_TRY(d2h(ctx, w, ctx->stage[1], op->M));
+    return 0;
+}
+
+int saena_b200_residual(saena_b200_ctx *ctx, int level, const double *u, const double *rhs, double *res) {
+    SB_ENTER();
+    DevOperator *op = get_op(ctx, level, SAENA_B200_KIND_A);
+    if (!op) SB_FAIL("residual: no such level");
+    for (int i = 0; i < 3; ++i) SB_TRY(stage_buf(ctx, i, op->M));
+    SB_TRY(h2d(ctx, ctx->stage[0], u, op->M));
+    SB_TRY(h2d(ctx, ctx->stage[1], rhs, op->M));
+    EpiArgs e{};
+    e.rhs = ctx->stage[1];
+    e.out = ctx->stage[2];
+    SB_TRY(sb_apply(ctx, *op, ctx->stage[0], EPI_RESIDUAL, e));
+    SB_TRY(d2h(ctx, res, ctx->stage[2], op->M));
+    return 0;
+}
+
+int saena_b200_smooth(saena_b200_ctx *ctx, int level, int smoother, int iters, double *u, const double *rhs) {
+    SB_ENTER();
+    if (level < 0 || level >= (int)ctx->levels.size()) SB_FAIL("smooth: no such level");
+    DevLevel &lv = ctx->levels[level];
+    SB_TRY(stage_buf(ctx, 1, lv.M));
+    lv.cur = 0;
+    SB_TRY(h2d(ctx, lv.u[0], u, lv.M));
+    SB_TRY(h2d(ctx, ctx->stage[1], rhs, lv.M));
+    SB_TRY(sb_smooth(ctx, level, smoother, iters, ctx->stage[1], false));
+    SB_TRY(d2h(ctx, u, lv.u[lv.cur], lv.M));
+    return 0;
+}
+
+int saena_b200_vcycle(saena_b200_ctx *ctx, int level, int smoother, int pre, int post, double *u,
+                      const double *rhs) {
+    SB_ENTER();
+    if (level < 0 || level >= (int)ctx->levels.size()) SB_FAIL("vcycle: no such level");
+    DevLevel &lv = ctx->levels[level];
+    SB_TRY(stage_buf(ctx, 1, lv.M));
+    lv.cur = 0;
+    SB_TRY(h2d(ctx, lv.u[0], u, lv.M));
+    SB_TRY(h2d(ctx, ctx->stage[1], rhs, lv.M));
+    SB_TRY(sb_vcycle(ctx, level, smoother, pre, post, ctx->stage[1], false));
+    SB_TRY(d2h(ctx, u, lv.u[lv.cur], lv.M));
+    return 0;
+}
+
+int saena_b200_coarsest_solve(saena_b200_ctx *ctx, const double *rhs, double *u) {
+    SB_ENTER();
+    const int n = ctx->coarse_n;
+    SB_TRY(stage_buf(ctx, 0, n));
+    SB_TRY(stage_buf(ctx, 1, n));
+    SB_TRY(h2d(ctx, ctx->stage[0], rhs, n));
+    SB_TRY(sb_coarsest_apply(ctx, ctx->stage[0], ctx->stage[1]));
+    SB_TRY(d2h(ctx, u, ctx->stage[1], n));
+    return 0;
+}
+
+int saena_b200_dot(saena_b200_ctx *ctx, const double *a, const double *b, int n, double *out) {
+    SB_ENTER();
+    SB_TRY(stage_buf(ctx, 0, n));
+    SB_TRY(stage_buf(ctx, 1, n));
+    SB_TRY(h2d(ctx, ctx->stage[0], a, n));
+    SB_TRY(h2d(ctx, ctx->stage[1], b, n));
+    SB_TRY(sb_dot(ctx, ctx->stage[0], ctx->stage[1], n, S_TMP));
+    SB_TRY(sb_read_scalars(ctx));
+    *out = ctx->scalars_host[S_TMP];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// measurement
+// ---------------------------------------------------------------------------------------------
+static int flush_l2(saena_b200_ctx *ctx) {
+    const size_t bytes = (size_t)256 << 20;  // > 126 MB L2
+    if (!ctx->flush_buf) {
+        SB_CUDA(cudaMalloc(&ctx->flush_buf, bytes));
+        ctx->flush_bytes = bytes;
+    }
+    SB_CUDA(cudaMemsetAsync(ctx->flush_buf, 0, ctx->flush_bytes, ctx->stream));
+    return 0;
+}
+
+int saena_b200_time_matvec(saena_b200_ctx *ctx, int level, int kind, int reps, int do_flush, float *ms_out) {
+    SB_ENTER();
+    DevOperator *op = get_op(ctx, level, kind);
+    if (!op) SB_FAIL("time_matvec: no such operator");
+    SB_TRY(stage_buf(ctx, 0, op->n_local_cols));
+    SB_TRY(stage_buf(ctx, 1, op->M));
+    SB_CUDA(cudaMemsetAsync(ctx->stage[0], 0, sizeof(double) * op->n_local_cols, ctx->stream));
+    EpiArgs e{};
+    e.out = ctx->stage[1];
+    float total = 0.f;
+    for (int it = 0; it < reps; ++it) {
+        if (do_flush) SB_TRY(flush_l2(ctx));
+        SB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        SB_TRY(sb_apply(ctx, *op, ctx->stage[0], EPI_PLAIN, e));
+        SB_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
+        SB_CUDA(cudaEventSynchronize(ctx->ev_t1));
+        float ms = 0.f;
+        SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+        total += ms;
+    }
+    *ms_out = reps ? total / reps : 0.f;
+    return 0;
+}
+
+int saena_b200_time_smooth_sweep(saena_b200_ctx *ctx, int level, int smoother, int reps, int do_flush,
+                                 float *ms_out) {
+    SB_ENTER();
+    if (level < 0 || level >= (int)ctx->levels.size()) SB_FAIL("time_smooth_sweep: no such level");
+    DevLevel &lv = ctx->levels[level];
+    SB_TRY(stage_buf(ctx, 1, lv.M));
+    SB_CUDA(cudaMemsetAsync(ctx->stage[1], 0, sizeof(double) * lv.M, ctx->stream));
+    float total = 0.f;
+    for (int it = 0; it < reps; ++it) {
+        if (do_flush) SB_TRY(flush_l2(ctx));
+        SB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        SB_TRY(sb_smooth(ctx, level, smoother, 1, ctx->stage[1], false));
+        SB_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
+        SB_CUDA(cudaEventSynchronize(ctx->ev_t1));
+        float ms = 0.f;
+        SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+        total += ms;
+    }
+    *ms_out = reps ? total / reps : 0.f;
+    return 0;
+}
+
+int64_t saena_b200_launch_count(const saena_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int saena_b200_set_mapping(saena_b200_ctx *ctx, int level, int kind, int mapping) {
+    if (!ctx) return 1;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    DevOperator *op = get_op(ctx, level, kind);
+    if (!op) SB_FAIL("set_mapping: no such operator");
+    op->forced_mapping = mapping;
+    return sb_prepare_operator(ctx, *op);
+}
+
+int64_t saena_b200_operator_bytes(const saena_b200_ctx *ctx, int level, int kind) {
+    if (!ctx || level < 0 || level >= (int)ctx->levels.size()) return -1;
+    const DevLevel &lv = ctx->levels[level];
+    const DevOperator &op = kind == SAENA_B200_KIND_A ? lv.A : (kind == SAENA_B200_KIND_P ? lv.P : lv.R);
+    return op.present ? sb_operator_bytes(op) : -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,217 @@
+// common.h -- internal declarations shared by the .cu files of libsaena_b200.so.
+// Nothing here is part of the ABI (that is include/saena_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "saena_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: every ABI entry point returns int and records a message in the context
+// ---------------------------------------------------------------------------------------------
+struct SbError {
+    std::string msg;
+};
+extern thread_local std::string g_sb_init_error;
+
+#define SB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->error = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ +    \
+                         ":" + std::to_string(__LINE__) + ")";                                     \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+#define SB_FAIL(text)                                                                              \
+    do {                                                                                           \
+        ctx->error = std::string(text) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")";   \
+        return 1;                                                                                  \
+    } while (0)
+
+#define SB_TRY(expr)                                                                               \
+    do {                                                                                           \
+        int rc_ = (expr);                                                                          \
+        if (rc_) return rc_;                                                                       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// SpMV epilogues: what one thread does with (A x)_i.  Fusing them into the SpMV is what makes a
+// smoother sweep / residual / prolong+correct a single pass over the operator.
+// ---------------------------------------------------------------------------------------------
+enum EpiKind {
+    EPI_PLAIN = 0,       // out = Ax                                  (matvec)
+    EPI_RESIDUAL = 1,    // out = Ax - rhs                            (saena_matrix.tpp:16-23)
+    EPI_CHEB_FIRST = 2,  // d = c1*invd*(rhs-Ax); dout=d; out=u+d      (saena_matrix.cpp:1099-1109)
+    EPI_CHEB_NEXT = 3,   // d = c1*din + c2*invd*(rhs-Ax); out=u+d     (saena_matrix.cpp:1111-1130)
+    EPI_JACOBI = 4,      // out = u - (Ax-rhs)*(invd*omega)            (saena_matrix.cpp:1061-1069)
+    EPI_SUB = 5,         // out = u - Ax                               (prolong + correct, solve.cpp:1325,1360)
+    EPI_COUNT = 6
+};
+
+struct EpiArgs {
+    const double *rhs;
+    const double *inv_diag;
+    const double *d_in;
+    double *d_out;
+    const double *u_in;
+    double *out;
+    double c1, c2;
+};
+
+// ---------------------------------------------------------------------------------------------
+// device-side operator
+// ---------------------------------------------------------------------------------------------
+struct HaloPeer {
+    int peer;
+    int offset;  // element offset into the packed send / ghost buffer
+    int count;
+};
+
+struct DevOperator {
+    bool present = false;
+    int kind = 0, level = 0;
+    int M = 0, n_local_cols = 0, col_offset = 0;
+    int64_t nnz_local = 0, nnz_remote = 0;
+    bool use_double = true;
+    bool wide_offsets = false;  // 64-bit row offsets (nnz_local >= 2^31)
+
+    // local block: CSR, column ids LOCAL (global - col_offset)
+    void *rowptr = nullptr;  // int32[M+1] or int64[M+1]
+    int *col = nullptr;
+    double *val = nullptr;
+
+    // row blocks of the streaming kernel: rows [blk_row[b], blk_row[b+1]) hold <= STREAM_TILE nnz
+    int *blk_row = nullptr;
+    int n_blk = 0;
+
+    // remote block re-sorted by row at upload: boundary rows only
+    int n_brows = 0;
+    int *brow = nullptr;       // [n_brows] local row id, ascending
+    int *brow_ptr = nullptr;   // [n_brows+1]
+    int *bcol = nullptr;       // [nnz_remote] index into the ghost buffer
+    double *bval = nullptr;    // [nnz_remote]
+    uint32_t *brow_mask = nullptr;  // bit i set <=> row i has remote entries (local kernel skips its epilogue)
+
+    // halo plan
+    int vIndexSize = 0, recvSize = 0;
+    int *vIndex = nullptr;
+    void *send_buf = nullptr;  // double[vIndexSize] or float[vIndexSize]
+    void *ghost_buf = nullptr; // double[recvSize] or float[recvSize]
+    std::vector<HaloPeer> sends, recvs;
+
+    // kernel mapping: lanes per row of the SpMV (1..32), 0 = streaming kernel
+    int lanes = 0;
+    bool use_stream = false;
+    int forced_mapping = 0;
+
+    double avg_nnz_row() const { return M ? double(nnz_local + nnz_remote) / M : 0.0; }
+};
+
+struct RepartPlan {
+    std::vector<saena_b200_block> send, recv;
+    bool identity() const { return send.empty() && recv.empty(); }
+};
+
+struct DevLevel {
+    DevOperator A, P, R;
+    double *inv_diag = nullptr;
+    double eig_max = 0.0;
+    int M = 0;             // A.M
+    int M_coarse_old = 0;  // Ac.M_old
+    int M_coarse = 0;      // Ac.M
+    RepartPlan repart;
+    bool aux_set = false;
+
+    // work vectors (Grid::allocate_mem + the smoother's temp1/temp2)
+    double *u[2] = {nullptr, nullptr};  // ping-pong iterate; u[cur] is current
+    int cur = 0;
+    double *d = nullptr;         // Chebyshev direction (temp2)
+    double *res = nullptr;       // residual (Grid::res)
+    double *rhs = nullptr;       // this level's right-hand side (parent's res_coarse after repart); level 0: external
+    double *xfer_old = nullptr;  // coarse vector in the old partition (Ac.M_old), used when repart is not identity
+};
+
+struct saena_b200_ctx {
+    int device = 0, rank = 0, nranks = 1;
+    std::string error;
+    cudaStream_t stream = nullptr;  // compute
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_packed = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    void *nccl_comm = nullptr;
+    int sm_count = 148;
+    std::vector<DevLevel> levels;
+    bool finalized = false;
+    int64_t launches = 0;
+
+    // coarsest dense factor
+    int coarse_n = 0;
+    double *coarse_A = nullptr;     // [n*n] row-major
+    double *coarse_Ainv = nullptr;  // [n*n] row-major
+    double *coarse_tmp = nullptr;   // [2n]
+
+    // reductions
+    double *red_partials = nullptr;  // [RED_MAX_BLOCKS * 4]
+    unsigned int *red_counter = nullptr;
+    double *scalars = nullptr;       // device scalars of the Krylov loop
+    double *scalars_host = nullptr;  // pinned mirror
+
+    // PCG vectors (level-0 size)
+    double *pcg_r = nullptr, *pcg_p = nullptr, *pcg_h = nullptr, *pcg_u = nullptr, *pcg_rhs = nullptr;
+    int pcg_cap = 0;
+
+    // hook staging (host <-> device copies of the per-operator hooks)
+    double *stage[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t stage_cap[4] = {0, 0, 0, 0};
+
+    // L2 flush buffer for the timing loops
+    void *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+};
+
+// scalar slots
+enum { S_RHO_RES = 0, S_PDOTH = 1, S_RR = 2, S_BETA_NUM = 3, S_TMP = 4, S_COUNT = 8 };
+
+static const int STREAM_TILE = 2048;      // nnz per row block of the streaming kernel (16 KB of products)
+static const int STREAM_THREADS = 256;
+static const int RED_MAX_BLOCKS = 1184;   // 148 SMs x 8
+
+// ---- operator.cu
+int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d);
+void sb_free_operator(DevOperator &op);
+void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op);
+int sb_prepare_operator(saena_b200_ctx *ctx, DevOperator &op);
+// w-style application of an operator with a fused epilogue; x is the local input vector.
+int sb_apply(saena_b200_ctx *ctx, DevOperator &op, const double *x, int epi, const EpiArgs &args);
+int64_t sb_operator_bytes(const DevOperator &op);
+
+// ---- nccl_comm.cu
+int sb_nccl_unique_id(void *out, std::string &err);
+int sb_nccl_init(saena_b200_ctx *ctx, const void *id);
+void sb_nccl_destroy(saena_b200_ctx *ctx);
+int sb_halo_exchange(saena_b200_ctx *ctx, DevOperator &op, cudaStream_t s);
+int sb_allreduce_sum(saena_b200_ctx *ctx, double *dev_vals, int count, cudaStream_t s);
+// moves blocks of `src` to the peers' `dst`; forward: send plan -> recv plan, backward: reversed
+int sb_repart(saena_b200_ctx *ctx, const RepartPlan &plan, bool backward, const double *src, double *dst,
+              cudaStream_t s);
+
+// ---- vector_ops.cu
+int sb_dot(saena_b200_ctx *ctx, const double *a, const double *b, int n, int slot);           // scalars[slot] = <a,b> (global)
+int sb_cheb_first_zero(saena_b200_ctx *ctx, int n, const double *rhs, const double *inv_diag, double c, double *d,
+                       double *u);                                                          // u = d = c*invd*rhs
+int sb_pcg_update(saena_b200_ctx *ctx, int n, double *u, double *r, const double *p, const double *h);  // + scalars[S_RR]
+int sb_pcg_p_update(saena_b200_ctx *ctx, int n, double *p, const double *rho);
+int sb_cg_p_update(saena_b200_ctx *ctx, int n, double *p, const double *r, int num_slot, int den_slot);
+int sb_negate_copy(saena_b200_ctx *ctx, int n, const double *src, double *dst);              // dst = -src
+int sb_fill_zero(saena_b200_ctx *ctx, double *p, size_t n);
+int sb_coarsest_apply(saena_b200_ctx *ctx, const double *rhs, double *u);
+int sb_read_scalars(saena_b200_ctx *ctx);  // device scalars -> scalars_host (synchronises the stream)
+
+// ---- solve.cu
+int sb_smooth(saena_b200_ctx *ctx, int l, int smoother, int iters, const double *rhs, bool u_is_zero);
+int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const double *rhs, bool u_is_zero);

@@ -1,0 +1,311 @@
+// operator.cu -- upload of one operator in the reference layout and its application on the GPU.
+//
+// Upload contract = the arrays saena_matrix::set_off_on_diagonal leaves behind
+// (/root/reference/src/saena_matrix_setup.cpp:793-1098; same for P and R:
+// prolong_matrix.cpp:18-378, restrict_matrix.cpp:229-494).  Device layout:
+//   local block  -> CSR: rowptr (scan of nnzPerRow_local), col made LOCAL (global - col_offset,
+//                   the reference's `v_p = v - split[rank]` folded in at upload), val
+//   remote block -> re-sorted from column-major-by-sender to row-major over the boundary rows
+//                   (no atomics in the remote kernel), column = index into the ghost buffer
+//   halo plan    -> vIndex + per-peer (offset,count) slices of the packed send / ghost buffers
+#include <algorithm>
+#include <numeric>
+
+#include "spmv_kernels.cuh"
+
+template <typename T>
+static int dev_upload(saena_b200_ctx *ctx, T **dst, const T *src, size_t n) {
+    *dst = nullptr;
+    SB_CUDA(cudaMalloc((void **)dst, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) SB_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void sb_free_operator(DevOperator &op) {
+    cudaFree(op.rowptr); cudaFree(op.col); cudaFree(op.val); cudaFree(op.blk_row);
+    cudaFree(op.brow); cudaFree(op.brow_ptr); cudaFree(op.bcol); cudaFree(op.bval); cudaFree(op.brow_mask);
+    cudaFree(op.vIndex); cudaFree(op.send_buf); cudaFree(op.ghost_buf);
+    op = DevOperator();
+}
+
+int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
+    if (d->level < 0 || d->level > 64) SB_FAIL("upload_operator: level out of range");
+    if (d->kind < 0 || d->kind > 2) SB_FAIL("upload_operator: kind must be A, P or R");
+    if (d->M < 0 || d->nnz_local < 0 || d->nnz_remote < 0) SB_FAIL("upload_operator: negative size");
+    if ((int)ctx->levels.size() <= d->level) ctx->levels.resize(d->level + 1);
+    DevLevel &lv = ctx->levels[d->level];
+    DevOperator &op = d->kind == SAENA_B200_KIND_A ? lv.A : (d->kind == SAENA_B200_KIND_P ? lv.P : lv.R);
+    if (op.present) sb_free_operator(op);
+    op.present = true;
+    op.kind = d->kind;
+    op.level = d->level;
+    op.M = d->M;
+    op.n_local_cols = d->n_local_cols;
+    op.col_offset = d->col_offset;
+    op.nnz_local = d->nnz_local;
+    op.nnz_remote = d->nnz_remote;
+    op.use_double = d->use_double != 0;
+    op.wide_offsets = d->nnz_local >= (int64_t)INT32_MAX;
+    if (d->kind == SAENA_B200_KIND_A) lv.M = d->M;
+    const int M = d->M;
+
+    // ---- local block -> CSR with local column ids
+    {
+        std::vector<int64_t> rp(M + 1, 0);
+        for (int i = 0; i < M; ++i) rp[i + 1] = rp[i] + d->nnzPerRow_local[i];
+        if (rp[M] != d->nnz_local) SB_FAIL("upload_operator: sum(nnzPerRow_local) != nnz_local");
+        if (op.wide_offsets) {
+            int64_t *p = nullptr;
+            SB_TRY(dev_upload(ctx, &p, rp.data(), rp.size()));
+            op.rowptr = p;
+        } else {
+            std::vector<int> rp32(rp.begin(), rp.end());
+            int *p = nullptr;
+            SB_TRY(dev_upload(ctx, &p, rp32.data(), rp32.size()));
+            op.rowptr = p;
+        }
+        std::vector<int> lc((size_t)d->nnz_local);
+        for (int64_t k = 0; k < d->nnz_local; ++k) {
+            const int c = d->col_local[k] - d->col_offset;
+            if (c < 0 || c >= d->n_local_cols) SB_FAIL("upload_operator: col_local outside this rank's column block");
+            lc[k] = c;
+        }
+        SB_TRY(dev_upload(ctx, &op.col, lc.data(), lc.size()));
+        SB_TRY(dev_upload(ctx, &op.val, d->val_local, (size_t)d->nnz_local));
+
+        // row blocks of the streaming kernel (LPR is fixed later; blocks are cut for the largest
+        // row count a CTA can take, STREAM_THREADS, and re-cut in sb_choose_mapping if LPR > 1)
+    }
+
+    // ---- remote block: column-major by sender -> row-major over boundary rows
+    op.recvSize = d->col_remote_size;
+    if (d->nnz_remote > 0) {
+        const int64_t nr = d->nnz_remote;
+        std::vector<int> ghost_of((size_t)nr);
+        {
+            int64_t k = 0;
+            for (int j = 0; j < d->col_remote_size; ++j)
+                for (int t = 0; t < d->nnzPerCol_remote[j]; ++t) ghost_of[k++] = j;
+            if (k != nr) SB_FAIL("upload_operator: sum(nnzPerCol_remote) != nnz_remote");
+        }
+        std::vector<int> cnt(M + 1, 0);
+        for (int64_t k = 0; k < nr; ++k) {
+            if (d->row_remote[k] < 0 || d->row_remote[k] >= M) SB_FAIL("upload_operator: row_remote out of range");
+            ++cnt[d->row_remote[k] + 1];
+        }
+        std::vector<int> brow, brow_ptr(1, 0);
+        std::vector<int> pos(M, -1);
+        for (int i = 0; i < M; ++i)
+            if (cnt[i + 1]) {
+                pos[i] = (int)brow.size();
+                brow.push_back(i);
+                brow_ptr.push_back(brow_ptr.back() + cnt[i + 1]);
+            }
+        std::vector<int> fill(brow_ptr.begin(), brow_ptr.end() - 1);
+        std::vector<int> bcol((size_t)nr);
+        std::vector<double> bval((size_t)nr);
+        for (int64_t k = 0; k < nr; ++k) {  // stable: ghost index ascending inside a row
+            const int b = pos[d->row_remote[k]];
+            bcol[fill[b]] = ghost_of[k];
+            bval[fill[b]] = d->val_remote[k];
+            ++fill[b];
+        }
+        std::vector<uint32_t> mask((size_t)(M + 31) / 32, 0u);
+        for (int r : brow) mask[r >> 5] |= 1u << (r & 31);
+        op.n_brows = (int)brow.size();
+        SB_TRY(dev_upload(ctx, &op.brow, brow.data(), brow.size()));
+        SB_TRY(dev_upload(ctx, &op.brow_ptr, brow_ptr.data(), brow_ptr.size()));
+        SB_TRY(dev_upload(ctx, &op.bcol, bcol.data(), bcol.size()));
+        SB_TRY(dev_upload(ctx, &op.bval, bval.data(), bval.size()));
+        SB_TRY(dev_upload(ctx, &op.brow_mask, mask.data(), mask.size()));
+    }
+
+    // ---- halo plan
+    op.vIndexSize = d->vIndexSize;
+    if (d->vIndexSize > 0) {
+        for (int i = 0; i < d->vIndexSize; ++i)
+            if (d->vIndex[i] < 0 || d->vIndex[i] >= d->n_local_cols) SB_FAIL("upload_operator: vIndex out of range");
+        SB_TRY(dev_upload(ctx, &op.vIndex, d->vIndex, (size_t)d->vIndexSize));
+    }
+    const size_t esz = op.use_double ? sizeof(double) : sizeof(float);
+    if (op.vIndexSize) SB_CUDA(cudaMalloc(&op.send_buf, (size_t)op.vIndexSize * esz));
+    if (op.recvSize) SB_CUDA(cudaMalloc(&op.ghost_buf, (size_t)op.recvSize * esz));
+    for (int i = 0; i < d->numSendProc; ++i) {
+        const int p = d->sendProcRank[i];
+        if (p < 0 || p >= ctx->nranks) SB_FAIL("upload_operator: sendProcRank out of range");
+        op.sends.push_back({p, d->vdispls[p], d->sendProcCount[i]});
+    }
+    for (int i = 0; i < d->numRecvProc; ++i) {
+        const int p = d->recvProcRank[i];
+        if (p < 0 || p >= ctx->nranks) SB_FAIL("upload_operator: recvProcRank out of range");
+        op.recvs.push_back({p, d->rdispls[p], d->recvProcCount[i]});
+    }
+    if ((!op.sends.empty() || !op.recvs.empty()) && ctx->nranks == 1)
+        SB_FAIL("upload_operator: halo plan given but the context has one rank");
+    ctx->finalized = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mapping heuristic: lanes per row from nnz/row; short rows stream.  (north_star: "warp-per-row
+// or row-block mapping chosen per level by nnz/row".)  Measured crossovers are in DESIGN.md.
+// ---------------------------------------------------------------------------------------------
+static int pow2_at_most(double v) {
+    int p = 1;
+    while (p * 2 <= v && p < 32) p *= 2;
+    return p;
+}
+
+void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op) {
+    (void)ctx;
+    const double avg = op.M ? double(op.nnz_local) / op.M : 0.0;
+    int m = op.forced_mapping;
+    if (m == 0) {
+        // default: stream rows shorter than 16, sub-warp per row above
+        if (avg < 16.0) m = -1;
+        else m = pow2_at_most(avg / 4.0);  // ~4+ elements per lane
+    }
+    if (m < 0) {
+        op.use_stream = true;
+        op.lanes = std::min(32, std::max(1, -m == 1 ? 1 : pow2_at_most(-m)));
+    } else {
+        op.use_stream = false;
+        op.lanes = std::min(32, std::max(1, pow2_at_most(m)));
+    }
+}
+
+// rows [blk_row[b], blk_row[b+1]) : at most `rows_per_block` rows and STREAM_TILE nnz
+static int build_row_blocks(saena_b200_ctx *ctx, DevOperator &op, int rows_per_block) {
+    std::vector<int64_t> rp(op.M + 1);
+    if (op.wide_offsets) {
+        SB_CUDA(cudaMemcpy(rp.data(), op.rowptr, sizeof(int64_t) * (op.M + 1), cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<int> rp32(op.M + 1);
+        SB_CUDA(cudaMemcpy(rp32.data(), op.rowptr, sizeof(int) * (op.M + 1), cudaMemcpyDeviceToHost));
+        std::copy(rp32.begin(), rp32.end(), rp.begin());
+    }
+    std::vector<int> blk(1, 0);
+    int r = 0;
+    while (r < op.M) {
+        int e = r;
+        const int64_t base = rp[r];
+        while (e < op.M && e - r < rows_per_block && rp[e + 1] - base <= STREAM_TILE) ++e;
+        if (e == r) e = r + 1;  // one row longer than the tile: alone in its block
+        blk.push_back(e);
+        r = e;
+    }
+    cudaFree(op.blk_row);
+    op.blk_row = nullptr;
+    op.n_blk = (int)blk.size() - 1;
+    SB_TRY(dev_upload(ctx, &op.blk_row, blk.data(), blk.size()));
+    return 0;
+}
+
+int sb_prepare_operator(saena_b200_ctx *ctx, DevOperator &op) {
+    if (!op.present) return 0;
+    sb_choose_mapping(ctx, op);
+    if (op.use_stream) SB_TRY(build_row_blocks(ctx, op, STREAM_THREADS / op.lanes));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+template <int EPI, typename OffT>
+static void launch_local(saena_b200_ctx *ctx, DevOperator &op, const double *x, const EpiArgs &e) {
+    const OffT *rp = (const OffT *)op.rowptr;
+    cudaStream_t s = ctx->stream;
+    if (op.M == 0) return;
+    ++ctx->launches;
+    if (op.use_stream) {
+        switch (op.lanes) {
+#define SB_STREAM_CASE(L)                                                                          \
+    case L:                                                                                        \
+        spmv_stream_kernel<L, EPI, OffT><<<op.n_blk, STREAM_THREADS, 0, s>>>(                      \
+            op.M, rp, op.col, op.val, x, e, op.brow_mask, op.blk_row);                             \
+        break;
+            SB_STREAM_CASE(1) SB_STREAM_CASE(2) SB_STREAM_CASE(4) SB_STREAM_CASE(8)
+            SB_STREAM_CASE(16) SB_STREAM_CASE(32)
+#undef SB_STREAM_CASE
+        }
+    } else {
+        const int blocks = (op.M + 255) / 256;  // 8 warps x 32 rows
+        switch (op.lanes) {
+#define SB_VEC_CASE(L)                                                                             \
+    case L:                                                                                        \
+        spmv_vec_kernel<L, EPI, OffT><<<blocks, 256, 0, s>>>(op.M, rp, op.col, op.val, x, e,       \
+                                                             op.brow_mask);                        \
+        break;
+            SB_VEC_CASE(1) SB_VEC_CASE(2) SB_VEC_CASE(4) SB_VEC_CASE(8) SB_VEC_CASE(16) SB_VEC_CASE(32)
+#undef SB_VEC_CASE
+        }
+    }
+}
+
+template <int EPI, typename OffT>
+static void launch_boundary(saena_b200_ctx *ctx, DevOperator &op, const double *x, const EpiArgs &e) {
+    if (op.n_brows == 0) return;
+    ++ctx->launches;
+    const int threads = 256, rows_per_block = threads / 8;
+    const int blocks = (op.n_brows + rows_per_block - 1) / rows_per_block;
+    const OffT *rp = (const OffT *)op.rowptr;
+    if (op.use_double)
+        spmv_boundary_kernel<EPI, OffT, double><<<blocks, threads, 0, ctx->stream>>>(
+            op.n_brows, op.brow, rp, op.col, op.val, op.brow_ptr, op.bcol, op.bval, x,
+            (const double *)op.ghost_buf, e);
+    else
+        spmv_boundary_kernel<EPI, OffT, float><<<blocks, threads, 0, ctx->stream>>>(
+            op.n_brows, op.brow, rp, op.col, op.val, op.brow_ptr, op.bcol, op.bval, x,
+            (const float *)op.ghost_buf, e);
+}
+
+template <int EPI>
+static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, const EpiArgs &e) {
+    const bool halo = !op.sends.empty() || !op.recvs.empty();
+    if (halo) {
+        // pack -> exchange on the comm stream, overlapped with the interior rows
+        if (op.vIndexSize) {
+            ++ctx->launches;
+            const int blocks = (op.vIndexSize + 255) / 256;
+            if (op.use_double)
+                halo_pack_kernel<double><<<blocks, 256, 0, ctx->stream>>>(op.vIndexSize, op.vIndex, x,
+                                                                          (double *)op.send_buf);
+            else
+                halo_pack_kernel<float><<<blocks, 256, 0, ctx->stream>>>(op.vIndexSize, op.vIndex, x,
+                                                                         (float *)op.send_buf);
+        }
+        SB_CUDA(cudaEventRecord(ctx->ev_packed, ctx->stream));
+        SB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
+        SB_TRY(sb_halo_exchange(ctx, op, ctx->comm_stream));
+        SB_CUDA(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
+    }
+    if (op.wide_offsets) launch_local<EPI, int64_t>(ctx, op, x, e);
+    else launch_local<EPI, int>(ctx, op, x, e);
+    if (halo) {
+        SB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+        if (op.wide_offsets) launch_boundary<EPI, int64_t>(ctx, op, x, e);
+        else launch_boundary<EPI, int>(ctx, op, x, e);
+    }
+    SB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int sb_apply(saena_b200_ctx *ctx, DevOperator &op, const double *x, int epi, const EpiArgs &args) {
+    if (!op.present) SB_FAIL("apply: operator was not uploaded");
+    switch (epi) {
+        case EPI_PLAIN: return apply_epi<EPI_PLAIN>(ctx, op, x, args);
+        case EPI_RESIDUAL: return apply_epi<EPI_RESIDUAL>(ctx, op, x, args);
+        case EPI_CHEB_FIRST: return apply_epi<EPI_CHEB_FIRST>(ctx, op, x, args);
+        case EPI_CHEB_NEXT: return apply_epi<EPI_CHEB_NEXT>(ctx, op, x, args);
+        case EPI_JACOBI: return apply_epi<EPI_JACOBI>(ctx, op, x, args);
+        case EPI_SUB: return apply_epi<EPI_SUB>(ctx, op, x, args);
+    }
+    SB_FAIL("apply: unknown epilogue");
+}
+
+// algorithmic bytes of w = Op v: nnz*(8+4) + M*p (row offsets) + N*8 (x once) + M*8 (w)
+int64_t sb_operator_bytes(const DevOperator &op) {
+    const int64_t p = op.wide_offsets ? 8 : 4;
+    return (op.nnz_local + op.nnz_remote) * 12 + (int64_t)op.M * p + (int64_t)op.n_local_cols * 8 +
+           (int64_t)op.M * 8;
+}

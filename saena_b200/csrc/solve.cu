@@ -1,0 +1,124 @@
+// solve.cu -- smoothers, V-cycle and the Krylov drivers on the uploaded hierarchy.
+//
+//   saena_object::smooth      /root/reference/include/saena_object.tpp:85-96
+//   saena_matrix::chebyshev   /root/reference/src/saena_matrix.cpp:1074-1131
+//   saena_matrix::jacobi      /root/reference/src/saena_matrix.cpp:1044-1071
+//   saena_object::vcycle      /root/reference/src/saena_object_solve.cpp:961-1431
+//   saena_object::solve_pCG   /root/reference/src/saena_object_solve.cpp:2389-2801
+//   saena_object::solve       /root/reference/src/saena_object_solve.cpp:1883-2014
+//   saena_object::solve_CG    /root/reference/src/saena_object_solve.cpp:2119-2386
+//
+// Every smoother sweep is ONE pass over A (SpMV with the update fused as epilogue); the iterate
+// ping-pongs between two buffers because a fused sweep must read the old u of other rows.  The
+// first sweep from a zero iterate (every coarse-level entry and the preconditioner's rho = 0)
+// needs no pass over A at all.  Prolongation is fused with the correction u -= P e.
+#include <math.h>
+
+#include "common.h"
+
+int sb_smooth(saena_b200_ctx *ctx, int l, int smoother, int iters, const double *rhs, bool u_is_zero) {
+    DevLevel &lv = ctx->levels[l];
+    if (iters <= 0 || lv.M == 0) {
+        if (iters > 0 && (!lv.A.sends.empty() || !lv.A.recvs.empty())) SB_FAIL("smooth: empty rank with a halo plan");
+        return 0;
+    }
+    EpiArgs e{};
+    e.rhs = rhs;
+    e.inv_diag = lv.inv_diag;
+    if (smoother == SAENA_B200_JACOBI) {
+        // u -= (omega D^-1)(A u - rhs), omega = float(2.0/3) promoted (saena_matrix.h:182)
+        e.c1 = (double)(float)(2.0 / 3);
+        for (int j = 0; j < iters; ++j) {
+            e.u_in = lv.u[lv.cur];
+            e.out = lv.u[lv.cur ^ 1];
+            SB_TRY(sb_apply(ctx, lv.A, lv.u[lv.cur], EPI_JACOBI, e));
+            lv.cur ^= 1;
+        }
+        return 0;
+    }
+    if (smoother != SAENA_B200_CHEBYSHEV) SB_FAIL("smooth: unknown smoother");
+    // scalar recurrences exactly as saena_matrix.cpp:1084-1091, :1112-1116
+    const double eig = lv.eig_max;
+    const double alpha = 0.13 * eig;
+    const double beta = eig;
+    const double delta = (beta - alpha) / 2.0;
+    const double theta = (beta + alpha) / 2.0;
+    const double s1 = theta / delta;
+    const double twos1 = 2.0 * s1;
+    double rhok = 1.0 / s1;
+    e.d_in = lv.d;
+    e.d_out = lv.d;
+    // first sweep: d = (1/theta) D^-1 (rhs - A u); u += d
+    if (u_is_zero) {
+        SB_TRY(sb_cheb_first_zero(ctx, lv.M, rhs, lv.inv_diag, 1.0 / theta, lv.d, lv.u[lv.cur]));
+    } else {
+        e.c1 = 1.0 / theta;
+        e.u_in = lv.u[lv.cur];
+        e.out = lv.u[lv.cur ^ 1];
+        SB_TRY(sb_apply(ctx, lv.A, lv.u[lv.cur], EPI_CHEB_FIRST, e));
+        lv.cur ^= 1;
+    }
+    for (int i = 1; i < iters; ++i) {
+        const double rhokp1 = 1.0 / (twos1 - rhok);
+        const double two_rhokp1 = 2.0 * rhokp1;
+        const double d1 = rhokp1 * rhok;
+        const double d2 = two_rhokp1 / delta;
+        rhok = rhokp1;
+        e.c1 = d1;
+        e.c2 = d2;
+        e.u_in = lv.u[lv.cur];
+        e.out = lv.u[lv.cur ^ 1];
+        SB_TRY(sb_apply(ctx, lv.A, lv.u[lv.cur], EPI_CHEB_NEXT, e));
+        lv.cur ^= 1;
+    }
+    return 0;
+}
+
+// V-cycle on grid l with right-hand side `rhs`; the iterate is lv.u[lv.cur] on entry and exit.
+int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const double *rhs, bool u_is_zero) {
+    const int max_level = (int)ctx->levels.size() - 1;
+    DevLevel &lv = ctx->levels[l];
+    // solve.cpp:991-1057 coarsest level: direct solve on the rank that owns it
+    if (l == max_level) {
+        if (lv.M > 0) SB_TRY(sb_coarsest_apply(ctx, rhs, lv.u[lv.cur]));
+        return 0;
+    }
+    DevLevel &cl = ctx->levels[l + 1];
+    // 1. pre-smooth (:1105-1107)
+    if (pre) SB_TRY(sb_smooth(ctx, l, smoother, pre, rhs, u_is_zero));
+    else if (u_is_zero) SB_TRY(sb_fill_zero(ctx, lv.u[lv.cur], lv.M));
+    // 2. residual res = A u - rhs (:1140); with a zero iterate and no pre-smoothing it is -rhs
+    if (pre == 0 && u_is_zero) {
+        SB_TRY(sb_negate_copy(ctx, lv.M, rhs, lv.res));
+    } else {
+        EpiArgs e{};
+        e.rhs = rhs;
+        e.out = lv.res;
+        SB_TRY(sb_apply(ctx, lv.A, lv.u[lv.cur], EPI_RESIDUAL, e));
+    }
+    // 3. restrict (:1175) into the coarse grid's rhs, through the old partition if they differ
+    {
+        EpiArgs e{};
+        const bool ident = lv.repart.identity();
+        e.out = ident ? cl.rhs : lv.xfer_old;
+        SB_TRY(sb_apply(ctx, lv.R, lv.res, EPI_PLAIN, e));
+        if (!ident) SB_TRY(sb_repart(ctx, lv.repart, false, lv.xfer_old, cl.rhs, ctx->stream));  // :1201-1203
+    }
+    // 4. recurse with a zero initial correction (:1249, :1256)
+    SB_TRY(sb_vcycle(ctx, l + 1, smoother, pre, post, cl.rhs, true));
+    // 5. + 6. prolong and correct: u -= P e_c (:1301-1303, :1325, :1360-1361)
+    {
+        const double *ec = cl.u[cl.cur];
+        if (!lv.repart.identity()) {
+            SB_TRY(sb_repart(ctx, lv.repart, true, ec, lv.xfer_old, ctx->stream));
+            ec = lv.xfer_old;
+        }
+        EpiArgs e{};
+        e.u_in = lv.u[lv.cur];
+        e.out = lv.u[lv.cur];  // row i reads and writes only u[i]: in place
+        SB_TRY(sb_apply(ctx, lv.P, ec, EPI_SUB, e));
+    }
+    // 7. post-smooth (:1397-1399)
+    if (post) SB_TRY(sb_smooth(ctx, l, smoother, post, rhs, false));
+    return 0;
+}

@@ -1,0 +1,201 @@
+// spmv_kernels.cuh -- FP64 / int32-column CSR SpMV kernels for sm_100a with fused epilogues.
+//
+// Replaces the scalar loops of saena_matrix::matvec_sparse (/root/reference/src/
+// saena_matrix_matvec.cpp:68-80 local part, :87-110 remote part), the residual variants of
+// include/saena_matrix.tpp:16-43 and the update loops of saena_matrix::chebyshev / jacobi
+// (src/saena_matrix.cpp:1044-1131).  All of it is HBM-bound (<= 0.17 flop/byte): no tensor
+// cores; what matters is that every byte of val/col/vectors is fetched once, in full 128-byte
+// lines, with enough loads in flight.
+//
+// Two row mappings, chosen per operator from nnz/row (sb_choose_mapping):
+//   spmv_vec<LANES>    LANES (1..32) lanes cooperate on a row, a warp owns 32 consecutive rows
+//                      and results are transposed so lane j finishes row j: the epilogue's
+//                      vector streams (rhs, inv_diag, d, u) are read and written fully coalesced.
+//   spmv_stream<LPR>   a CTA owns a block of consecutive rows holding <= STREAM_TILE non-zeros;
+//                      val/col are streamed in perfectly coalesced order, products go to shared
+//                      memory, then LPR lanes per row reduce their segment.  Best for short rows
+//                      (7-point level 0) where a per-row mapping wastes lanes.
+#pragma once
+
+#include "common.h"
+
+template <int EPI>
+__device__ __forceinline__ void sb_epilogue(int i, double ax, const EpiArgs &e) {
+    if (EPI == EPI_PLAIN) {
+        e.out[i] = ax;
+    } else if (EPI == EPI_RESIDUAL) {
+        e.out[i] = ax - e.rhs[i];
+    } else if (EPI == EPI_CHEB_FIRST) {
+        const double d = e.c1 * e.inv_diag[i] * (e.rhs[i] - ax);
+        e.d_out[i] = d;
+        e.out[i] = e.u_in[i] + d;
+    } else if (EPI == EPI_CHEB_NEXT) {
+        const double res = e.c2 * e.inv_diag[i] * (e.rhs[i] - ax);
+        const double d = (e.c1 * e.d_in[i]) + res;
+        e.d_out[i] = d;
+        e.out[i] = e.u_in[i] + d;
+    } else if (EPI == EPI_JACOBI) {
+        const double t = (ax - e.rhs[i]) * (e.inv_diag[i] * e.c1);
+        e.out[i] = e.u_in[i] - t;
+    } else if (EPI == EPI_SUB) {
+        e.out[i] = e.u_in[i] - ax;
+    }
+}
+
+__device__ __forceinline__ bool sb_row_skipped(const uint32_t *__restrict__ mask, int row) {
+    return mask != nullptr && ((mask[row >> 5] >> (row & 31)) & 1u);
+}
+
+// streaming loads of the matrix arrays: read once, do not pollute L1
+__device__ __forceinline__ double sb_ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ int sb_ld_stream(const int *p) { return __ldcs(p); }
+
+// ---------------------------------------------------------------------------------------------
+// spmv_vec: LANES lanes per row, warp = 32 consecutive rows, transposed epilogue
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int EPI, typename OffT>
+__global__ void __launch_bounds__(256)
+spmv_vec_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+                const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
+                const uint32_t *__restrict__ skip_mask) {
+    constexpr int G = 32 / LANES;  // rows in flight per warp per step
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int row0 = warp * 32;
+    if (row0 >= M) return;
+    const int my_row = row0 + lane;
+    // lane j fetches the extent of row j (coalesced), shuffled to the cooperating lanes below
+    OffT my_start = 0, my_end = 0;
+    if (my_row < M) {
+        my_start = rowptr[my_row];
+        my_end = rowptr[my_row + 1];
+    }
+    double mine = 0.0;
+    const int g = lane / LANES;   // which row of the step this lane works on
+    const int sub = lane % LANES;
+#pragma unroll
+    for (int t = 0; t < LANES; ++t) {
+        const int src = t * G + g;  // lane that owns the row this group works on in step t
+        const OffT start = __shfl_sync(0xffffffffu, my_start, src);
+        const OffT end = __shfl_sync(0xffffffffu, my_end, src);
+        double sum = 0.0;
+        for (OffT k = start + sub; k < end; k += LANES) sum += sb_ld_stream(val + k) * __ldg(x + sb_ld_stream(col + k));
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        // lane j = t*G + g' wants the sum of group g' = j % G
+        const double v = __shfl_sync(0xffffffffu, sum, (lane % G) * LANES);
+        if (lane / G == t) mine = v;
+    }
+    if (my_row < M && !sb_row_skipped(skip_mask, my_row)) sb_epilogue<EPI>(my_row, mine, e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// spmv_stream: CTA = block of consecutive rows with <= STREAM_TILE nnz
+// ---------------------------------------------------------------------------------------------
+template <int LPR, int EPI, typename OffT>
+__global__ void __launch_bounds__(STREAM_THREADS)
+spmv_stream_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+                   const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
+                   const uint32_t *__restrict__ skip_mask, const int *__restrict__ blk_row) {
+    constexpr int ROWS = STREAM_THREADS / LPR;  // max rows per block
+    __shared__ double s_prod[STREAM_TILE];
+    __shared__ OffT s_rp[STREAM_THREADS + 1];
+    __shared__ double s_red[STREAM_THREADS / 32];
+    const int tid = threadIdx.x;
+    const int r0 = blk_row[blockIdx.x];
+    const int r1 = blk_row[blockIdx.x + 1];
+    const int nrows = r1 - r0;  // <= ROWS
+    if (tid <= nrows) s_rp[tid] = rowptr[r0 + tid];
+    __syncthreads();
+    const OffT base = s_rp[0];
+    const OffT nnzb = s_rp[nrows] - base;
+
+    if (nnzb > STREAM_TILE) {
+        // a single row longer than the tile (the host puts such a row alone in its block)
+        double sum = 0.0;
+        for (OffT k = tid; k < nnzb; k += STREAM_THREADS)
+            sum += sb_ld_stream(val + base + k) * __ldg(x + sb_ld_stream(col + base + k));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if ((tid & 31) == 0) s_red[tid >> 5] = sum;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < STREAM_THREADS / 32; ++w) tot += s_red[w];
+            if (!sb_row_skipped(skip_mask, r0)) sb_epilogue<EPI>(r0, tot, e);
+        }
+        return;
+    }
+
+    // phase 1: products in storage order -- every load is a full coalesced line
+    const int n = (int)nnzb;
+#pragma unroll 4
+    for (int k = tid; k < n; k += STREAM_THREADS)
+        s_prod[k] = sb_ld_stream(val + base + k) * __ldg(x + sb_ld_stream(col + base + k));
+    __syncthreads();
+
+    // phase 2: LPR lanes reduce one row's segment
+    if (LPR == 1) {
+        if (tid < nrows) {
+            const int a = (int)(s_rp[tid] - base), b = (int)(s_rp[tid + 1] - base);
+            double sum = 0.0;
+            for (int k = a; k < b; ++k) sum += s_prod[k];
+            const int row = r0 + tid;
+            if (!sb_row_skipped(skip_mask, row)) sb_epilogue<EPI>(row, sum, e);
+        }
+    } else {
+        __shared__ double s_rowsum[ROWS];
+        const int rr = tid / LPR, sub = tid % LPR;
+        double sum = 0.0;
+        if (rr < nrows) {
+            const int a = (int)(s_rp[rr] - base), b = (int)(s_rp[rr + 1] - base);
+            for (int k = a + sub; k < b; k += LPR) sum += s_prod[k];
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (sub == 0 && rr < nrows) s_rowsum[rr] = sum;
+        __syncthreads();
+        if (tid < nrows) {
+            const int row = r0 + tid;
+            if (!sb_row_skipped(skip_mask, row)) sb_epilogue<EPI>(row, s_rowsum[tid], e);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// boundary rows: rows with entries in other ranks' columns.  8 lanes per row: local segment
+// (recomputed -- these rows are a few percent of the block) + remote segment read from the ghost
+// buffer the halo exchange filled (float when the operator's use_double is false:
+// matvec_sparse_float, saena_matrix_matvec.cpp:531-538 widens on use).
+// ---------------------------------------------------------------------------------------------
+template <int EPI, typename OffT, typename GhostT>
+__global__ void __launch_bounds__(256)
+spmv_boundary_kernel(int n_brows, const int *__restrict__ brow, const OffT *__restrict__ rowptr,
+                     const int *__restrict__ col, const double *__restrict__ val,
+                     const int *__restrict__ brow_ptr, const int *__restrict__ bcol,
+                     const double *__restrict__ bval, const double *__restrict__ x,
+                     const GhostT *__restrict__ ghost, EpiArgs e) {
+    constexpr int LANES = 8;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = gid / LANES, sub = gid % LANES;
+    double sum = 0.0;
+    int row = -1;
+    if (b < n_brows) {
+        row = brow[b];
+        const OffT s = rowptr[row], t = rowptr[row + 1];
+        for (OffT k = s + sub; k < t; k += LANES) sum += val[k] * __ldg(x + col[k]);
+        const int rs = brow_ptr[b], rt = brow_ptr[b + 1];
+        for (int k = rs + sub; k < rt; k += LANES) sum += bval[k] * (double)ghost[bcol[k]];
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (sub == 0 && row >= 0) sb_epilogue<EPI>(row, sum, e);
+}
+
+// halo pack: vSend[i] = v[vIndex[i]] (saena_matrix_matvec.cpp:25-26; :463-464 casts to float)
+template <typename SendT>
+__global__ void halo_pack_kernel(int n, const int *__restrict__ vIndex, const double *__restrict__ v,
+                                 SendT *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (SendT)v[vIndex[i]];
+}

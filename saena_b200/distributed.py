@@ -1,0 +1,56 @@
+"""Process-group plumbing for the N>1 path: one process per GPU, launched by torchrun.
+
+torch.distributed is used only to bootstrap (sharing the NCCL unique id, barriers, max-over-ranks
+timing); the data path -- halo exchange, dot-product all-reduce, coarse-vector repartition -- is
+NCCL called from libsaena_b200.so on its own streams.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+
+from .hierarchy import Operator
+
+
+def exchange_nccl_id(make_id: Callable[[], bytes]) -> bytes:
+    """Rank 0 creates the id (saena_b200_nccl_unique_id), everyone receives the 128 bytes."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    if rank == 0:
+        buf = torch.tensor(list(make_id()), dtype=torch.uint8, device=dev)
+    else:
+        buf = torch.zeros(128, dtype=torch.uint8, device=dev)
+    dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().tolist())
+
+
+def halo_exchange_host(op: Operator, v: np.ndarray) -> np.ndarray:
+    """The halo exchange of one operator with torch.distributed point-to-point on HOST buffers,
+    following the same plan the device path executes with ncclSend/ncclRecv (pack with vIndex,
+    slices at vdispls / rdispls, float cast when use_double is false).  Used by the CPU (gloo)
+    test of the plan; the solve path never calls it."""
+    import torch
+    import torch.distributed as dist
+
+    dt = np.float64 if op.use_double else np.float32
+    send = v[op.vIndex].astype(dt)
+    ghost = np.zeros(op.col_remote_size, dt)
+    reqs = []
+    recv_bufs = []
+    for p, c in zip(op.recvProcRank, op.recvProcCount):
+        t = torch.zeros(int(c), dtype=torch.float64 if op.use_double else torch.float32)
+        recv_bufs.append((int(p), t))
+        reqs.append(dist.irecv(t, src=int(p)))
+    for p, c in zip(op.sendProcRank, op.sendProcCount):
+        o = int(op.vdispls[p])
+        reqs.append(dist.isend(torch.from_numpy(send[o:o + int(c)].copy()), dst=int(p)))
+    for r in reqs:
+        r.wait()
+    for p, t in recv_bufs:
+        o = int(op.rdispls[p])
+        ghost[o:o + t.numel()] = t.numpy()
+    return ghost.astype(np.float64)

@@ -310,3 +310,59 @@ def partition_hierarchy(h: Hierarchy, nprocs: int, agglomerate_below: int = 0) -
                             level.repart_recv.append((peer, int(a - sn[r]), int(b - a)))
             out[r].levels.append(level)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# (de)serialisation: a flat dict of numpy arrays (np.savez friendly) -- used for the golden
+# fixtures under tests/golden/ and for handing a hierarchy between processes.
+# --------------------------------------------------------------------------------------
+_OP_ARRAYS = ("nnzPerRow_local", "col_local", "val_local", "row_remote", "val_remote", "nnzPerCol_remote",
+              "nnzPerProcScan", "vIndex", "vdispls", "rdispls", "sendProcRank", "sendProcCount", "recvProcRank",
+              "recvProcCount")
+_OP_SCALARS = ("kind", "level", "M", "Mbig", "Nbig", "row_offset", "col_offset", "n_local_cols", "use_double",
+               "nprocs", "rank")
+
+
+def hierarchy_to_arrays(h: Hierarchy) -> dict:
+    out = {"meta": np.array([len(h.levels), h.coarse_n, h.nprocs, h.rank], I64),
+           "coarse_row": h.coarse_row, "coarse_col": h.coarse_col, "coarse_val": h.coarse_val}
+    for lv in h.levels:
+        p = f"L{lv.level}."
+        out[p + "inv_diag"] = lv.inv_diag
+        out[p + "scalars"] = np.array([lv.eig_max, float(lv.active), lv.M_coarse_old, lv.M_coarse,
+                                       float(lv.P is not None)], F64)
+        out[p + "repart_send"] = np.array(lv.repart_send, I32).reshape(-1, 3)
+        out[p + "repart_recv"] = np.array(lv.repart_recv, I32).reshape(-1, 3)
+        for name, op in (("A", lv.A), ("P", lv.P), ("R", lv.R)):
+            if op is None:
+                continue
+            q = p + name + "."
+            out[q + "scalars"] = np.array([int(getattr(op, s)) for s in _OP_SCALARS], I64)
+            for a in _OP_ARRAYS:
+                out[q + a] = getattr(op, a)
+    return out
+
+
+def hierarchy_from_arrays(d) -> Hierarchy:
+    nlev, coarse_n, nprocs, rank = (int(x) for x in d["meta"])
+    levels = []
+    for l in range(nlev):
+        p = f"L{l}."
+        eig, active, mco, mc, has_p = d[p + "scalars"]
+
+        def op(name):
+            q = p + name + "."
+            sc = dict(zip(_OP_SCALARS, (int(x) for x in d[q + "scalars"])))
+            sc["use_double"] = bool(sc["use_double"])
+            return Operator(**sc, **{a: np.array(d[q + a]) for a in _OP_ARRAYS})
+
+        lv = Level(level=l, A=op("A"), inv_diag=np.array(d[p + "inv_diag"]), eig_max=float(eig), active=bool(active),
+                   M_coarse_old=int(mco), M_coarse=int(mc),
+                   repart_send=[tuple(int(x) for x in r) for r in d[p + "repart_send"]],
+                   repart_recv=[tuple(int(x) for x in r) for r in d[p + "repart_recv"]])
+        if has_p:
+            lv.P, lv.R = op("P"), op("R")
+        levels.append(lv)
+    return Hierarchy(levels=levels, coarse_n=coarse_n, coarse_row=np.array(d["coarse_row"]),
+                     coarse_col=np.array(d["coarse_col"]), coarse_val=np.array(d["coarse_val"]), nprocs=nprocs,
+                     rank=rank)

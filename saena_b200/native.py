@@ -1,0 +1,300 @@
+"""ctypes binding of libsaena_b200.so -- exactly the C ABI of include/saena_b200.h.
+
+There is no fallback: if the library is missing it is built with nvcc (saena_b200/build.py);
+if no CUDA device is usable `saena_b200_init` fails and `Context()` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .hierarchy import F64, I32, Hierarchy, Level, Operator
+
+c_i32_p = ctypes.POINTER(ctypes.c_int32)
+c_f64_p = ctypes.POINTER(ctypes.c_double)
+
+JACOBI, CHEBYSHEV = 0, 1
+NCCL_ID_BYTES = 128
+
+
+class OperatorDesc(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("level", ctypes.c_int32), ("M", ctypes.c_int32),
+                ("n_local_cols", ctypes.c_int32), ("col_offset", ctypes.c_int32), ("use_double", ctypes.c_int32),
+                ("nnz_local", ctypes.c_int64), ("nnzPerRow_local", c_i32_p), ("col_local", c_i32_p),
+                ("val_local", c_f64_p), ("nnz_remote", ctypes.c_int64), ("col_remote_size", ctypes.c_int32),
+                ("row_remote", c_i32_p), ("val_remote", c_f64_p), ("nnzPerCol_remote", c_i32_p),
+                ("vIndexSize", ctypes.c_int32), ("vIndex", c_i32_p), ("numSendProc", ctypes.c_int32),
+                ("sendProcRank", c_i32_p), ("sendProcCount", c_i32_p), ("vdispls", c_i32_p),
+                ("numRecvProc", ctypes.c_int32), ("recvProcRank", c_i32_p), ("recvProcCount", c_i32_p),
+                ("rdispls", c_i32_p)]
+
+
+class Block(ctypes.Structure):
+    _fields_ = [("peer", ctypes.c_int32), ("offset", ctypes.c_int32), ("count", ctypes.c_int32)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None):
+    """Loads (building first if needed) libsaena_b200.so and declares the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if path is None:
+        from . import build
+        path = build.LIB if os.path.exists(build.LIB) and not build._stale() else build.build_library()
+    L = ctypes.CDLL(path)
+    vp, i, d = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    ip, dp = ctypes.POINTER(ctypes.c_int), c_f64_p
+    L.saena_b200_last_error.restype = ctypes.c_char_p
+    L.saena_b200_last_error.argtypes = [vp]
+    L.saena_b200_nccl_unique_id.argtypes = [vp]
+    L.saena_b200_init.argtypes = [ctypes.POINTER(vp), i, i, i, vp]
+    L.saena_b200_destroy.argtypes = [vp]
+    L.saena_b200_upload_operator.argtypes = [vp, ctypes.POINTER(OperatorDesc)]
+    L.saena_b200_upload_level_aux.argtypes = [vp, i, dp, d, i, i, i, ctypes.POINTER(Block), i, ctypes.POINTER(Block)]
+    L.saena_b200_upload_coarsest.argtypes = [vp, i, ctypes.c_int64, c_i32_p, c_i32_p, dp]
+    L.saena_b200_finalize.argtypes = [vp]
+    solve_args = [vp, vp, vp, i, d, i, i, i, ip, dp, i, ip]
+    L.saena_b200_solve_pcg.argtypes = solve_args
+    L.saena_b200_solve_pcg_dev.argtypes = solve_args
+    L.saena_b200_solve_vcycle.argtypes = solve_args
+    L.saena_b200_solve_cg.argtypes = [vp, vp, vp, i, d, ip, dp, i, ip]
+    L.saena_b200_matvec.argtypes = [vp, i, i, vp, vp]
+    L.saena_b200_residual.argtypes = [vp, i, vp, vp, vp]
+    L.saena_b200_smooth.argtypes = [vp, i, i, i, vp, vp]
+    L.saena_b200_vcycle.argtypes = [vp, i, i, i, i, vp, vp]
+    L.saena_b200_coarsest_solve.argtypes = [vp, vp, vp]
+    L.saena_b200_dot.argtypes = [vp, vp, vp, i, dp]
+    L.saena_b200_time_matvec.argtypes = [vp, i, i, i, i, ctypes.POINTER(ctypes.c_float)]
+    L.saena_b200_time_smooth_sweep.argtypes = [vp, i, i, i, i, ctypes.POINTER(ctypes.c_float)]
+    L.saena_b200_launch_count.restype = ctypes.c_int64
+    L.saena_b200_launch_count.argtypes = [vp]
+    L.saena_b200_set_mapping.argtypes = [vp, i, i, i]
+    L.saena_b200_operator_bytes.restype = ctypes.c_int64
+    L.saena_b200_operator_bytes.argtypes = [vp, i, i]
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "saena_b200_nccl_unique_id", "saena_b200_init", "saena_b200_destroy", "saena_b200_last_error",
+    "saena_b200_upload_operator", "saena_b200_upload_level_aux", "saena_b200_upload_coarsest",
+    "saena_b200_finalize", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
+    "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
+    "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
+    "saena_b200_time_smooth_sweep", "saena_b200_launch_count", "saena_b200_set_mapping",
+    "saena_b200_operator_bytes",
+]
+
+
+def nccl_unique_id() -> bytes:
+    L = load_library()
+    buf = ctypes.create_string_buffer(NCCL_ID_BYTES)
+    if L.saena_b200_nccl_unique_id(buf):
+        raise NativeError(L.saena_b200_last_error(None).decode())
+    return buf.raw
+
+
+def _i32p(a: np.ndarray):
+    return a.ctypes.data_as(c_i32_p)
+
+
+def _f64p(a: np.ndarray):
+    return a.ctypes.data_as(c_f64_p)
+
+
+def _vp(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def smoother_id(name) -> int:
+    if isinstance(name, int):
+        return name
+    if name == "chebyshev":
+        return CHEBYSHEV
+    if name == "jacobi":
+        return JACOBI
+    raise ValueError(f"unknown smoother {name!r}")  # the reference: "Error: Unknown smoother" then exit
+
+
+class Context:
+    """One rank's device context: an uploaded hierarchy and the solve entry points."""
+
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None):
+        self._L = load_library()
+        self._h = ctypes.c_void_p()
+        idbuf = ctypes.create_string_buffer(nccl_id, NCCL_ID_BYTES) if nccl_id else None
+        rc = self._L.saena_b200_init(ctypes.byref(self._h), device, rank, nranks, idbuf)
+        if rc:
+            raise NativeError(self._L.saena_b200_last_error(None).decode())
+        self.rank, self.nranks, self.device = rank, nranks, device
+        self.level_rows: List[int] = []
+        self.hier: Optional[Hierarchy] = None
+
+    def _ck(self, rc: int):
+        if rc:
+            raise NativeError(self._L.saena_b200_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._L.saena_b200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- upload ----
+    def upload_operator(self, op: Operator):
+        a = [np.ascontiguousarray(x, I32) for x in
+             (op.nnzPerRow_local, op.col_local, op.row_remote, op.nnzPerCol_remote, op.vIndex, op.sendProcRank,
+              op.sendProcCount, op.vdispls, op.recvProcRank, op.recvProcCount, op.rdispls)]
+        vl, vr = np.ascontiguousarray(op.val_local, F64), np.ascontiguousarray(op.val_remote, F64)
+        d = OperatorDesc(kind=op.kind, level=op.level, M=op.M, n_local_cols=op.n_local_cols,
+                         col_offset=op.col_offset, use_double=int(op.use_double), nnz_local=op.nnz_local,
+                         nnzPerRow_local=_i32p(a[0]), col_local=_i32p(a[1]), val_local=_f64p(vl),
+                         nnz_remote=op.nnz_remote, col_remote_size=op.col_remote_size, row_remote=_i32p(a[2]),
+                         val_remote=_f64p(vr), nnzPerCol_remote=_i32p(a[3]), vIndexSize=op.vIndexSize,
+                         vIndex=_i32p(a[4]), numSendProc=len(a[5]), sendProcRank=_i32p(a[5]),
+                         sendProcCount=_i32p(a[6]), vdispls=_i32p(a[7]), numRecvProc=len(a[8]),
+                         recvProcRank=_i32p(a[8]), recvProcCount=_i32p(a[9]), rdispls=_i32p(a[10]))
+        self._ck(self._L.saena_b200_upload_operator(self._h, ctypes.byref(d)))
+
+    def upload_hierarchy(self, h: Hierarchy):
+        """Upload once: what the adaptor does at the end of amg::set_matrix."""
+        for lv in h.levels:
+            self.upload_operator(lv.A)
+            if lv.P is not None:
+                self.upload_operator(lv.P)
+                self.upload_operator(lv.R)
+            inv = np.ascontiguousarray(lv.inv_diag, F64)
+            send = (Block * max(len(lv.repart_send), 1))(*[Block(*b) for b in lv.repart_send])
+            recv = (Block * max(len(lv.repart_recv), 1))(*[Block(*b) for b in lv.repart_recv])
+            self._ck(self._L.saena_b200_upload_level_aux(self._h, lv.level, _f64p(inv), float(lv.eig_max),
+                                                        lv.M_coarse_old, lv.M_coarse, len(lv.repart_send), send,
+                                                        len(lv.repart_recv), recv))
+        owns_coarsest = h.levels[-1].A.M > 0
+        if owns_coarsest:
+            r, c = np.ascontiguousarray(h.coarse_row, I32), np.ascontiguousarray(h.coarse_col, I32)
+            v = np.ascontiguousarray(h.coarse_val, F64)
+            self._ck(self._L.saena_b200_upload_coarsest(self._h, h.coarse_n, len(v), _i32p(r), _i32p(c), _f64p(v)))
+        else:
+            self._ck(self._L.saena_b200_upload_coarsest(self._h, 0, 0, None, None, None))
+        self._ck(self._L.saena_b200_finalize(self._h))
+        self.hier = h
+        self.level_rows = [lv.A.M for lv in h.levels]
+
+    # ---- solvers ----
+    def _solve(self, fn, rhs, u, max_iter, tol, smoother, pre, post):
+        iters, n = ctypes.c_int(0), ctypes.c_int(0)
+        hist = np.zeros(max_iter + 2, F64)
+        self._ck(fn(self._h, _vp(rhs), _vp(u), int(max_iter), float(tol), smoother_id(smoother), int(pre), int(post),
+                    ctypes.byref(iters), _f64p(hist), len(hist), ctypes.byref(n)))
+        return iters.value, hist[:n.value]
+
+    def solve_pcg(self, rhs: np.ndarray, max_iter=50, tol=1e-8, smoother="chebyshev", pre=3, post=3):
+        rhs = np.ascontiguousarray(rhs, F64)
+        u = np.zeros(self.level_rows[0], F64)
+        it, hist = self._solve(self._L.saena_b200_solve_pcg, rhs, u, max_iter, tol, smoother, pre, post)
+        return u, it, hist
+
+    def solve_pcg_dev(self, rhs_ptr: int, u_ptr: int, max_iter=50, tol=1e-8, smoother="chebyshev", pre=3, post=3):
+        """rhs / u are raw device pointers (e.g. torch.Tensor.data_ptr())."""
+        return self._solve(self._L.saena_b200_solve_pcg_dev, rhs_ptr, u_ptr, max_iter, tol, smoother, pre, post)
+
+    def solve_vcycle(self, rhs, max_iter=50, tol=1e-8, smoother="chebyshev", pre=3, post=3):
+        rhs = np.ascontiguousarray(rhs, F64)
+        u = np.zeros(self.level_rows[0], F64)
+        it, hist = self._solve(self._L.saena_b200_solve_vcycle, rhs, u, max_iter, tol, smoother, pre, post)
+        return u, it, hist
+
+    def solve_cg(self, rhs, max_iter=500, tol=1e-8):
+        rhs = np.ascontiguousarray(rhs, F64)
+        u = np.zeros(self.level_rows[0], F64)
+        iters, n = ctypes.c_int(0), ctypes.c_int(0)
+        hist = np.zeros(max_iter + 2, F64)
+        self._ck(self._L.saena_b200_solve_cg(self._h, _vp(rhs), _vp(u), int(max_iter), float(tol),
+                                             ctypes.byref(iters), _f64p(hist), len(hist), ctypes.byref(n)))
+        return u, iters.value, hist[:n.value]
+
+    # ---- hooks ----
+    def _op(self, level, kind) -> Operator:
+        lv = self.hier.levels[level]
+        return (lv.A, lv.P, lv.R)[kind]
+
+    def matvec(self, level: int, kind: int, v: np.ndarray) -> np.ndarray:
+        v = np.ascontiguousarray(v, F64)
+        op = self._op(level, kind)
+        assert len(v) == op.n_local_cols
+        w = np.zeros(op.M, F64)
+        self._ck(self._L.saena_b200_matvec(self._h, level, kind, _vp(v), _vp(w)))
+        return w
+
+    def residual(self, level, u, rhs):
+        u, rhs = np.ascontiguousarray(u, F64), np.ascontiguousarray(rhs, F64)
+        res = np.zeros_like(u)
+        self._ck(self._L.saena_b200_residual(self._h, level, _vp(u), _vp(rhs), _vp(res)))
+        return res
+
+    def smooth(self, level, smoother, iters, u, rhs):
+        u = np.array(u, F64, copy=True)
+        rhs = np.ascontiguousarray(rhs, F64)
+        self._ck(self._L.saena_b200_smooth(self._h, level, smoother_id(smoother), int(iters), _vp(u), _vp(rhs)))
+        return u
+
+    def vcycle(self, level, u, rhs, pre=3, post=3, smoother="chebyshev"):
+        u = np.array(u, F64, copy=True)
+        rhs = np.ascontiguousarray(rhs, F64)
+        self._ck(self._L.saena_b200_vcycle(self._h, level, smoother_id(smoother), int(pre), int(post), _vp(u),
+                                           _vp(rhs)))
+        return u
+
+    def coarsest_solve(self, rhs):
+        rhs = np.ascontiguousarray(rhs, F64)
+        u = np.zeros_like(rhs)
+        self._ck(self._L.saena_b200_coarsest_solve(self._h, _vp(rhs), _vp(u)))
+        return u
+
+    def dot(self, a, b) -> float:
+        a, b = np.ascontiguousarray(a, F64), np.ascontiguousarray(b, F64)
+        out = ctypes.c_double(0)
+        self._ck(self._L.saena_b200_dot(self._h, _vp(a), _vp(b), len(a), ctypes.byref(out)))
+        return out.value
+
+    # ---- measurement ----
+    def time_matvec(self, level, kind, reps=20, flush_l2=False) -> float:
+        ms = ctypes.c_float(0)
+        self._ck(self._L.saena_b200_time_matvec(self._h, level, kind, reps, int(flush_l2), ctypes.byref(ms)))
+        return ms.value
+
+    def time_smooth_sweep(self, level, smoother="chebyshev", reps=20, flush_l2=False) -> float:
+        ms = ctypes.c_float(0)
+        self._ck(self._L.saena_b200_time_smooth_sweep(self._h, level, smoother_id(smoother), reps, int(flush_l2),
+                                                      ctypes.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(self._L.saena_b200_launch_count(self._h))
+
+    def set_mapping(self, level, kind, mapping: int):
+        """mapping > 0: that many lanes per row (sub-warp mapping); < 0: streaming row blocks with
+        -mapping lanes per row in the reduce phase; 0: heuristic from nnz/row."""
+        self._ck(self._L.saena_b200_set_mapping(self._h, level, kind, int(mapping)))
+
+    def operator_bytes(self, level, kind) -> int:
+        return int(self._L.saena_b200_operator_bytes(self._h, level, kind))

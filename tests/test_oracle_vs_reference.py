@@ -1,0 +1,57 @@
+"""The CPU restatement against the UNMODIFIED reference compiled here (oracle/_ref), live, on a
+hierarchy built in this process -- including sizes and option sets the golden files do not hold.
+Skipped where oracle/_ref is absent."""
+import numpy as np
+import pytest
+
+from oracle import ref
+from oracle.oracle import Oracle
+from tests.util import TOL_HIST, TOL_OP, check_pcg, rel
+
+pytestmark = pytest.mark.ref
+
+
+@pytest.fixture(scope="module")
+def poisson16():
+    s = ref.RefSolver.poisson(16)
+    yield s, s.hierarchy()
+    s.close()
+
+
+def test_ops_every_level(poisson16):
+    s, h = poisson16
+    o = Oracle(h)
+    rng = np.random.default_rng(7)
+    for l, lv in enumerate(h.levels):
+        v, b = rng.standard_normal(lv.A.M), rng.standard_normal(lv.A.M)
+        assert rel(o.matvec(l, 0, v), s.matvec(l, 0, v)) < TOL_OP
+        assert rel(o.residual(l, v, b), s.residual(l, v, b)) < TOL_OP
+        for it in (1, 2, 3, 5):
+            assert rel(o.smooth(l, "chebyshev", it, v, b), s.smooth(l, "chebyshev", it, v, b)) < TOL_OP
+        assert rel(o.smooth(l, "jacobi", 3, v, b), s.smooth(l, "jacobi", 3, v, b)) < TOL_OP
+        if lv.P is not None:
+            vc = rng.standard_normal(lv.P.n_local_cols)
+            assert rel(o.matvec(l, 1, vc), s.matvec(l, 1, vc)) < TOL_OP
+            assert rel(o.matvec(l, 2, v), s.matvec(l, 2, v)) < TOL_OP
+        assert rel(o.vcycle(l, np.zeros(lv.A.M), b), s.vcycle(l, np.zeros(lv.A.M), b)) < 1e-11
+    bc = rng.standard_normal(h.coarse_n)
+    assert rel(o.coarsest_solve(bc), s.coarsest_solve(bc)) < TOL_OP
+    a, b = rng.standard_normal(1000), rng.standard_normal(1000)
+    assert abs(o.dot(a, b) - s.dot(a, b)) <= 1e-13 * np.linalg.norm(a) * np.linalg.norm(b)
+
+
+def test_pcg_iterations_and_history(poisson16):
+    s, h = poisson16
+    u_ref, it_ref, hist_ref = s.solve_pcg()
+    u, it, hist = Oracle(h).solve_pcg(s.rhs(), s.opts.max_iter, s.opts.tol, "chebyshev", s.opts.pre, s.opts.post)
+    assert it == it_ref
+    check_pcg(it, hist, u, it_ref, hist_ref, u_ref, TOL_HIST)
+
+
+def test_pcg_jacobi_smoother_and_max_iter_cap(poisson16):
+    s, h = poisson16
+    # jacobi 2/1 converges slower; cap the iterations to exercise the `i == max_iter` exit
+    u_ref, it_ref, hist_ref = s.solve_pcg(max_iter=3, tol=1e-14, smoother="jacobi", pre=2, post=1)
+    u, it, hist = Oracle(h).solve_pcg(s.rhs(), 3, 1e-14, "jacobi", 2, 1)
+    assert it == it_ref == 3
+    check_pcg(it, hist, u, it_ref, hist_ref, u_ref, TOL_HIST)

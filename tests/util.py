@@ -1,0 +1,86 @@
+"""Shared helpers of the parity tests.
+
+`impl` below is anything with the methods matvec / residual / smooth / vcycle / coarsest_solve /
+dot and a PCG entry point: the C oracle (oracle.oracle.Oracle), the compiled reference
+(oracle.ref.RefSolver) or the CUDA path (saena_b200.native.Context) -- the three expose the same
+names on purpose, so one checker serves "oracle vs golden", "oracle vs reference" and
+"CUDA vs oracle/golden".
+"""
+import os
+
+import numpy as np
+
+from saena_b200.hierarchy import hierarchy_from_arrays
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN = ["poisson9_cheb", "poisson12_cheb"]
+
+# tolerances of BASELINE.json's north_star
+TOL_OP = 1e-12       # each SpMV, smoother sweep and transfer: relative error in the 2-norm
+TOL_HIST = 1e-9      # residual-norm history, relative, per iteration
+ITER_SLACK = 1       # iteration count +-1
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    nb = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / nb) if nb > 0 else float(np.linalg.norm(a))
+
+
+class Golden:
+    def __init__(self, name):
+        self.name = name
+        self.d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.hier = hierarchy_from_arrays({k[5:]: self.d[k] for k in self.d.files if k.startswith("hier.")})
+        self.rhs = self.d["rhs"]
+        self.max_iter, self.tol, self.pre, self.post = (int(self.d["opts"][0]), float(self.d["opts"][1]),
+                                                        int(self.d["opts"][2]), int(self.d["opts"][3]))
+
+    def __getitem__(self, k):
+        return self.d[k]
+
+
+def check_ops_against_golden(impl, g: Golden, tol=TOL_OP):
+    """every per-operator function on the golden inputs vs what the reference returned"""
+    h = g.hier
+    worst = {}
+    for l, lv in enumerate(h.levels):
+        v, b = g[f"in.L{l}.v"], g[f"in.L{l}.b"]
+        worst[f"L{l}.A"] = rel(impl.matvec(l, 0, v), g[f"out.L{l}.A_matvec"])
+        worst[f"L{l}.residual"] = rel(impl.residual(l, v, b), g[f"out.L{l}.residual"])
+        worst[f"L{l}.cheb3"] = rel(impl.smooth(l, "chebyshev", 3, v, b), g[f"out.L{l}.chebyshev3"])
+        worst[f"L{l}.cheb1"] = rel(impl.smooth(l, "chebyshev", 1, v, b), g[f"out.L{l}.chebyshev1"])
+        worst[f"L{l}.jacobi2"] = rel(impl.smooth(l, "jacobi", 2, v, b), g[f"out.L{l}.jacobi2"])
+        if lv.P is not None:
+            worst[f"L{l}.P"] = rel(impl.matvec(l, 1, g[f"in.L{l}.vc"]), g[f"out.L{l}.P_matvec"])
+            worst[f"L{l}.R"] = rel(impl.matvec(l, 2, v), g[f"out.L{l}.R_matvec"])
+    worst["coarsest"] = rel(impl.coarsest_solve(g["in.coarsest.b"]), g["out.coarsest.u"])
+    d = impl.dot(g["in.L0.v"], g["in.L0.b"])
+    worst["dot"] = abs(d - float(g["out.dot"][0])) / abs(float(g["out.dot"][0]))
+    bad = {k: e for k, e in worst.items() if not e <= tol}
+    assert not bad, f"{g.name}: beyond {tol:g}: {bad}"
+    return worst
+
+
+def check_vcycle_against_golden(impl, g: Golden, tol=1e-11):
+    # a V-cycle chains ~10 operator applications per level; allow the per-op bound to accumulate
+    h = g.hier
+    worst = {}
+    for l, lv in enumerate(h.levels):
+        v, b = g[f"in.L{l}.v"], g[f"in.L{l}.b"]
+        worst[f"L{l}.vcycle"] = rel(impl.vcycle(l, np.zeros(lv.A.M), b), g[f"out.L{l}.vcycle"])
+        worst[f"L{l}.vcycle_jac"] = rel(impl.vcycle(l, v, b, pre=1, post=2, smoother="jacobi"),
+                                         g[f"out.L{l}.vcycle_jacobi_1_2"])
+    bad = {k: e for k, e in worst.items() if not e <= tol}
+    assert not bad, f"{g.name}: beyond {tol:g}: {bad}"
+    return worst
+
+
+def check_pcg(iters, hist, u, ref_iters, ref_hist, ref_u, tol_hist=TOL_HIST):
+    assert abs(iters - ref_iters) <= ITER_SLACK, (iters, ref_iters)
+    n = min(len(hist), len(ref_hist))
+    err = np.abs(hist[:n] - ref_hist[:n]) / ref_hist[:n]
+    assert err.max() <= tol_hist, f"residual history differs: {err}"
+    if iters == ref_iters:
+        assert rel(u, ref_u) <= 1e-8
+    return float(err.max())
