@@ -142,7 +142,9 @@ int saena_b200_time_smooth_sweep(saena_b200_ctx *ctx, int level, int smoother, i
                                  float *ms_out);
 /* kernels launched by this context since init (bench.py's gpu_launches) */
 int64_t saena_b200_launch_count(const saena_b200_ctx *ctx);
-/* 0: heuristic; >0: force the lanes-per-row of one operator's SpMV mapping (tuning/profiling) */
+/* Force one operator's SpMV row mapping (tuning / profiling / tests): 0 = heuristic from nnz/row;
+ * 1..32 = that many lanes per row; -1..-32 = streaming row blocks with that many lanes per row in
+ * the reduce phase; 100 = sliced layout (32-row slices, column-major, one lane per row). */
 int saena_b200_set_mapping(saena_b200_ctx *ctx, int level, int kind, int mapping);
 /* algorithmic bytes of one application of an operator (SURVEY.md 8d formula), for the roofline */
 int64_t saena_b200_operator_bytes(const saena_b200_ctx *ctx, int level, int kind);

@@ -90,6 +90,13 @@ struct DevOperator {
     int *blk_row = nullptr;
     int n_blk = 0;
 
+    // sliced layout (32-row slices, column-major, padded per slice) for short regular rows
+    long long *sell_ptr = nullptr;  // [n_slices+1] element offsets
+    int *sell_col = nullptr;
+    double *sell_val = nullptr;
+    int64_t sell_padded = 0;        // stored entries incl. padding
+    int64_t sell_padded_est = 0;    // what the padding would be (computed at upload)
+
     // remote block re-sorted by row at upload: boundary rows only
     int n_brows = 0;
     int *brow = nullptr;       // [n_brows] local row id, ascending
@@ -105,10 +112,11 @@ struct DevOperator {
     void *ghost_buf = nullptr; // double[recvSize] or float[recvSize]
     std::vector<HaloPeer> sends, recvs;
 
-    // kernel mapping: lanes per row of the SpMV (1..32), 0 = streaming kernel
-    int lanes = 0;
+    // kernel mapping
+    int lanes = 0;            // lanes per row (vec) / lanes per row in the reduce phase (stream)
     bool use_stream = false;
-    int forced_mapping = 0;
+    bool use_sell = false;
+    int forced_mapping = 0;   // see saena_b200_set_mapping
 
     double avg_nnz_row() const { return M ? double(nnz_local + nnz_remote) / M : 0.0; }
 };
@@ -177,6 +185,7 @@ struct saena_b200_ctx {
 // scalar slots
 enum { S_RHO_RES = 0, S_PDOTH = 1, S_RR = 2, S_BETA_NUM = 3, S_TMP = 4, S_COUNT = 8 };
 
+static const int SB_MAPPING_SELL = 100;   // forced_mapping / set_mapping code of the sliced layout
 static const int STREAM_TILE = 2048;      // nnz per row block of the streaming kernel (16 KB of products)
 static const int STREAM_THREADS = 256;
 static const int RED_MAX_BLOCKS = 1184;   // 148 SMs x 8

@@ -25,6 +25,7 @@ void sb_free_operator(DevOperator &op) {
     cudaFree(op.rowptr); cudaFree(op.col); cudaFree(op.val); cudaFree(op.blk_row);
     cudaFree(op.brow); cudaFree(op.brow_ptr); cudaFree(op.bcol); cudaFree(op.bval); cudaFree(op.brow_mask);
     cudaFree(op.vIndex); cudaFree(op.send_buf); cudaFree(op.ghost_buf);
+    cudaFree(op.sell_ptr); cudaFree(op.sell_col); cudaFree(op.sell_val);
     op = DevOperator();
 }
 
@@ -54,6 +55,12 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
         std::vector<int64_t> rp(M + 1, 0);
         for (int i = 0; i < M; ++i) rp[i + 1] = rp[i] + d->nnzPerRow_local[i];
         if (rp[M] != d->nnz_local) SB_FAIL("upload_operator: sum(nnzPerRow_local) != nnz_local");
+        op.sell_padded_est = 0;
+        for (int s0 = 0; s0 < M; s0 += 32) {
+            int mx = 0;
+            for (int i = s0; i < std::min(M, s0 + 32); ++i) mx = std::max(mx, d->nnzPerRow_local[i]);
+            op.sell_padded_est += (int64_t)mx * 32;
+        }
         if (op.wide_offsets) {
             int64_t *p = nullptr;
             SB_TRY(dev_upload(ctx, &p, rp.data(), rp.size()));
@@ -161,15 +168,22 @@ void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op) {
     const double avg = op.M ? double(op.nnz_local) / op.M : 0.0;
     int m = op.forced_mapping;
     if (m == 0) {
-        // default: stream rows shorter than 16, sub-warp per row above
-        if (avg < 16.0) m = -1;
-        else m = pow2_at_most(avg / 4.0);  // ~4+ elements per lane
+        // short and regular rows: sliced layout (padding <= 15 %); otherwise a sub-warp per row
+        // with ~4+ elements per lane.  Crossovers measured on B200, see DESIGN.md.
+        // measured on B200 (profiles/r01_mapping_sweep.md): the sliced layout wins whenever its
+        // padding is small (7-pt Poisson 5.9 TB/s vs 5.6 best sub-warp; band 61/row 6.8 vs 5.3)
+        const bool regular = op.nnz_local > 0 && double(op.sell_padded_est) <= 1.20 * double(op.nnz_local);
+        if (regular) m = SB_MAPPING_SELL;
+        else m = pow2_at_most(std::max(1.0, (avg + 1.0) / 4.0));
     }
-    if (m < 0) {
+    op.use_stream = op.use_sell = false;
+    if (m == SB_MAPPING_SELL) {
+        op.use_sell = true;
+        op.lanes = 1;
+    } else if (m < 0) {
         op.use_stream = true;
-        op.lanes = std::min(32, std::max(1, -m == 1 ? 1 : pow2_at_most(-m)));
+        op.lanes = std::min(32, std::max(1, pow2_at_most(-m)));
     } else {
-        op.use_stream = false;
         op.lanes = std::min(32, std::max(1, pow2_at_most(m)));
     }
 }
@@ -201,10 +215,63 @@ static int build_row_blocks(saena_b200_ctx *ctx, DevOperator &op, int rows_per_b
     return 0;
 }
 
+// 32-row slices, column-major inside a slice, padded to the slice's longest row
+static int build_sell(saena_b200_ctx *ctx, DevOperator &op) {
+    if (op.sell_ptr) return 0;
+    const int M = op.M;
+    std::vector<int64_t> rp(M + 1);
+    if (op.wide_offsets) {
+        SB_CUDA(cudaMemcpy(rp.data(), op.rowptr, sizeof(int64_t) * (M + 1), cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<int> rp32(M + 1);
+        SB_CUDA(cudaMemcpy(rp32.data(), op.rowptr, sizeof(int) * (M + 1), cudaMemcpyDeviceToHost));
+        std::copy(rp32.begin(), rp32.end(), rp.begin());
+    }
+    std::vector<int> col((size_t)op.nnz_local);
+    std::vector<double> val((size_t)op.nnz_local);
+    if (op.nnz_local) {
+        SB_CUDA(cudaMemcpy(col.data(), op.col, sizeof(int) * col.size(), cudaMemcpyDeviceToHost));
+        SB_CUDA(cudaMemcpy(val.data(), op.val, sizeof(double) * val.size(), cudaMemcpyDeviceToHost));
+    }
+    const int ns = (M + 31) / 32;
+    std::vector<long long> sp(ns + 1, 0);
+    for (int s0 = 0; s0 < ns; ++s0) {
+        int64_t mx = 0;
+        for (int i = s0 * 32; i < std::min(M, s0 * 32 + 32); ++i) mx = std::max(mx, rp[i + 1] - rp[i]);
+        sp[s0 + 1] = sp[s0] + mx * 32;
+    }
+    const int64_t padded = sp[ns];
+    std::vector<int> scol((size_t)padded, 0);
+    std::vector<double> sval((size_t)padded, 0.0);
+    for (int s0 = 0; s0 < ns; ++s0) {
+        const int len = (int)((sp[s0 + 1] - sp[s0]) / 32);
+        for (int t = 0; t < 32; ++t) {
+            const int i = s0 * 32 + t;
+            const int64_t a = i < M ? rp[i] : 0, b = i < M ? rp[i + 1] : 0;
+            const int pad_col = (b > a) ? col[b - 1] : 0;  // a column this row (or any row) already touches
+            for (int j = 0; j < len; ++j) {
+                const int64_t dst = sp[s0] + (int64_t)j * 32 + t;
+                if (a + j < b) {
+                    scol[dst] = col[a + j];
+                    sval[dst] = val[a + j];
+                } else {
+                    scol[dst] = pad_col;
+                }
+            }
+        }
+    }
+    op.sell_padded = padded;
+    SB_TRY(dev_upload(ctx, &op.sell_ptr, sp.data(), sp.size()));
+    SB_TRY(dev_upload(ctx, &op.sell_col, scol.data(), scol.size()));
+    SB_TRY(dev_upload(ctx, &op.sell_val, sval.data(), sval.size()));
+    return 0;
+}
+
 int sb_prepare_operator(saena_b200_ctx *ctx, DevOperator &op) {
     if (!op.present) return 0;
     sb_choose_mapping(ctx, op);
     if (op.use_stream) SB_TRY(build_row_blocks(ctx, op, STREAM_THREADS / op.lanes));
+    if (op.use_sell) SB_TRY(build_sell(ctx, op));
     return 0;
 }
 
@@ -217,7 +284,10 @@ static void launch_local(saena_b200_ctx *ctx, DevOperator &op, const double *x, 
     cudaStream_t s = ctx->stream;
     if (op.M == 0) return;
     ++ctx->launches;
-    if (op.use_stream) {
+    if (op.use_sell) {
+        const int blocks = (op.M + 255) / 256;
+        spmv_sell_kernel<EPI><<<blocks, 256, 0, s>>>(op.M, op.sell_ptr, op.sell_col, op.sell_val, x, e, op.brow_mask);
+    } else if (op.use_stream) {
         switch (op.lanes) {
 #define SB_STREAM_CASE(L)                                                                          \
     case L:                                                                                        \

@@ -28,7 +28,13 @@ int sb_smooth(saena_b200_ctx *ctx, int l, int smoother, int iters, const double 
     if (smoother == SAENA_B200_JACOBI) {
         // u -= (omega D^-1)(A u - rhs), omega = float(2.0/3) promoted (saena_matrix.h:182)
         e.c1 = (double)(float)(2.0 / 3);
-        for (int j = 0; j < iters; ++j) {
+        int j = 0;
+        if (u_is_zero) {
+            // A*0 = 0: u = 0 - (0 - rhs)*(invd*omega) = (omega*invd)*rhs, no pass over A
+            SB_TRY(sb_cheb_first_zero(ctx, lv.M, rhs, lv.inv_diag, e.c1, lv.d, lv.u[lv.cur]));
+            j = 1;
+        }
+        for (; j < iters; ++j) {
             e.u_in = lv.u[lv.cur];
             e.out = lv.u[lv.cur ^ 1];
             SB_TRY(sb_apply(ctx, lv.A, lv.u[lv.cur], EPI_JACOBI, e));

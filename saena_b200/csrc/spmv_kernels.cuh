@@ -7,7 +7,9 @@
 // cores; what matters is that every byte of val/col/vectors is fetched once, in full 128-byte
 // lines, with enough loads in flight.
 //
-// Two row mappings, chosen per operator from nnz/row (sb_choose_mapping):
+// Three row mappings, chosen per operator from nnz/row and row-length regularity (sb_choose_mapping):
+//   spmv_sell          32-row slices stored column-major (padded per slice): lane = row, every load
+//                      coalesced and independent.  Short regular rows (the 7-point level 0).
 //   spmv_vec<LANES>    LANES (1..32) lanes cooperate on a row, a warp owns 32 consecutive rows
 //                      and results are transposed so lane j finishes row j: the epilogue's
 //                      vector streams (rhs, inv_diag, d, u) are read and written fully coalesced.
@@ -53,6 +55,8 @@ __device__ __forceinline__ int sb_ld_stream(const int *p) { return __ldcs(p); }
 // ---------------------------------------------------------------------------------------------
 // spmv_vec: LANES lanes per row, warp = 32 consecutive rows, transposed epilogue
 // ---------------------------------------------------------------------------------------------
+constexpr int VEC_UNROLL = 4;
+
 template <int LANES, int EPI, typename OffT>
 __global__ void __launch_bounds__(256)
 spmv_vec_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
@@ -79,7 +83,20 @@ spmv_vec_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict__ 
         const OffT start = __shfl_sync(0xffffffffu, my_start, src);
         const OffT end = __shfl_sync(0xffffffffu, my_end, src);
         double sum = 0.0;
-        for (OffT k = start + sub; k < end; k += LANES) sum += sb_ld_stream(val + k) * __ldg(x + sb_ld_stream(col + k));
+        for (OffT k = start + sub; k < end; k += LANES * VEC_UNROLL) {
+            // issue all loads of the trip before the first use: VEC_UNROLL independent chains
+            int c[VEC_UNROLL];
+            double a[VEC_UNROLL];
+#pragma unroll
+            for (int q = 0; q < VEC_UNROLL; ++q) {
+                const OffT kk = k + q * LANES;
+                const bool in = kk < end;
+                c[q] = in ? sb_ld_stream(col + kk) : 0;
+                a[q] = in ? sb_ld_stream(val + kk) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < VEC_UNROLL; ++q) sum += a[q] * __ldg(x + c[q]);
+        }
 #pragma unroll
         for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         // lane j = t*G + g' wants the sum of group g' = j % G
@@ -105,7 +122,7 @@ spmv_stream_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict
     const int r0 = blk_row[blockIdx.x];
     const int r1 = blk_row[blockIdx.x + 1];
     const int nrows = r1 - r0;  // <= ROWS
-    if (tid <= nrows) s_rp[tid] = rowptr[r0 + tid];
+    for (int i = tid; i <= nrows; i += STREAM_THREADS) s_rp[i] = rowptr[r0 + i];
     __syncthreads();
     const OffT base = s_rp[0];
     const OffT nnzb = s_rp[nrows] - base;
@@ -129,9 +146,23 @@ spmv_stream_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict
 
     // phase 1: products in storage order -- every load is a full coalesced line
     const int n = (int)nnzb;
-#pragma unroll 4
-    for (int k = tid; k < n; k += STREAM_THREADS)
-        s_prod[k] = sb_ld_stream(val + base + k) * __ldg(x + sb_ld_stream(col + base + k));
+    {
+        constexpr int U = STREAM_TILE / STREAM_THREADS;  // every thread's share of a full tile
+        int c[U];
+        double a[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {  // all loads of the tile in flight before the first use
+            const int k = tid + q * STREAM_THREADS;
+            const bool in = k < n;
+            c[q] = in ? sb_ld_stream(col + base + k) : 0;
+            a[q] = in ? sb_ld_stream(val + base + k) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            const int k = tid + q * STREAM_THREADS;
+            if (k < n) s_prod[k] = a[q] * __ldg(x + c[q]);
+        }
+    }
     __syncthreads();
 
     // phase 2: LPR lanes reduce one row's segment
@@ -160,6 +191,45 @@ spmv_stream_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict
             if (!sb_row_skipped(skip_mask, row)) sb_epilogue<EPI>(row, s_rowsum[tid], e);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// spmv_sell: sliced layout for short, regular rows (the 7-point level 0).  At upload the CSR
+// rows are regrouped in slices of 32 consecutive rows, each slice stored column-major and padded
+// to its longest row (val 0.0, col = the row's own last column), still FP64 values / int32
+// columns.  Lane t owns row t of the slice: the j-th entries of the 32 rows are one 256-byte and
+// one 128-byte line, every load of the loop is independent and fully coalesced, and for a
+// stencil the x gather is coalesced too (neighbour j of 32 consecutive rows = 32 consecutive x).
+// No shuffles, no shared memory; the epilogue streams are coalesced by construction.
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(256)
+spmv_sell_kernel(int M, const long long *__restrict__ slice_ptr, const int *__restrict__ col,
+                 const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
+                 const uint32_t *__restrict__ skip_mask) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int slice = row >> 5;
+    if ((slice << 5) >= M) return;
+    const long long base = slice_ptr[slice];
+    const int len = (int)((slice_ptr[slice + 1] - base) >> 5);
+    const int *cp = col + base + lane;
+    const double *vp = val + base + lane;
+    double sum = 0.0;
+    int j = 0;
+    for (; j + 4 <= len; j += 4) {
+        int c[4];
+        double a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            c[q] = sb_ld_stream(cp + (j + q) * 32);
+            a[q] = sb_ld_stream(vp + (j + q) * 32);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sum += a[q] * __ldg(x + c[q]);
+    }
+    for (; j < len; ++j) sum += sb_ld_stream(vp + j * 32) * __ldg(x + sb_ld_stream(cp + j * 32));
+    if (row < M && !sb_row_skipped(skip_mask, row)) sb_epilogue<EPI>(row, sum, e);
 }
 
 // ---------------------------------------------------------------------------------------------

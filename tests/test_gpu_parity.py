@@ -1,0 +1,214 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (saena_b200.native -> include/
+saena_b200.h), against (1) the golden vectors the reference wrote, (2) the CPU oracle on the same
+seeded inputs, (3) the compiled reference itself where oracle/_ref travelled with the snapshot.
+Tolerances are the north_star's: 1e-12 relative per SpMV / smoother sweep / transfer, iteration
+count +-1, residual-norm history 1e-9."""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from saena_b200.hierarchy import KIND_A, KIND_P, KIND_R, Hierarchy, Level, Operator
+from saena_b200.native import Context
+from tests.util import (GOLDEN, TOL_HIST, TOL_OP, Golden, check_ops_against_golden, check_pcg,
+                        check_vcycle_against_golden, rel)
+
+pytestmark = pytest.mark.gpu
+
+MAPPINGS = [0, 1, 2, 4, 8, 16, 32, -1, -2, -4, -8, -16, -32, 100]
+
+
+@pytest.fixture(scope="module", params=GOLDEN)
+def golden_ctx(request):
+    g = Golden(request.param)
+    ctx = Context()
+    ctx.upload_hierarchy(g.hier)
+    yield g, ctx
+    ctx.close()
+
+
+def test_ops_match_reference_golden(golden_ctx):
+    g, ctx = golden_ctx
+    check_ops_against_golden(ctx, g)
+
+
+def test_vcycle_matches_reference_golden(golden_ctx):
+    g, ctx = golden_ctx
+    check_vcycle_against_golden(ctx, g)
+
+
+def test_pcg_matches_reference_golden(golden_ctx):
+    g, ctx = golden_ctx
+    u, iters, hist = ctx.solve_pcg(g.rhs, g.max_iter, g.tol, "chebyshev", g.pre, g.post)
+    check_pcg(iters, hist, u, int(g["out.pcg.iters"][0]), g["out.pcg.hist"], g["out.pcg.u"])
+    A = g.hier.levels[0].A.to_scipy_local()
+    assert np.linalg.norm(A @ u - g.rhs) / np.linalg.norm(g.rhs) < g.tol
+    assert ctx.launch_count() > 0
+
+
+def test_every_kernel_mapping_gives_the_same_answer(golden_ctx):
+    g, ctx = golden_ctx
+    o = Oracle(g.hier)
+    rng = np.random.default_rng(11)
+    try:
+        for l, lv in enumerate(g.hier.levels):
+            v, b = rng.standard_normal(lv.A.M), rng.standard_normal(lv.A.M)
+            want_mv, want_sm = o.matvec(l, KIND_A, v), o.smooth(l, "chebyshev", 2, v, b)
+            for m in MAPPINGS:
+                ctx.set_mapping(l, KIND_A, m)
+                assert rel(ctx.matvec(l, KIND_A, v), want_mv) < TOL_OP, (l, m)
+                assert rel(ctx.smooth(l, "chebyshev", 2, v, b), want_sm) < TOL_OP, (l, m)
+            if lv.P is not None:
+                vc = rng.standard_normal(lv.P.n_local_cols)
+                for m in MAPPINGS:
+                    ctx.set_mapping(l, KIND_P, m)
+                    ctx.set_mapping(l, KIND_R, m)
+                    assert rel(ctx.matvec(l, KIND_P, vc), o.matvec(l, KIND_P, vc)) < TOL_OP, (l, m)
+                    assert rel(ctx.matvec(l, KIND_R, v), o.matvec(l, KIND_R, v)) < TOL_OP, (l, m)
+    finally:
+        for l, lv in enumerate(g.hier.levels):
+            for k in (KIND_A, KIND_P, KIND_R):
+                if k == KIND_A or lv.P is not None:
+                    ctx.set_mapping(l, k, 0)
+
+
+def test_other_solvers_and_option_sets_against_oracle(golden_ctx):
+    g, ctx = golden_ctx
+    o = Oracle(g.hier)
+    # jacobi smoother, asymmetric sweeps, iteration cap (the `i == max_iter` exit)
+    u_o, it_o, h_o = o.solve_pcg(g.rhs, 3, 1e-14, "jacobi", 2, 1)
+    u, it, h = ctx.solve_pcg(g.rhs, 3, 1e-14, "jacobi", 2, 1)
+    assert it == it_o == 3
+    check_pcg(it, h, u, it_o, h_o, u_o)
+    # no pre-smoothing / no post-smoothing
+    for pre, post in ((0, 2), (2, 0)):
+        u_o, it_o, h_o = o.solve_pcg(g.rhs, 50, 1e-8, "chebyshev", pre, post)
+        u, it, h = ctx.solve_pcg(g.rhs, 50, 1e-8, "chebyshev", pre, post)
+        check_pcg(it, h, u, it_o, h_o, u_o)
+    # saena_object::solve (stationary V-cycles)
+    u_o, it_o, h_o = o.solve_vcycle(g.rhs, 50, 1e-8)
+    u, it, h = ctx.solve_vcycle(g.rhs, 50, 1e-8)
+    check_pcg(it, h, u, it_o, h_o, u_o)
+    # saena_object::solve_CG (unpreconditioned): must converge to the same solution
+    u_cg, it_cg, h_cg = ctx.solve_cg(g.rhs, 2000, 1e-10)
+    assert h_cg[-1] / h_cg[0] < 1e-10
+    assert rel(u_cg, u_o) < 1e-6
+
+
+def _random_csr(rng, n_rows, n_cols, row_nnz):
+    counts = np.asarray(row_nnz, np.int32)
+    cols = np.concatenate([np.sort(rng.choice(n_cols, c, replace=False)) for c in counts]) if counts.sum() else \
+        np.zeros(0, np.int64)
+    return counts, cols.astype(np.int32), rng.uniform(-1, 1, counts.sum())
+
+
+def _two_level(rng, A_counts, A_cols, A_vals, n, nc=40):
+    """a syntactically valid 2-level hierarchy around an arbitrary level-0 operator"""
+    def op(kind, level, M, N, counts, cols, vals):
+        return Operator(kind=kind, level=level, M=M, Mbig=M, Nbig=N, row_offset=0, col_offset=0, n_local_cols=N,
+                        nnzPerRow_local=counts, col_local=cols, val_local=vals)
+    pc, pcol, pv = _random_csr(rng, n, nc, rng.integers(0, 4, n))
+    rc, rcol, rv = _random_csr(rng, nc, n, rng.integers(0, 30, nc))
+    dense = rng.uniform(-1, 1, (nc, nc)) + nc * np.eye(nc)
+    cr, cc = np.nonzero(dense)
+    lv0 = Level(0, op(KIND_A, 0, n, n, A_counts, A_cols, A_vals), inv_diag=rng.uniform(0.5, 1.5, n), eig_max=1.7,
+                P=op(KIND_P, 0, n, nc, pc, pcol, pv), R=op(KIND_R, 0, nc, n, rc, rcol, rv), M_coarse_old=nc,
+                M_coarse=nc)
+    lv1 = Level(1, op(KIND_A, 1, nc, nc, np.full(nc, nc, np.int32), np.tile(np.arange(nc, dtype=np.int32), nc),
+                      dense.ravel()), inv_diag=1.0 / np.diag(dense), eig_max=1.5)
+    return Hierarchy([lv0, lv1], coarse_n=nc, coarse_row=cr.astype(np.int32), coarse_col=cc.astype(np.int32),
+                     coarse_val=dense[cr, cc])
+
+
+@pytest.mark.parametrize("case", ["ragged", "empty_rows", "one_long_row", "dense_rows", "single_row"])
+def test_edge_case_row_shapes(case):
+    """ragged rows, empty rows, a row longer than the streaming tile, wide rows -- every mapping"""
+    rng = np.random.default_rng(99)
+    n = {"single_row": 1}.get(case, 3000)
+    if case == "ragged":
+        nnz = rng.integers(0, 70, n)
+    elif case == "empty_rows":
+        nnz = np.where(rng.random(n) < 0.6, 0, rng.integers(1, 9, n))
+    elif case == "one_long_row":
+        nnz = rng.integers(1, 8, n)
+        nnz[[0, 1500, n - 1]] = [2900, 2500, 2100]   # > STREAM_TILE (2048)
+    elif case == "dense_rows":
+        nnz = np.full(n, 300)
+    else:
+        nnz = np.array([1])
+    counts, cols, vals = _random_csr(rng, n, n, nnz)
+    h = _two_level(rng, counts, cols, vals, n)
+    o = Oracle(h)
+    ctx = Context()
+    try:
+        ctx.upload_hierarchy(h)
+        v, b = rng.standard_normal(n), rng.standard_normal(n)
+        want, want_res = o.matvec(0, KIND_A, v), o.residual(0, v, b)
+        want_cheb, want_jac = o.smooth(0, "chebyshev", 3, v, b), o.smooth(0, "jacobi", 2, v, b)
+        scale = np.linalg.norm(want) or 1.0
+        for m in MAPPINGS:
+            ctx.set_mapping(0, KIND_A, m)
+            assert np.linalg.norm(ctx.matvec(0, KIND_A, v) - want) <= TOL_OP * scale, (case, m)
+            assert rel(ctx.residual(0, v, b), want_res) < TOL_OP, (case, m)
+            assert rel(ctx.smooth(0, "chebyshev", 3, v, b), want_cheb) < TOL_OP, (case, m)
+            assert rel(ctx.smooth(0, "jacobi", 2, v, b), want_jac) < TOL_OP, (case, m)
+        vc = rng.standard_normal(40)
+        assert rel(ctx.matvec(0, KIND_P, vc), o.matvec(0, KIND_P, vc)) < TOL_OP
+        assert rel(ctx.matvec(0, KIND_R, v), o.matvec(0, KIND_R, v)) < TOL_OP
+        assert rel(ctx.vcycle(0, v, b), o.vcycle(0, v, b)) < 1e-11
+    finally:
+        ctx.close()
+
+
+def test_dot_and_linearity_properties():
+    g = Golden(GOLDEN[1])
+    ctx = Context()
+    try:
+        ctx.upload_hierarchy(g.hier)
+        rng = np.random.default_rng(1)
+        n = g.hier.levels[0].A.M
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        a = 0.37
+        lin = ctx.matvec(0, KIND_A, a * x + y)
+        assert rel(lin, a * ctx.matvec(0, KIND_A, x) + ctx.matvec(0, KIND_A, y)) < 1e-13
+        # R = P^T (restrict_matrix.cpp:116-121): <R x, z> == <x, P z>
+        z = rng.standard_normal(g.hier.levels[0].P.n_local_cols)
+        lhs = float(ctx.matvec(0, KIND_R, x) @ z)
+        rhs = float(x @ ctx.matvec(0, KIND_P, z))
+        assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+        big = rng.standard_normal(3_000_001)
+        assert abs(ctx.dot(big, big) - float(big @ big)) <= 1e-12 * float(big @ big)
+        assert ctx.dot(np.zeros(0), np.zeros(0)) == 0.0
+    finally:
+        ctx.close()
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("mx", [20, 34])
+def test_cuda_vs_compiled_reference_same_process_same_hierarchy(mx):
+    """BASELINE.json configs[0] (Poisson 32^3, via experiments/Poisson.cpp's sequence) and a smaller
+    one: reference setup on the host, hierarchy uploaded once, then both solve on the same
+    hierarchy object in this process."""
+    from oracle import ref
+    s = ref.RefSolver.poisson(mx)
+    ctx = Context()
+    try:
+        h = s.hierarchy()
+        ctx.upload_hierarchy(h)
+        rng = np.random.default_rng(2)
+        for l, lv in enumerate(h.levels):
+            v, b = rng.standard_normal(lv.A.M), rng.standard_normal(lv.A.M)
+            assert rel(ctx.matvec(l, KIND_A, v), s.matvec(l, KIND_A, v)) < TOL_OP
+            assert rel(ctx.smooth(l, "chebyshev", 3, v, b), s.smooth(l, "chebyshev", 3, v, b)) < TOL_OP
+            assert rel(ctx.smooth(l, "jacobi", 1, v, b), s.smooth(l, "jacobi", 1, v, b)) < TOL_OP
+            if lv.P is not None:
+                vc = rng.standard_normal(lv.P.n_local_cols)
+                assert rel(ctx.matvec(l, KIND_P, vc), s.matvec(l, KIND_P, vc)) < TOL_OP
+                assert rel(ctx.matvec(l, KIND_R, v), s.matvec(l, KIND_R, v)) < TOL_OP
+            assert rel(ctx.vcycle(l, np.zeros(lv.A.M), b), s.vcycle(l, np.zeros(lv.A.M), b)) < 1e-11
+        u_ref, it_ref, hist_ref = s.solve_pcg()
+        u, it, hist = ctx.solve_pcg(s.rhs(), s.opts.max_iter, s.opts.tol, "chebyshev", s.opts.pre, s.opts.post)
+        assert it == it_ref
+        check_pcg(it, hist, u, it_ref, hist_ref, u_ref, TOL_HIST)
+    finally:
+        ctx.close()
+        s.close()

@@ -1,0 +1,94 @@
+"""The tensor-op restatement of the reference's SA setup (saena_b200/sa_setup.py -- used only to
+feed the bench and large tests) against the reference's own hierarchy, and its device-side row
+partitioner against the numpy one."""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from saena_b200.hierarchy import partition_hierarchy
+from saena_b200.sa_setup import (SetupOptions, build_device_hierarchy, build_hierarchy, poisson3d_coo,
+                                 poisson3d_rhs)
+from tests.util import GOLDEN, Golden, rel
+
+
+def _same_operator(a, b, tol=1e-13):
+    assert (a.M, a.Nbig, a.nnz_local, a.nnz_remote) == (b.M, b.Nbig, b.nnz_local, b.nnz_remote)
+    assert np.array_equal(a.nnzPerRow_local, b.nnzPerRow_local)
+    assert np.array_equal(a.col_local, b.col_local)
+    assert np.max(np.abs(a.val_local - b.val_local)) <= tol * np.max(np.abs(b.val_local))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_setup_reproduces_the_reference_hierarchy_in_the_golden_file(name):
+    g = Golden(name)
+    n = round(g.hier.levels[0].A.M ** (1 / 3))
+    h = build_hierarchy(*poisson3d_coo(n), device="cpu")
+    assert len(h.levels) == len(g.hier.levels)
+    for a, b in zip(h.levels, g.hier.levels):
+        _same_operator(a.A, b.A)
+        assert rel(a.inv_diag, b.inv_diag) < 1e-13
+        assert abs(a.eig_max - b.eig_max) < 2e-2 * b.eig_max   # the reference's own Lanczos start is random
+        assert a.A.use_double == b.A.use_double
+        if b.P is not None:
+            _same_operator(a.P, b.P)
+            _same_operator(a.R, b.R)
+            assert a.P.use_double == b.P.use_double
+    assert rel(poisson3d_rhs(n), g.rhs) < 1e-13
+
+
+@pytest.mark.ref
+def test_setup_reproduces_the_live_reference_at_32_cubed():
+    from oracle import ref
+    s = ref.RefSolver.poisson(34)
+    try:
+        href = s.hierarchy()
+        h = build_hierarchy(*poisson3d_coo(32), device="cpu")
+        assert len(h.levels) == len(href.levels)
+        for a, b in zip(h.levels, href.levels):
+            _same_operator(a.A, b.A)
+            if b.P is not None:
+                _same_operator(a.P, b.P)
+                _same_operator(a.R, b.R)
+        # and the solve on it behaves like the reference's: same iteration count
+        u, it, hist = Oracle(h).solve_pcg(poisson3d_rhs(32))
+        u_ref, it_ref, hist_ref = s.solve_pcg()
+        assert abs(it - it_ref) <= 1 and rel(u, u_ref) < 1e-6
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("nprocs,agg", [(1, 0), (2, 0), (3, 200), (4, 10**9)])
+def test_device_partitioner_matches_numpy_partitioner(nprocs, agg):
+    dh = build_device_hierarchy(*poisson3d_coo(10), device="cpu")
+    one = dh.to_rank(0, 1)
+    want = partition_hierarchy(one, nprocs, agglomerate_below=agg) if nprocs > 1 else [one]
+    for r in range(nprocs):
+        got = dh.to_rank(r, nprocs, agglomerate_below=agg)
+        assert len(got.levels) == len(want[r].levels)
+        for a, b in zip(got.levels, want[r].levels):
+            for name in ("A", "P", "R"):
+                x, y = getattr(a, name), getattr(b, name)
+                if y is None:
+                    assert x is None
+                    continue
+                for f in ("nnzPerRow_local", "col_local", "val_local", "row_remote", "val_remote", "nnzPerCol_remote",
+                          "vIndex", "sendProcRank", "sendProcCount", "recvProcRank", "recvProcCount"):
+                    assert np.array_equal(getattr(x, f), getattr(y, f)), (r, a.level, name, f)
+                if nprocs > 1:
+                    assert np.array_equal(x.vdispls, y.vdispls) and np.array_equal(x.rdispls, y.rdispls)
+                assert (x.M, x.col_offset, x.n_local_cols, x.use_double) == (y.M, y.col_offset, y.n_local_cols, y.use_double)
+            assert a.repart_send == b.repart_send and a.repart_recv == b.repart_recv
+            assert (a.M_coarse_old, a.M_coarse) == (b.M_coarse_old, b.M_coarse)
+            assert np.array_equal(a.inv_diag, b.inv_diag)
+
+
+def test_nonsymmetric_strength_and_filter_edge_cases():
+    # positive off-diagonals are not strong; a row with only a diagonal becomes its own aggregate
+    n = 6
+    row = np.array([0, 0, 1, 1, 1, 2, 2, 3, 4, 4, 5, 5])
+    col = np.array([0, 1, 0, 1, 2, 1, 2, 3, 4, 5, 4, 5])
+    val = np.array([2., -1, -1, 2, 0.5, 0.5, 2, 1, 2, -1, -1, 2])
+    h = build_hierarchy(n, row, col, val, SetupOptions(least_row_threshold=1), device="cpu")
+    P = h.levels[0].P.to_scipy_local().toarray()
+    assert P.shape[0] == 6 and np.all(np.abs(P).sum(1) > 0)
+    assert h.levels[1].A.M == P.shape[1] < 6
