@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- AMG-PCG solve of the 3D 7-point Poisson problem on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 256]
+
+A "step" is one complete `solve_pCG` (zero initial guess, AMG V-cycle preconditioner with 3+3
+Chebyshev sweeps, stop at ||r||/||r0|| < 1e-8: the reference's experiments/Poisson.cpp loop with
+data/options006_poisson.xml) on synthetic data: the 256^3-unknown Poisson operator and the
+sin*sin*sin right-hand side of laplacian3D_set_rhs.  The hierarchy is built once, untimed (setup is
+outside the hot path; saena_b200/sa_setup.py restates the reference's setup so the hierarchy has
+the reference's shape), uploaded once, and stays resident in HBM.
+
+Printed JSON line (rank 0): `value` = unknowns solved per second, whole job, inputs resident in
+HBM, CUDA events on the library's compute stream, max over ranks; `e2e` = the same through the
+host-buffer entry point (pinned host rhs -> H2D -> solve -> D2H u inside the timed region);
+`roofline` = the dominant kernel's algorithmic bytes / its CUDA-event duration against the
+measured HBM peak; `cpu_baseline` = the reference's own CPU solve (oracle/_ref, the compiled
+reference) on a bounded sample.  `--impl reference` times only that CPU arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "AMG-PCG solve throughput, 3D 7-pt Poisson, rel. residual 1e-8 (unknowns solved per second)"
+UNIT = "Munknowns/s"
+OPTS = dict(max_iter=50, tol=1e-8, smoother="chebyshev", pre=3, post=3)   # data/options006_poisson.xml
+CPU_SAMPLE_MX = 50                                                         # reference arm: 48^3 unknowns
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy bandwidth)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.path = device, None, f"/tmp/saena_bench_clocks_{os.getpid()}.csv"
+
+    def __enter__(self):
+        try:
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.out,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.out.close()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 6:
+                    continue
+                sm.append(float(f[0])); mx.append(float(f[1]))
+                for n, v in zip(names, f[2:6]):
+                    if v == "Active":
+                        reasons.add(n)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm: the reference's own CPU implementation (compiled from /root/reference into
+# oracle/_ref by oracle/Makefile), one MPI rank = one core (no MPI in this image; the reference's
+# OpenMP is off by default, CMakeLists.txt:27).  Falls back to the C oracle port.
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_solve(reps: int, warmup: int = 0, mx: int = CPU_SAMPLE_MX):
+    from oracle import ref
+    n = (mx - 2) ** 3
+    if ref.available():
+        t = time.perf_counter()
+        s = ref.RefSolver.poisson(mx)
+        setup_s = time.perf_counter() - t
+        u, iters, hist = s.solve_pcg()
+        for _ in range(warmup):
+            s.time_solve_pcg(1)
+        sec = s.time_solve_pcg(reps) / reps
+        s.close()
+        kind = "reference"
+        what = (f"the reference's own solve_pCG (oracle/_ref = unmodified paralab/Saena sources, -Ofast, 1 MPI rank) "
+                f"on 3D Poisson {mx - 2}^3 = {n} unknowns (laplacian3D mx={mx}), same options; {reps} solves, "
+                f"{iters} iterations each; host setup {setup_s:.1f} s not timed")
+    else:
+        from oracle.oracle import Oracle
+        from saena_b200.sa_setup import build_hierarchy, poisson3d_coo, poisson3d_rhs
+        h = build_hierarchy(*poisson3d_coo(mx - 2), device="cpu")
+        o, rhs = Oracle(h), poisson3d_rhs(mx - 2)
+        u, iters, hist = o.solve_pcg(rhs, **OPTS)
+        t = time.perf_counter()
+        for _ in range(reps):
+            o.solve_pcg(rhs, **OPTS)
+        sec = (time.perf_counter() - t) / reps
+        kind = "port"
+        what = (f"C restatement of the reference solve (oracle/saena_oracle.c) on 3D Poisson {mx - 2}^3 = {n} unknowns, "
+                f"same options; {reps} solves, {iters} iterations each")
+    return dict(value=n / sec / 1e6, unit=UNIT, cores=1, kind=kind, sample=what), sec, iters, n
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    base, sec, iters, n = cpu_reference_solve(max(args.steps, 1), args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D 7-point Poisson AMG-PCG, bounded sample {CPU_SAMPLE_MX - 2}^3 unknowns of the "
+                                   f"256^3 workload", "options": "data/options006_poisson.xml values"},
+            "iterations": iters, "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("SAENA_BENCH_N", 256)),
+                    help="unknowns per dimension (256 = BASELINE.json configs[1])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--agglomerate-below", type=int, default=200_000)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if args.warmup < 3:
+        log("warm-up raised to 3 (timing rules)")
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from saena_b200 import native
+    from saena_b200.distributed import exchange_nccl_id
+    from saena_b200.hierarchy import KIND_A, KIND_P, KIND_R
+    from saena_b200.sa_setup import build_device_hierarchy, poisson3d_coo, poisson3d_rhs
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the solve path has no CPU fallback")
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        nccl_id = exchange_nccl_id(native.nccl_unique_id)
+
+    # ---- setup (untimed): hierarchy of the reference's shape, built on this rank's GPU
+    n = args.n
+    t0 = time.perf_counter()
+    N, row, col, val = poisson3d_coo(n)
+    dh = build_device_hierarchy(N, row, col, val, verbose=(rank == 0 and bool(os.environ.get("SAENA_BENCH_VERBOSE"))))
+    del row, col, val
+    if rank == 0:
+        log(f"[setup] hierarchy built in {time.perf_counter() - t0:.1f}s\n{dh.summary()}")
+    hier = dh.to_rank(rank, world, agglomerate_below=args.agglomerate_below if world > 1 else 0)
+    del dh
+    torch.cuda.empty_cache()
+    ctx = native.Context(device=local, rank=rank, nranks=world, nccl_id=nccl_id)
+    ctx.upload_hierarchy(hier)
+    if rank == 0:
+        log(f"[setup] uploaded in {time.perf_counter() - t0:.1f}s total")
+    l0 = hier.levels[0].A
+    rhs_full = poisson3d_rhs(n)
+    rhs_host = torch.from_numpy(rhs_full[l0.row_offset:l0.row_offset + l0.M].copy()).pin_memory()
+    del rhs_full
+    u_host = torch.empty(l0.M, dtype=torch.float64).pin_memory()
+    rhs_dev = rhs_host.cuda()
+    u_dev = torch.zeros(l0.M, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up
+    iters = hist = None
+    for _ in range(args.warmup):
+        iters, hist = ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+    # ---- timed: K solves, inputs resident in HBM, CUDA events on the library's compute stream
+    launches0 = ctx.launch_count()
+    barrier()
+    with ClockSampler(local) as clocks:
+        ctx.timer_start()
+        for _ in range(args.steps):
+            iters, hist = ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+        ms_total = ctx.timer_stop()
+        barrier()
+    launches = ctx.launch_count() - launches0
+    ms_step = max_over_ranks(ms_total / args.steps)
+    clk = clocks.summary()
+
+    # ---- e2e: host buffers through the reference-facing entry point, copies inside the timed region
+    ctx._ck(ctx._L.saena_b200_solve_pcg(ctx._h, rhs_host.data_ptr(), u_host.data_ptr(), OPTS["max_iter"], OPTS["tol"],
+                                        1, OPTS["pre"], OPTS["post"], *_iters_hist_args()))
+    barrier()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        ctx._ck(ctx._L.saena_b200_solve_pcg(ctx._h, rhs_host.data_ptr(), u_host.data_ptr(), OPTS["max_iter"],
+                                            OPTS["tol"], 1, OPTS["pre"], OPTS["post"], *_iters_hist_args()))
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t) * 1e3 / args.steps)
+
+    # ---- check the answer we timed: ||A u - rhs|| / ||rhs|| through an independent route (torch)
+    rel_res = float(hist[-1] / hist[0])
+
+    # ---- per-level kernel table + roofline of the dominant kernel (CUDA events per launch)
+    peak, peak_src = measured_peaks()
+    levels_tbl, dominant = [], None
+    for l, lv in enumerate(hier.levels):
+        if lv.A.M == 0:
+            continue
+        a_bytes = ctx.operator_bytes(l, KIND_A)
+        # first Chebyshev sweep: 12 nnz + M*(4 + 8*[u gathered, rhs, inv_diag, d out, u out]) = SpMV + 24 M
+        sweep_bytes = a_bytes + 24 * lv.A.M
+        big = a_bytes > 300e6   # larger than L2: no flush needed; smaller levels are flushed between launches
+        ms_mv = ctx.time_matvec(l, KIND_A, 20, flush_l2=not big)
+        ms_sw = ctx.time_smooth_sweep(l, "chebyshev", 20, flush_l2=not big)
+        ent = {"level": l, "rows": lv.A.M, "nnz": lv.A.nnz, "mapping": ctx.get_mapping(l, KIND_A), "spmv_ms": ms_mv, "spmv_GBs": a_bytes / ms_mv / 1e6,
+               "cheb_sweep_ms": ms_sw, "cheb_sweep_GBs": sweep_bytes / ms_sw / 1e6,
+               "frac_of_peak": sweep_bytes / ms_sw / 1e6 / peak}
+        if lv.P is not None and lv.P.M:
+            ent["P_ms"] = ctx.time_matvec(l, KIND_P, 20, flush_l2=not big)
+            ent["R_ms"] = ctx.time_matvec(l, KIND_R, 20, flush_l2=not big)
+            ent["P_mapping"], ent["R_mapping"] = ctx.get_mapping(l, KIND_P), ctx.get_mapping(l, KIND_R)
+        levels_tbl.append(ent)
+        # share of a V-cycle: 5 fused sweeps + residual ~ 6 passes
+        if dominant is None or ms_sw * 5 > dominant[0]:
+            dominant = (ms_sw * 5, l, sweep_bytes, ms_sw)
+    _, dl, dbytes, dms = dominant
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"n{n}_level{dl}_cheb_sweep")
+    roofline = {"bound": "hbm", "achieved": dbytes / dms / 1e6, "peak": peak, "unit": "GB/s",
+                "frac": dbytes / dms / 1e6 / peak, "traffic": traffic,
+                "kernel": f"fused Chebyshev sweep (SpMV + update epilogue) on level {dl}", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dbytes, "launch_ms": dms}
+
+    total_unknowns = n ** 3
+    line = {"metric": METRIC, "value": total_unknowns / (ms_step / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D 7-point Poisson {n}^3 = {total_unknowns} unknowns, AMG-PCG to 1e-8 "
+                                   f"(BASELINE.json configs[1] at n=256)",
+                       "options": "options006_poisson.xml: chebyshev 3+3, conn_str 0.2, float_level 0, max_iter 50",
+                       "levels": len(hier.levels), "partition": f"{world} row block(s), nnz-balanced",
+                       "l2": "inputs larger than L2 (level-0/1 operators are GBs); per-kernel timings of "
+                             "L2-sized levels flush L2 between launches"},
+            "solve_s": ms_step / 1e3, "iterations": iters, "rel_residual": rel_res,
+            "e2e": {"value": total_unknowns / (e2e_ms / 1e3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 8 * total_unknowns, "d2h_bytes_per_step": 8 * total_unknowns,
+                    "timer": "wall clock between device synchronisations (host copies included)"},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "levels": levels_tbl}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"], _, cpu_iters, _ = cpu_reference_solve(5)
+            line["cpu_baseline"]["iterations"] = cpu_iters
+        except Exception as e:  # the bench line must still come out
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(e)}
+    ctx.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _iters_hist_args():
+    import ctypes
+    it, n = ctypes.c_int(0), ctypes.c_int(0)
+    hist = (ctypes.c_double * 64)()
+    _iters_hist_args.keep = (it, n, hist)
+    return ctypes.byref(it), hist, 64, ctypes.byref(n)
+
+
+if __name__ == "__main__":
+    main()

@@ -140,12 +140,20 @@ int saena_b200_dot(saena_b200_ctx *ctx, const double *a, const double *b, int n,
 int saena_b200_time_matvec(saena_b200_ctx *ctx, int level, int kind, int reps, int flush_l2, float *ms_out);
 int saena_b200_time_smooth_sweep(saena_b200_ctx *ctx, int level, int smoother, int reps, int flush_l2,
                                  float *ms_out);
+/* CUDA-event stopwatch on the context's compute stream (the stream every kernel of this library
+ * is launched on): start records an event, stop records a second one, waits for it and returns
+ * the device time between them. */
+int saena_b200_timer_start(saena_b200_ctx *ctx);
+int saena_b200_timer_stop(saena_b200_ctx *ctx, float *ms_out);
 /* kernels launched by this context since init (bench.py's gpu_launches) */
 int64_t saena_b200_launch_count(const saena_b200_ctx *ctx);
 /* Force one operator's SpMV row mapping (tuning / profiling / tests): 0 = heuristic from nnz/row;
- * 1..32 = that many lanes per row; -1..-32 = streaming row blocks with that many lanes per row in
- * the reduce phase; 100 = sliced layout (32-row slices, column-major, one lane per row). */
+ * 1..16 = that many lanes per row, 32 rows per warp; 32..256 = that many threads per row, one row
+ * per thread group; -1..-32 = streaming row blocks with that many lanes per row in the reduce
+ * phase; 100 = sliced layout (32-row slices, column-major, one lane per row). */
 int saena_b200_set_mapping(saena_b200_ctx *ctx, int level, int kind, int mapping);
+/* the mapping in use (same codes) */
+int saena_b200_get_mapping(const saena_b200_ctx *ctx, int level, int kind);
 /* algorithmic bytes of one application of an operator (SURVEY.md 8d formula), for the roofline */
 int64_t saena_b200_operator_bytes(const saena_b200_ctx *ctx, int level, int kind);
 

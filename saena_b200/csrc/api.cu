@@ -226,10 +226,9 @@ int saena_b200_finalize(saena_b200_ctx *ctx) {
         SB_TRY(sb_prepare_operator(ctx, lv.P));
         SB_TRY(sb_prepare_operator(ctx, lv.R));
     }
-    if (ctx->levels[L - 1].M > 0 && ctx->coarse_n != ctx->levels[L - 1].M && L > 0) {
-        // the rank that owns the coarsest rows must hold the whole coarsest operator
-        SB_FAIL("finalize: coarsest factor missing or its size differs from the coarsest level's rows");
-    }
+    if (ctx->coarse_n != 0 && ctx->levels[L - 1].M > 0 && ctx->coarse_n != ctx->levels[L - 1].M)
+        SB_FAIL("finalize: the coarsest factor's size differs from the coarsest level's rows");
+    // (no factor at all is accepted: a lone operator uploaded for matvec only; any V-cycle then fails loudly)
     const int n0 = ctx->levels[0].M;
     cudaFree(ctx->pcg_r); cudaFree(ctx->pcg_p); cudaFree(ctx->pcg_h); cudaFree(ctx->pcg_u); cudaFree(ctx->pcg_rhs);
     SB_TRY(alloc_d(ctx, &ctx->pcg_r, n0));
@@ -578,6 +577,23 @@ int saena_b200_time_smooth_sweep(saena_b200_ctx *ctx, int level, int smoother, i
     return 0;
 }
 
+int saena_b200_timer_start(saena_b200_ctx *ctx) {
+    if (!ctx) return 1;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+    return 0;
+}
+
+int saena_b200_timer_stop(saena_b200_ctx *ctx, float *ms_out) {
+    if (!ctx) return 1;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    SB_CUDA(cudaEventSynchronize(ctx->ev_t1));
+    SB_CUDA(cudaEventElapsedTime(ms_out, ctx->ev_t0, ctx->ev_t1));
+    return 0;
+}
+
 int64_t saena_b200_launch_count(const saena_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int saena_b200_set_mapping(saena_b200_ctx *ctx, int level, int kind, int mapping) {
@@ -587,6 +603,14 @@ int saena_b200_set_mapping(saena_b200_ctx *ctx, int level, int kind, int mapping
     if (!op) SB_FAIL("set_mapping: no such operator");
     op->forced_mapping = mapping;
     return sb_prepare_operator(ctx, *op);
+}
+
+int saena_b200_get_mapping(const saena_b200_ctx *ctx, int level, int kind) {
+    if (!ctx || level < 0 || level >= (int)ctx->levels.size()) return 0;
+    const DevLevel &lv = ctx->levels[level];
+    const DevOperator &op = kind == SAENA_B200_KIND_A ? lv.A : (kind == SAENA_B200_KIND_P ? lv.P : lv.R);
+    if (!op.present) return 0;
+    return op.use_sell ? SB_MAPPING_SELL : (op.use_stream ? -op.lanes : op.lanes);
 }
 
 int64_t saena_b200_operator_bytes(const saena_b200_ctx *ctx, int level, int kind) {

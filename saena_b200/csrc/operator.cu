@@ -174,7 +174,11 @@ void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op) {
         // padding is small (7-pt Poisson 5.9 TB/s vs 5.6 best sub-warp; band 61/row 6.8 vs 5.3)
         const bool regular = op.nnz_local > 0 && double(op.sell_padded_est) <= 1.20 * double(op.nnz_local);
         if (regular) m = SB_MAPPING_SELL;
-        else m = pow2_at_most(std::max(1.0, (avg + 1.0) / 4.0));
+        else {
+            // ~4+ elements per lane; rows of hundreds..thousands of entries get 32..256 threads
+            m = 1;
+            while (m * 2 <= (avg + 1.0) / 4.0 && m < 256) m *= 2;
+        }
     }
     op.use_stream = op.use_sell = false;
     if (m == SB_MAPPING_SELL) {
@@ -184,7 +188,9 @@ void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op) {
         op.use_stream = true;
         op.lanes = std::min(32, std::max(1, pow2_at_most(-m)));
     } else {
-        op.lanes = std::min(32, std::max(1, pow2_at_most(m)));
+        int l = 1;
+        while (l * 2 <= m && l < 256) l *= 2;
+        op.lanes = l;
     }
 }
 
@@ -298,6 +304,16 @@ static void launch_local(saena_b200_ctx *ctx, DevOperator &op, const double *x, 
             SB_STREAM_CASE(16) SB_STREAM_CASE(32)
 #undef SB_STREAM_CASE
         }
+    } else if (op.lanes >= 32) {
+        switch (op.lanes) {
+#define SB_RG_CASE(T)                                                                              \
+    case T:                                                                                        \
+        spmv_rowgroup_kernel<T, EPI, OffT><<<(op.M + 256 / T - 1) / (256 / T), 256, 0, s>>>(       \
+            op.M, rp, op.col, op.val, x, e, op.brow_mask);                                         \
+        break;
+            SB_RG_CASE(32) SB_RG_CASE(64) SB_RG_CASE(128) SB_RG_CASE(256)
+#undef SB_RG_CASE
+        }
     } else {
         const int blocks = (op.M + 255) / 256;  // 8 warps x 32 rows
         switch (op.lanes) {
@@ -306,7 +322,7 @@ static void launch_local(saena_b200_ctx *ctx, DevOperator &op, const double *x, 
         spmv_vec_kernel<L, EPI, OffT><<<blocks, 256, 0, s>>>(op.M, rp, op.col, op.val, x, e,       \
                                                              op.brow_mask);                        \
         break;
-            SB_VEC_CASE(1) SB_VEC_CASE(2) SB_VEC_CASE(4) SB_VEC_CASE(8) SB_VEC_CASE(16) SB_VEC_CASE(32)
+            SB_VEC_CASE(1) SB_VEC_CASE(2) SB_VEC_CASE(4) SB_VEC_CASE(8) SB_VEC_CASE(16)
 #undef SB_VEC_CASE
         }
     }

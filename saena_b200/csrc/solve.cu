@@ -86,7 +86,10 @@ int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const
     DevLevel &lv = ctx->levels[l];
     // solve.cpp:991-1057 coarsest level: direct solve on the rank that owns it
     if (l == max_level) {
-        if (lv.M > 0) SB_TRY(sb_coarsest_apply(ctx, rhs, lv.u[lv.cur]));
+        if (lv.M > 0) {
+            if (ctx->coarse_n != lv.M) SB_FAIL("vcycle: no coarsest factor was uploaded for the coarsest level");
+            SB_TRY(sb_coarsest_apply(ctx, rhs, lv.u[lv.cur]));
+        }
         return 0;
     }
     DevLevel &cl = ctx->levels[l + 1];

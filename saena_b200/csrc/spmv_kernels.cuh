@@ -10,7 +10,8 @@
 // Three row mappings, chosen per operator from nnz/row and row-length regularity (sb_choose_mapping):
 //   spmv_sell          32-row slices stored column-major (padded per slice): lane = row, every load
 //                      coalesced and independent.  Short regular rows (the 7-point level 0).
-//   spmv_vec<LANES>    LANES (1..32) lanes cooperate on a row, a warp owns 32 consecutive rows
+//   spmv_rowgroup<TPR> 32..256 threads per row: the deep coarse levels (thousands of nnz per row)
+//   spmv_vec<LANES>    LANES (1..16) lanes cooperate on a row, a warp owns 32 consecutive rows
 //                      and results are transposed so lane j finishes row j: the epilogue's
 //                      vector streams (rhs, inv_diag, d, u) are read and written fully coalesced.
 //   spmv_stream<LPR>   a CTA owns a block of consecutive rows holding <= STREAM_TILE non-zeros;
@@ -104,6 +105,55 @@ spmv_vec_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict__ 
         if (lane / G == t) mine = v;
     }
     if (my_row < M && !sb_row_skipped(skip_mask, my_row)) sb_epilogue<EPI>(my_row, mine, e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// spmv_rowgroup: TPR = 32..256 threads per row, 256/TPR rows per CTA.  For the deep coarse levels
+// of a smoothed-aggregation hierarchy: a few thousand rows with thousands of non-zeros each
+// (256^3 Poisson: level 4 has 21 466 rows x 3025 nnz/row).  One row per warp-group keeps all SMs
+// busy where the 32-rows-per-warp mapping above would leave most of the chip idle.
+// ---------------------------------------------------------------------------------------------
+template <int TPR, int EPI, typename OffT>
+__global__ void __launch_bounds__(256)
+spmv_rowgroup_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+                     const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
+                     const uint32_t *__restrict__ skip_mask) {
+    constexpr int ROWS = 256 / TPR;
+    constexpr int WPR = TPR / 32;  // warps per row
+    __shared__ double s_part[8];
+    const int g = threadIdx.x / TPR, sub = threadIdx.x % TPR;
+    const int row = blockIdx.x * ROWS + g;
+    double sum = 0.0;
+    if (row < M) {
+        const OffT start = rowptr[row], end = rowptr[row + 1];
+        for (OffT k = start + sub; k < end; k += TPR * VEC_UNROLL) {
+            int c[VEC_UNROLL];
+            double a[VEC_UNROLL];
+#pragma unroll
+            for (int q = 0; q < VEC_UNROLL; ++q) {
+                const OffT kk = k + q * TPR;
+                const bool in = kk < end;
+                c[q] = in ? sb_ld_stream(col + kk) : 0;
+                a[q] = in ? sb_ld_stream(val + kk) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < VEC_UNROLL; ++q) sum += a[q] * __ldg(x + c[q]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (WPR == 1) {
+        if (sub == 0 && row < M && !sb_row_skipped(skip_mask, row)) sb_epilogue<EPI>(row, sum, e);
+    } else {
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
+        __syncthreads();
+        if (sub == 0 && row < M && !sb_row_skipped(skip_mask, row)) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) tot += s_part[g * WPR + w];
+            sb_epilogue<EPI>(row, tot, e);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

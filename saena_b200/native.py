@@ -76,9 +76,12 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_dot.argtypes = [vp, vp, vp, i, dp]
     L.saena_b200_time_matvec.argtypes = [vp, i, i, i, i, ctypes.POINTER(ctypes.c_float)]
     L.saena_b200_time_smooth_sweep.argtypes = [vp, i, i, i, i, ctypes.POINTER(ctypes.c_float)]
+    L.saena_b200_timer_start.argtypes = [vp]
+    L.saena_b200_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.saena_b200_launch_count.restype = ctypes.c_int64
     L.saena_b200_launch_count.argtypes = [vp]
     L.saena_b200_set_mapping.argtypes = [vp, i, i, i]
+    L.saena_b200_get_mapping.argtypes = [vp, i, i]
     L.saena_b200_operator_bytes.restype = ctypes.c_int64
     L.saena_b200_operator_bytes.argtypes = [vp, i, i]
     _lib = L
@@ -91,7 +94,7 @@ EXPORTED_SYMBOLS = [
     "saena_b200_finalize", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
-    "saena_b200_time_smooth_sweep", "saena_b200_launch_count", "saena_b200_set_mapping",
+    "saena_b200_time_smooth_sweep", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_set_mapping", "saena_b200_get_mapping",
     "saena_b200_operator_bytes",
 ]
 
@@ -288,6 +291,14 @@ class Context:
                                                       ctypes.byref(ms)))
         return ms.value
 
+    def timer_start(self):
+        self._ck(self._L.saena_b200_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = ctypes.c_float(0)
+        self._ck(self._L.saena_b200_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
+
     def launch_count(self) -> int:
         return int(self._L.saena_b200_launch_count(self._h))
 
@@ -295,6 +306,9 @@ class Context:
         """mapping > 0: that many lanes per row (sub-warp mapping); < 0: streaming row blocks with
         -mapping lanes per row in the reduce phase; 0: heuristic from nnz/row."""
         self._ck(self._L.saena_b200_set_mapping(self._h, level, kind, int(mapping)))
+
+    def get_mapping(self, level, kind) -> int:
+        return int(self._L.saena_b200_get_mapping(self._h, level, kind))
 
     def operator_bytes(self, level, kind) -> int:
         return int(self._L.saena_b200_operator_bytes(self._h, level, kind))

@@ -333,8 +333,6 @@ class DeviceHierarchy:
         # what the others ask of me: entries whose column I own and whose row I do not
         wanted = (M.col >= c0) & (M.col < c1) & ~mine
         dst = torch.searchsorted(rs, M.row[wanted], right=True) - 1
-        # empty ranks share a split value: searchsorted(right) lands on the last of them, which
-        # owns no rows; walk back to the rank whose block is non-empty and contains the row
         key = torch.unique(dst * M.n_cols + M.col[wanted])
         dst_u, col_u = key // M.n_cols, key % M.n_cols
         send_count = torch.bincount(dst_u, minlength=nprocs).cpu().numpy().astype(np.int32)

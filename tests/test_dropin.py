@@ -1,0 +1,37 @@
+"""The drop-in boundary end to end: the reference's own driver sequence (experiments/Poisson.cpp)
+through the unchanged saena.hpp API, with saena::amg::solve_pCG and saena::matrix::matvec resolved
+to saena_b200/adaptor/saena_b200_adaptor.cpp (GPU) and saena_object::solve_pCG run as the CPU
+reference on the SAME hierarchy object in the same process.  oracle/_ref/libsaena_dropin.so is
+built by `make -C oracle dropin` where /root/reference exists and travels with the snapshot."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import ITER_SLACK, TOL_HIST, TOL_OP
+
+pytestmark = [pytest.mark.gpu, pytest.mark.ref]
+
+LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libsaena_dropin.so")
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libsaena_dropin.so not built")
+@pytest.mark.parametrize("mx", [18, 34])   # 34 -> 32^3: BASELINE.json configs[0]
+def test_public_api_solve_pcg_on_gpu_matches_reference_cpu_solve(mx):
+    L = ctypes.CDLL(LIB)
+    cap = 64
+    hg, hc = np.zeros(cap), np.zeros(cap)
+    ig, ic, ng, nc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    du, dmv = ctypes.c_double(), ctypes.c_double()
+    dp = ctypes.POINTER(ctypes.c_double)
+    rc = L.dropin_poisson_check(mx, ctypes.byref(ig), ctypes.byref(ic), hg.ctypes.data_as(dp), ctypes.byref(ng),
+                                hc.ctypes.data_as(dp), ctypes.byref(nc), cap, ctypes.byref(du), ctypes.byref(dmv))
+    assert rc == 0
+    assert abs(ig.value - ic.value) <= ITER_SLACK
+    n = min(ng.value, nc.value)
+    assert n >= 3
+    assert np.max(np.abs(hg[:n] - hc[:n]) / hc[:n]) <= TOL_HIST
+    assert hg[ng.value - 1] / hg[0] < 1e-8
+    assert du.value < 1e-8
+    assert dmv.value < TOL_OP
