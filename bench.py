@@ -287,6 +287,31 @@ def main():
                 "kernel": f"fused Chebyshev sweep (SpMV + update epilogue) on level {dl}", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dbytes, "launch_ms": dms}
 
+    # whole-solve algorithmic bytes (SURVEY 8d formulas on the uploaded sizes) -> effective bandwidth
+    pre, post = OPTS["pre"], OPTS["post"]
+    vcycle_bytes = 0
+    for l, lv in enumerate(hier.levels[:-1]):
+        M = lv.A.M
+        a = ctx.operator_bytes(l, KIND_A)
+        vcycle_bytes += 32 * M                              # first pre-sweep from a zero iterate: rhs, inv_diag in; d, u out
+        vcycle_bytes += (pre - 1 + post) * (a + 32 * M)      # fused sweeps: SpMV + rhs, inv_diag, d in; d, u out
+        vcycle_bytes += a + 8 * M                            # residual
+        vcycle_bytes += ctx.operator_bytes(l, KIND_R)        # restriction
+        vcycle_bytes += ctx.operator_bytes(l, KIND_P) + 8 * M  # prolongation + correction (u read)
+    M0, a0 = hier.levels[0].A.M, ctx.operator_bytes(0, KIND_A)
+    krylov_bytes = a0 + 16 * M0 + 48 * M0 + 16 * M0 + 24 * M0  # h = A p, <p,h>, update + <r,r>, <r,rho>, p update
+    solve_bytes = (iters + 1) * vcycle_bytes + iters * krylov_bytes
+    solve_gbs = solve_bytes / ms_step / 1e6
+
+    halo = None
+    if world > 1:
+        full_ms, local_ms, halo_ms = ctx.time_matvec_parts(0, KIND_A, 20)
+        full_ms, local_ms, halo_ms = max_over_ranks(full_ms), max_over_ranks(local_ms), max_over_ranks(halo_ms)
+        halo = {"level": 0, "spmv_full_ms": full_ms, "spmv_local_only_ms": local_ms, "pack_exchange_only_ms": halo_ms,
+                "hidden_frac": max(0.0, min(1.0, 1.0 - (full_ms - local_ms) / halo_ms)) if halo_ms > 0 else None,
+                "ghost_values_per_rank": int(hier.levels[0].A.col_remote_size),
+                "ghost_dtype": "f64" if hier.levels[0].A.use_double else "f32 (float_level 0)"}
+
     total_unknowns = n ** 3
     line = {"metric": METRIC, "value": total_unknowns / (ms_step / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -298,10 +323,14 @@ def main():
                        "l2": "inputs larger than L2 (level-0/1 operators are GBs); per-kernel timings of "
                              "L2-sized levels flush L2 between launches"},
             "solve_s": ms_step / 1e3, "iterations": iters, "rel_residual": rel_res,
+            "solve_algorithmic_GB": solve_bytes / 1e9, "solve_effective_GBs": solve_gbs,
+            "solve_frac_of_hbm_peak": solve_gbs / peak,
             "e2e": {"value": total_unknowns / (e2e_ms / 1e3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 8 * total_unknowns, "d2h_bytes_per_step": 8 * total_unknowns,
                     "timer": "wall clock between device synchronisations (host copies included)"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "levels": levels_tbl}
+    if halo is not None:
+        line["halo_overlap"] = halo
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"], _, cpu_iters, _ = cpu_reference_solve(5)

@@ -97,11 +97,22 @@ int saena_b200_upload_level_aux(saena_b200_ctx *ctx, int level, const double *in
                                 int M_coarse_old, int M_coarse, int n_send, const saena_b200_block *send,
                                 int n_recv, const saena_b200_block *recv);
 
+/* Only for a hierarchy set up with scale=true (saena::amg::set_scale, saena::matrix::assemble(true)):
+ * D^-1/2 of each level's unscaled operator (saena_matrix::inv_sq_diag_orig).  The V-cycle scales
+ * the restricted residual and the coarse correction with the coarse level's vector
+ * (src/saena_object_solve.cpp:1245-1247, :1264-1266) and the solvers scale the final u with level
+ * 0's (:2709-2711).  Uploading it for level 0 switches the scaled path on. */
+int saena_b200_upload_level_scale(saena_b200_ctx *ctx, int level, const double *inv_sq_diag_orig);
+
 /* Coarsest operator as global COO (what setup_SuperLU passes on, saena_object_solve.cpp:282-308).
  * It is LU-factored on the host once and kept on the device as a dense factor; the rank that
  * owns the coarsest level's rows applies it (the others pass n = 0). */
 int saena_b200_upload_coarsest(saena_b200_ctx *ctx, int n, int64_t nnz, const int32_t *row, const int32_t *col,
                                const double *val);
+
+/* saena_object::direct_solver (include/saena_object.h:165): 0 = the direct solve (default, "SuperLU"
+ * in the reference, the dense factor here), 1 = solve_coarsest_CG (src/saena_object_solve.cpp:14-114). */
+int saena_b200_set_coarsest_solver(saena_b200_ctx *ctx, int use_cg);
 
 /* Seal the hierarchy: allocates the per-level work vectors (Grid::allocate_mem, grid.cpp:165-172)
  * and picks each operator's kernel mapping from its nnz/row. */
@@ -140,6 +151,11 @@ int saena_b200_dot(saena_b200_ctx *ctx, const double *a, const double *b, int n,
 int saena_b200_time_matvec(saena_b200_ctx *ctx, int level, int kind, int reps, int flush_l2, float *ms_out);
 int saena_b200_time_smooth_sweep(saena_b200_ctx *ctx, int level, int smoother, int reps, int flush_l2,
                                  float *ms_out);
+/* N > 1 (collective): the same operator application timed three ways -- complete (exchange
+ * overlapped with the interior rows), local kernels alone, pack + exchange alone -- so that
+ * hidden = 1 - (full - local) / halo can be reported. */
+int saena_b200_time_matvec_parts(saena_b200_ctx *ctx, int level, int kind, int reps, float *full_ms,
+                                 float *local_ms, float *halo_ms);
 /* CUDA-event stopwatch on the context's compute stream (the stream every kernel of this library
  * is launched on): start records an event, stop records a second one, waits for it and returns
  * the device time between them. */

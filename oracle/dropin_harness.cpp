@@ -22,7 +22,7 @@
 #include <fcntl.h>
 
 static std::vector<double> g_rr;
-extern "C" void saena_ref_record_rr(double rr) { g_rr.push_back(rr); }
+extern "C" void saena_ref_record_rr(double rr, int sz) { (void)sz; g_rr.push_back(rr); }
 extern "C" int saena_b200_adaptor_last_iterations(void);
 extern "C" int saena_b200_adaptor_last_history(double *out, int cap);
 extern "C" void saena_b200_adaptor_release(saena::amg *solver);

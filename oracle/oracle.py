@@ -40,7 +40,8 @@ class _Block(ctypes.Structure):
 
 
 class _Level(ctypes.Structure):
-    _fields_ = [("A", _Op), ("P", _Op), ("R", _Op), ("inv_diag", c_double_p), ("eig_max", ctypes.c_double),
+    _fields_ = [("A", _Op), ("P", _Op), ("R", _Op), ("inv_diag", c_double_p), ("inv_sq_diag", c_double_p),
+                ("eig_max", ctypes.c_double),
                 ("M_coarse_old", ctypes.c_int), ("M_coarse", ctypes.c_int), ("n_repart_send", ctypes.c_int),
                 ("n_repart_recv", ctypes.c_int), ("repart_send", ctypes.POINTER(_Block)),
                 ("repart_recv", ctypes.POINTER(_Block))]
@@ -48,7 +49,8 @@ class _Level(ctypes.Structure):
 
 class _Hier(ctypes.Structure):
     _fields_ = [("nranks", ctypes.c_int), ("nlevels", ctypes.c_int), ("level", ctypes.POINTER(_Level)),
-                ("coarse_n", ctypes.c_int), ("coarse_dense", c_double_p)]
+                ("coarse_n", ctypes.c_int), ("coarse_dense", c_double_p), ("scale", ctypes.c_int),
+                ("coarsest_cg", ctypes.c_int)]
 
 
 def build() -> str:
@@ -94,7 +96,7 @@ def _vecs(vs: Sequence[np.ndarray]):
 class Oracle:
     """The hierarchy of every rank, laid out for the C oracle."""
 
-    def __init__(self, hier: Hierarchy | List[Hierarchy]):
+    def __init__(self, hier: Hierarchy | List[Hierarchy], coarsest_cg: bool = False):
         self.ranks: List[Hierarchy] = hier if isinstance(hier, list) else [hier]
         self.nranks = len(self.ranks)
         self.nlevels = len(self.ranks[0].levels)
@@ -111,6 +113,10 @@ class Oracle:
                 inv = np.ascontiguousarray(lv.inv_diag, F64)
                 self._keep.append(inv)
                 c.inv_diag = _dp(inv)
+                if lv.inv_sq_diag is not None:
+                    isq = np.ascontiguousarray(lv.inv_sq_diag, F64)
+                    self._keep.append(isq)
+                    c.inv_sq_diag = _dp(isq)
                 c.eig_max = lv.eig_max
                 c.M_coarse_old, c.M_coarse = lv.M_coarse_old, lv.M_coarse
                 for name, blocks in (("repart_send", lv.repart_send), ("repart_recv", lv.repart_recv)):
@@ -122,7 +128,8 @@ class Oracle:
         dense = np.zeros((h0.coarse_n, h0.coarse_n), F64)
         np.add.at(dense, (h0.coarse_row, h0.coarse_col), h0.coarse_val)
         self.coarse_dense = dense
-        self._h = _Hier(self.nranks, self.nlevels, self._levels, h0.coarse_n, _dp(dense))
+        self._h = _Hier(self.nranks, self.nlevels, self._levels, h0.coarse_n, _dp(dense), int(h0.scale),
+                        int(coarsest_cg))
 
     def _op(self, op: Operator) -> _Op:
         a = dict(nnzPerRow_local=np.ascontiguousarray(op.nnzPerRow_local, I32),
@@ -199,6 +206,12 @@ class Oracle:
         rhs = np.ascontiguousarray(rhs, F64)
         u = np.zeros_like(rhs)
         lib().so_coarsest_solve(ctypes.byref(self._h), _dp(rhs), _dp(u))
+        return u
+
+    def coarsest_cg(self, rhs, u0=None):
+        rhs = np.ascontiguousarray(rhs, F64)
+        u = np.zeros_like(rhs) if u0 is None else np.array(u0, F64, copy=True)
+        lib().so_coarsest_cg(ctypes.byref(self._h), _dp(rhs), _dp(u))
         return u
 
     def vcycle(self, l, u, rhs, pre=3, post=3, smoother="chebyshev"):

@@ -22,6 +22,7 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libsaena_ref.so")
 # field ids of sref_array (ref_harness.cpp)
 F_NNZ_PER_ROW_LOCAL, F_COL_LOCAL, F_VAL_LOCAL, F_INV_DIAG, F_SPLIT, F_SPLIT_NEW = range(6)
 F_ROW_REMOTE, F_VAL_REMOTE, F_NNZ_PER_COL_REMOTE, F_ENTRY_ROW, F_ENTRY_COL, F_ENTRY_VAL = range(6, 12)
+F_INV_SQ_DIAG_ORIG = 12
 
 
 class _Opts(ctypes.Structure):
@@ -78,6 +79,7 @@ def lib():
             raise RuntimeError(f"{LIB_PATH} missing: run `make -C oracle ref` where /root/reference exists")
         L = ctypes.CDLL(LIB_PATH)
         L.sref_poisson_new.restype = ctypes.c_void_p
+        L.sref_poisson_new_scaled.restype = ctypes.c_void_p
         L.sref_coo_new.restype = ctypes.c_void_p
         L.sref_array.restype = ctypes.c_long
         L.sref_dot.restype = ctypes.c_double
@@ -98,10 +100,18 @@ class RefSolver:
         self.opts = opts
 
     @classmethod
-    def poisson(cls, mx: int, opts: RefOptions | None = None, quiet: bool = True) -> "RefSolver":
+    def poisson(cls, mx: int, opts: RefOptions | None = None, quiet: bool = True, scale: bool = False) -> "RefSolver":
+        if scale:
+            # the reference's own scale=true path crashes in its host code: matrix_setup() calls
+            # scale_matrix(full_scale=false) (src/saena_matrix_setup.cpp:570-571), which never fills
+            # inv_sq_diag_orig (:1407-1418), and set_repartition_rhs() then dereferences the empty
+            # vector (src/saena_object_repart_shrink.cpp:349-350).  Every shipped driver runs
+            # scale=false (experiments/Poisson.cpp:41).  The scale hooks of the solve path are
+            # therefore checked CUDA-vs-oracle only (tests/test_gpu_parity.py::test_scale_hooks).
+            raise NotImplementedError("the reference segfaults with scale=true (see comment)")
         opts = opts or RefOptions()
         c = opts._c()
-        return cls(lib().sref_poisson_new(int(mx), ctypes.byref(c), int(quiet)), opts)
+        return cls(lib().sref_poisson_new_scaled(int(mx), ctypes.byref(c), int(quiet), 0), opts)
 
     @classmethod
     def from_coo(cls, n, row, col, val, rhs, opts: RefOptions | None = None, quiet: bool = True) -> "RefSolver":
@@ -148,6 +158,7 @@ class RefSolver:
 
     def hierarchy(self) -> Hierarchy:
         ml = self.max_level
+        scale = bool(lib().sref_scale(self._h))
         levels = []
         for l in range(ml + 1):
             info = self._info(l, KIND_A)
@@ -158,8 +169,10 @@ class RefSolver:
                 lv.R = self._operator(l, KIND_R)
                 lv.M_coarse_old = lv.R.M
                 lv.M_coarse = lv.R.M
+            if scale:
+                lv.inv_sq_diag = self._arr(l, KIND_A, F_INV_SQ_DIAG_ORIG, F64)
             levels.append(lv)
-        h = Hierarchy(levels=levels, coarse_n=levels[-1].A.Mbig,
+        h = Hierarchy(levels=levels, scale=scale, coarse_n=levels[-1].A.Mbig,
                       coarse_row=self._arr(ml, KIND_A, F_ENTRY_ROW, I32),
                       coarse_col=self._arr(ml, KIND_A, F_ENTRY_COL, I32),
                       coarse_val=self._arr(ml, KIND_A, F_ENTRY_VAL, F64))
@@ -203,6 +216,15 @@ class RefSolver:
         rhs = np.array(rhs, F64, copy=True)
         u = np.zeros_like(rhs)
         lib().sref_coarsest_solve(self._h, _p(u), _p(rhs))
+        return u
+
+    def set_direct_solver(self, name: str):
+        lib().sref_set_direct_solver(self._h, int(name == "CG"))
+
+    def coarsest_cg(self, rhs) -> np.ndarray:
+        rhs = np.array(rhs, F64, copy=True)
+        u = np.zeros_like(rhs)
+        lib().sref_coarsest_cg(self._h, _p(u), _p(rhs))
         return u
 
     def solve_pcg(self, max_iter=None, tol=None, smoother=None, pre=None, post=None):

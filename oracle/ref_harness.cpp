@@ -32,7 +32,8 @@
 
 // ---------------------------------------------------------------- residual history
 static std::vector<double> g_rr;
-extern "C" void saena_ref_record_rr(double rr) { g_rr.push_back(rr); }
+static int g_rr_len = -1;  // only <r,r> of vectors of this length are recorded (level-0 size)
+extern "C" void saena_ref_record_rr(double rr, int sz) { if (g_rr_len < 0 || sz == g_rr_len) g_rr.push_back(rr); }
 
 namespace {
 
@@ -71,10 +72,10 @@ void ensure_mpi() {
 
 saena_object *obj(Handle *h) { return h->solver->get_object(); }
 
-void finish_setup(Handle *h, saena::vector *rhs, bool quiet) {
+void finish_setup(Handle *h, saena::vector *rhs, bool quiet, bool scale = false) {
     QuietStdout q(quiet);
     h->solver = new saena::amg();
-    h->solver->set_scale(false);  // Poisson.cpp:41,193
+    h->solver->set_scale(scale);  // Poisson.cpp:41,193 run with scale = false
     h->solver->set_matrix(h->A, h->opts);
     h->solver->set_rhs(*rhs);
 }
@@ -101,8 +102,13 @@ static saena::options *make_opts(const sref_opts *o) {
                               o->filter_max, o->filter_start, o->filter_rate, false, 0.1f, 5000);
 }
 
+void *sref_poisson_new_scaled(int mx, const sref_opts *o, int quiet, int scale);
+
 // 3D 7-point Poisson, exactly the driver sequence of experiments/Poisson.cpp.
-void *sref_poisson_new(int mx, const sref_opts *o, int quiet) {
+void *sref_poisson_new(int mx, const sref_opts *o, int quiet) { return sref_poisson_new_scaled(mx, o, quiet, 0); }
+
+// ... with the `scale` switch of Poisson.cpp:41 exposed (A.assemble(scale), solver.set_scale(scale))
+void *sref_poisson_new_scaled(int mx, const sref_opts *o, int quiet, int scale) {
     ensure_mpi();
     MPI_Comm comm = MPI_COMM_WORLD;
     Handle *h = new Handle();
@@ -111,7 +117,7 @@ void *sref_poisson_new(int mx, const sref_opts *o, int quiet) {
         h->A = new saena::matrix(comm);
         saena::laplacian3D(h->A, mx, mx, mx);
         h->A->set_remove_boundary(true);
-        h->A->assemble(false);
+        h->A->assemble(scale != 0);
     }
     value_t *rhs_std = nullptr;
     index_t orig_sz = saena::laplacian3D_set_rhs(rhs_std, mx, mx, mx, comm);
@@ -121,7 +127,7 @@ void *sref_poisson_new(int mx, const sref_opts *o, int quiet) {
     h->rhs->set(&rhs_std[0], orig_sz, my_split);
     h->rhs->assemble();
     h->opts = make_opts(o);
-    finish_setup(h, h->rhs, quiet != 0);
+    finish_setup(h, h->rhs, quiet != 0, scale != 0);
     saena_free(rhs_std);
     return h;
 }
@@ -162,6 +168,7 @@ void sref_free(void *hv) {
 
 // number of grids = max_level + 1; operators P/R/Ac exist on levels < max_level
 int sref_max_level(void *hv) { return obj((Handle *)hv)->max_level; }
+int sref_scale(void *hv) { return obj((Handle *)hv)->scale ? 1 : 0; }
 
 struct sref_level_info {
     int M, Mbig, Nbig;
@@ -209,7 +216,7 @@ int sref_level_info_get(void *hv, int l, int kind, sref_level_info *out) {
 // field ids for sref_array
 enum { F_NNZ_PER_ROW_LOCAL = 0, F_COL_LOCAL = 1, F_VAL_LOCAL = 2, F_INV_DIAG = 3, F_SPLIT = 4, F_SPLIT_NEW = 5,
        F_ROW_REMOTE = 6, F_VAL_REMOTE = 7, F_NNZ_PER_COL_REMOTE = 8, F_ENTRY_ROW = 9, F_ENTRY_COL = 10,
-       F_ENTRY_VAL = 11 };
+       F_ENTRY_VAL = 11, F_INV_SQ_DIAG_ORIG = 12 };
 
 // Copies one layout array of an operator into `dst` (if non-null) and returns its element count.
 long sref_array(void *hv, int l, int kind, int field, void *dst) {
@@ -227,6 +234,7 @@ long sref_array(void *hv, int l, int kind, int field, void *dst) {
             case F_COL_LOCAL: COPY_PTR(A->col_local, A->nnz_l_local);
             case F_VAL_LOCAL: COPY_PTR(A->val_local, A->nnz_l_local);
             case F_INV_DIAG: COPY_PTR(A->inv_diag, A->M);
+            case F_INV_SQ_DIAG_ORIG: COPY_VEC(A->inv_sq_diag_orig);
             case F_SPLIT: COPY_VEC(A->split);
             case F_ROW_REMOTE: COPY_PTR(A->row_remote, A->nnz_l_remote);
             case F_VAL_REMOTE: COPY_PTR(A->val_remote, A->nnz_l_remote);
@@ -321,6 +329,15 @@ void sref_vcycle(void *hv, int l, int pre, int post, int smoother, double *u, do
     o->vcycle(&o->grids[l], u, rhs);
 }
 
+// saena_object::direct_solver: "SuperLU" (default, saena_object.h:165) or "CG"
+void sref_set_direct_solver(void *hv, int use_cg) { obj((Handle *)hv)->direct_solver = use_cg ? "CG" : "SuperLU"; }
+
+// solve_coarsest_CG (saena_object_solve.cpp:14-114) on the coarsest grid
+void sref_coarsest_cg(void *hv, double *u, double *rhs) {
+    saena_object *o = obj((Handle *)hv);
+    o->solve_coarsest_CG(o->grids[o->max_level].A, u, rhs);
+}
+
 // Coarsest-level direct solve as the reference does it (SuperLU_DIST pdgssvx).
 void sref_coarsest_solve(void *hv, double *u, double *rhs) {
     saena_object *o = obj((Handle *)hv);
@@ -335,11 +352,13 @@ int sref_solve_pcg(void *hv, int max_iter, double tol, int smoother, int pre, in
     if (h->vcycle_mem) { obj(h)->free_vcycle_memory(); h->vcycle_mem = false; }
     h->opts->set_solve_params(max_iter, tol, smoother ? "chebyshev" : "jacobi", pre, post);
     g_rr.clear();
+    g_rr_len = obj(h)->grids[0].A->M;
     value_t *u = nullptr;
     {
         QuietStdout q(quiet != 0);
         h->solver->solve_pCG(u, h->opts, false);
     }
+    g_rr_len = -1;
     const int M = obj(h)->grids[0].A->M;
     if (u_out) memcpy(u_out, u, sizeof(double) * (size_t)M);
     saena_free(u);

@@ -217,6 +217,46 @@ void so_coarsest_solve(const so_hierarchy *h, const double *rhs, double *u) {
     free(x); free(r); free(c); free(LU); free(piv);
 }
 
+/* src/saena_object_solve.cpp:14-114 (the coarsest level lives on rank 0) */
+void so_coarsest_cg(const so_hierarchy *h, const double *rhs, double *u) {
+    const double CG_coarsest_tol = 1e-12; /* saena_object.h:156 */
+    const int CG_coarsest_max_iter = 150; /* saena_object.h:155 */
+    const int n = h->nranks;
+    const so_operator *A = &h->level[(h->nlevels - 1) * n].A;
+    const so_operator *ops[1] = {A};
+    const int sz = A->M;
+    double *res = dalloc(sz), *dir = dalloc(sz), *mv = dalloc(sz);
+    memcpy(res, rhs, sizeof(double) * (size_t)sz);
+    const double *rp[1] = {res};
+    const int M1[1] = {sz};
+    const double initial_dot = so_dot(1, M1, rp, rp);
+    const double thres = initial_dot * CG_coarsest_tol * CG_coarsest_tol;
+    double dot = initial_dot, dot_prev, factor;
+    int max_iter = CG_coarsest_max_iter;
+    if (dot < CG_coarsest_tol * CG_coarsest_tol) max_iter = 0;
+    memcpy(dir, res, sizeof(double) * (size_t)sz);
+    int i = 1;
+    while (i < max_iter) {
+        const double *dp[1] = {dir};
+        double *mp[1] = {mv};
+        so_matvec(ops, 1, dp, mp);
+        const double *mcp[1] = {mv};
+        factor = so_dot(1, M1, dp, mcp);
+        factor = dot / factor;
+        for (int j = 0; j < sz; ++j) {
+            u[j] += factor * dir[j];
+            res[j] -= factor * mv[j];
+        }
+        dot_prev = dot;
+        dot = so_dot(1, M1, rp, rp);
+        if (dot < thres) break;
+        factor = dot / dot_prev;
+        for (int j = 0; j < sz; ++j) dir[j] = res[j] + factor * dir[j];
+        i++;
+    }
+    free(res); free(dir); free(mv);
+}
+
 /* ------------------------------------------------------------------ repartition
  * src/grid.cpp:99-130 (repart_u): blocks of the old-partition vector go to the ranks owning
  * them in the new partition.  `back` runs the plan in reverse (grid.cpp:132-163). */
@@ -265,7 +305,8 @@ void so_vcycle(const so_hierarchy *h, int l, int smoother, int pre, int post, do
     const int n = h->nranks;
     /* :991-1057 coarsest level: direct solve (lives on rank 0) */
     if (l == h->nlevels - 1) {
-        so_coarsest_solve(h, rhs[0], u[0]);
+        if (h->coarsest_cg) so_coarsest_cg(h, rhs[0], u[0]);
+        else so_coarsest_solve(h, rhs[0], u[0]);
         return;
     }
     const so_operator **A = (const so_operator **)calloc((size_t)n, sizeof(void *));
@@ -296,7 +337,20 @@ void so_vcycle(const so_hierarchy *h, int l, int smoother, int pre, int post, do
     /* :1201-1203 repart_u, :1249 uCorrCoarse = 0, :1256 recurse */
     const int rp = has_repart(h, l);
     if (rp) repart(h, l, 0, res_coarse, res_coarse_new);
-    so_vcycle(h, l + 1, smoother, pre, post, uCorrCoarse, rp ? res_coarse_new : res_coarse);
+    double **rc = rp ? res_coarse_new : res_coarse;
+    /* :1245-1247 scale_vector(res_coarse, coarse inv_sq_diag_orig) */
+    if (h->scale)
+        for (int r = 0; r < n; ++r) {
+            const so_level *cl = &h->level[(l + 1) * n + r];
+            for (int i = 0; i < cl->A.M; ++i) rc[r][i] *= cl->inv_sq_diag[i];
+        }
+    so_vcycle(h, l + 1, smoother, pre, post, uCorrCoarse, rc);
+    /* :1264-1266 */
+    if (h->scale)
+        for (int r = 0; r < n; ++r) {
+            const so_level *cl = &h->level[(l + 1) * n + r];
+            for (int i = 0; i < cl->A.M; ++i) uCorrCoarse[r][i] *= cl->inv_sq_diag[i];
+        }
     /* :1301-1303 repart_back_u */
     if (rp) repart(h, l, 1, uCorrCoarse, uCorrCoarse_old);
     /* :1325 prolong, :1360-1361 correct */
@@ -377,6 +431,9 @@ int so_solve_pcg(const so_hierarchy *h, const double *const *rhs, double *const 
     }
     if (i == max_iter) i--; /* :2673-2674 */
 done:
+    if (h->scale) /* :2709-2711 */
+        for (int k = 0; k < n; ++k)
+            for (int j = 0; j < M[k]; ++j) u[k][j] *= h->level[k].inv_sq_diag[j];
     *hist_len = nh;
     for (int k = 0; k < n; ++k) { free(r[k]); free(rho[k]); free(p[k]); free(hh[k]); }
     free(r); free(rho); free(p); free(hh); free(M); free(A);
@@ -413,6 +470,9 @@ int so_solve_vcycle(const so_hierarchy *h, const double *const *rhs, double *con
         if (current_dot < THRSHLD) break;
     }
     if (i == max_iter) --i;
+    if (h->scale) /* :2000-2002 */
+        for (int k = 0; k < n; ++k)
+            for (int j = 0; j < M[k]; ++j) u[k][j] *= h->level[k].inv_sq_diag[j];
     *hist_len = nh;
     for (int k = 0; k < n; ++k) free(r[k]);
     free(r); free(M); free(A);

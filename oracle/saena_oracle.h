@@ -58,6 +58,7 @@ typedef struct so_block {
 typedef struct so_level {
     so_operator A, P, R;     /* P and R unused on the coarsest level */
     const double *inv_diag;  /* [A.M] */
+    const double *inv_sq_diag; /* [A.M] inv_sq_diag_orig, NULL unless the hierarchy is scaled */
     double eig_max;          /* eig_max_of_invdiagXA */
     int M_coarse_old;        /* Ac.M_old */
     int M_coarse;            /* Ac.M */
@@ -72,6 +73,8 @@ typedef struct so_hierarchy {
     const so_level *level;
     int coarse_n;            /* rows of the coarsest operator (lives on rank 0) */
     const double *coarse_dense; /* [coarse_n * coarse_n] row-major dense copy of it */
+    int scale;               /* saena_object::scale */
+    int coarsest_cg;         /* saena_object::direct_solver == "CG" (default 0: "SuperLU") */
 } so_hierarchy;
 
 enum { SO_JACOBI = 0, SO_CHEBYSHEV = 1 };
@@ -95,6 +98,10 @@ double so_dot(int nranks, const int *M, const double *const *a, const double *co
 /* Dense LU with partial pivoting + one step of iterative refinement on the coarsest operator
  * (stands for SuperLU_DIST pdgssvx, saena_object_solve.cpp:793-958). */
 void so_coarsest_solve(const so_hierarchy *h, const double *rhs, double *u);
+
+/* saena_object_solve.cpp:14-114: CG on the coarsest level, <=150 iterations to 1e-12 (saena_object.h:155-156).
+ * u is the initial guess on entry (the V-cycle passes 0). */
+void so_coarsest_cg(const so_hierarchy *h, const double *rhs, double *u);
 
 /* saena_object_solve.cpp:961-1431 starting at grid `l`; u[r], rhs[r] have length level[l].A.M */
 void so_vcycle(const so_hierarchy *h, int l, int smoother, int pre, int post, double *const *u,

@@ -136,10 +136,6 @@ void upload_PR(saena_b200_ctx *ctx, Op &op, int kind, int level, int n_rows, int
 DeviceSide &device_side(saena_object *obj) {
     auto it = g_solvers.find(obj);
     if (it != g_solvers.end()) return it->second;
-    if (obj->scale) {
-        std::printf("Error: saena_b200: scale=true is not supported on the device path\n");
-        std::exit(EXIT_FAILURE);
-    }
     DeviceSide ds;
     saena_matrix *A0 = obj->grids[0].A;
     ds.ctx = new_context(A0->comm, ds.rank, ds.nprocs);
@@ -177,6 +173,8 @@ DeviceSide &device_side(saena_object *obj) {
         CK(ds.ctx, saena_b200_upload_level_aux(ds.ctx, l, A->inv_diag, A->eig_max_of_invdiagXA, M_old, M_new,
                                                (int)send.size(), send.data(), (int)recv.size(), recv.data()),
            "upload level aux");
+        if (obj->scale)  // D^-1/2 hooks of the V-cycle (saena_object_solve.cpp:1245-1247,1264-1266,2709-2711)
+            CK(ds.ctx, saena_b200_upload_level_scale(ds.ctx, l, A->inv_sq_diag_orig.data()), "upload level scale");
     }
     // coarsest operator: the COO entries setup_SuperLU passes on (saena_object_solve.cpp:282-308)
     saena_matrix *Ac = obj->grids[L].A;
@@ -212,6 +210,11 @@ int run_solver(saena_object *obj, Which which, value_t *&u, saena::options *opts
     obj->set_solve_params(opts->get_max_iter(), opts->get_tol(), opts->get_smoother(), opts->get_preSmooth(),
                           opts->get_postSmooth());
     DeviceSide &ds = device_side(obj);
+    if (obj->direct_solver != "SuperLU" && obj->direct_solver != "CG") {
+        if (!ds.rank) std::printf("Error: Unknown direct solver! \n");  // saena_object_solve.cpp:1011-1013
+        std::exit(EXIT_FAILURE);
+    }
+    CK(ds.ctx, saena_b200_set_coarsest_solver(ds.ctx, obj->direct_solver == "CG"), "set coarsest solver");
     saena_matrix *A = obj->grids[0].A;
     const index_t sz = A->M;
     if (u == nullptr) u = saena_aligned_alloc<value_t>(sz);  // saena_object_solve.cpp:2478-2480

@@ -76,9 +76,11 @@ int saena_b200_destroy(saena_b200_ctx *ctx) {
         DevLevel &lv = ctx->levels[l];
         sb_free_operator(lv.A); sb_free_operator(lv.P); sb_free_operator(lv.R);
         cudaFree(lv.inv_diag);
+        cudaFree(lv.inv_sq_diag);
         free_level_work(lv, l > 0);
     }
     cudaFree(ctx->coarse_A); cudaFree(ctx->coarse_Ainv); cudaFree(ctx->coarse_tmp);
+    cudaFree(ctx->ccg_res); cudaFree(ctx->ccg_dir); cudaFree(ctx->ccg_mv);
     cudaFree(ctx->red_partials); cudaFree(ctx->red_counter); cudaFree(ctx->scalars);
     cudaFreeHost(ctx->scalars_host);
     cudaFree(ctx->pcg_r); cudaFree(ctx->pcg_p); cudaFree(ctx->pcg_h); cudaFree(ctx->pcg_u); cudaFree(ctx->pcg_rhs);
@@ -123,6 +125,20 @@ int saena_b200_upload_level_aux(saena_b200_ctx *ctx, int level, const double *in
             SB_FAIL("upload_level_aux: recv block out of range");
     lv.aux_set = true;
     ctx->finalized = false;
+    return 0;
+}
+
+int saena_b200_upload_level_scale(saena_b200_ctx *ctx, int level, const double *inv_sq_diag_orig) {
+    if (!ctx) return 1;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    if (level < 0 || level >= (int)ctx->levels.size() || !ctx->levels[level].A.present)
+        SB_FAIL("upload_level_scale: upload A of this level first");
+    DevLevel &lv = ctx->levels[level];
+    cudaFree(lv.inv_sq_diag);
+    lv.inv_sq_diag = nullptr;
+    SB_CUDA(cudaMalloc((void **)&lv.inv_sq_diag, sizeof(double) * std::max(lv.M, 1)));
+    if (lv.M) SB_CUDA(cudaMemcpy(lv.inv_sq_diag, inv_sq_diag_orig, sizeof(double) * lv.M, cudaMemcpyHostToDevice));
+    if (level == 0) ctx->scale = true;
     return 0;
 }
 
@@ -309,6 +325,7 @@ static int pcg_device(saena_b200_ctx *ctx, const double *rhs, double *u, int max
         SB_TRY(sb_dot(ctx, r, r, n, S_RR));
         SB_TRY(sb_read_scalars(ctx));
         push_hist(ctx->scalars_host[S_RR], hist, hist_cap, nh);
+        if (ctx->scale) SB_TRY(sb_scale_vector(ctx, n, u, l0.inv_sq_diag));  // :2517-2519
         *iters = 1;
         *hist_len = nh;
         return 0;
@@ -334,6 +351,7 @@ static int pcg_device(saena_b200_ctx *ctx, const double *rhs, double *u, int max
         SB_TRY(sb_pcg_p_update(ctx, n, p, l0.u[l0.cur]));          // :2662-2667
     }
     if (i == max_iter) i--;  // :2673-2674
+    if (ctx->scale) SB_TRY(sb_scale_vector(ctx, n, u, l0.inv_sq_diag));  // :2709-2711
     *iters = i + 1;          // :2678-2682
     *hist_len = nh;
     (void)current_dot;
@@ -391,6 +409,7 @@ int saena_b200_solve_vcycle(saena_b200_ctx *ctx, const double *rhs, double *u, i
         if (!(ctx->scalars_host[S_RR] >= THRSHLD)) break;
     }
     if (i == max_iter) --i;
+    if (ctx->scale) SB_TRY(sb_scale_vector(ctx, n, l0.u[l0.cur], l0.inv_sq_diag));  // :2000-2002
     *iters = i + 1;
     *hist_len = nh;
     SB_TRY(d2h(ctx, u, l0.u[l0.cur], n));
@@ -555,6 +574,21 @@ int saena_b200_time_matvec(saena_b200_ctx *ctx, int level, int kind, int reps, i
     return 0;
 }
 
+// halo overlap of one operator: full application, local kernels alone, pack + exchange alone
+int saena_b200_time_matvec_parts(saena_b200_ctx *ctx, int level, int kind, int reps, float *full_ms,
+                                 float *local_ms, float *halo_ms) {
+    SB_ENTER();
+    float *out[3] = {full_ms, local_ms, halo_ms};
+    for (int mode = 0; mode < 3; ++mode) {
+        ctx->apply_mode = mode;
+        int rc = saena_b200_time_matvec(ctx, level, kind, 3, 0, out[mode]);  // warm-up
+        if (!rc) rc = saena_b200_time_matvec(ctx, level, kind, reps, 0, out[mode]);
+        ctx->apply_mode = 0;
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 int saena_b200_time_smooth_sweep(saena_b200_ctx *ctx, int level, int smoother, int reps, int do_flush,
                                  float *ms_out) {
     SB_ENTER();
@@ -603,6 +637,12 @@ int saena_b200_set_mapping(saena_b200_ctx *ctx, int level, int kind, int mapping
     if (!op) SB_FAIL("set_mapping: no such operator");
     op->forced_mapping = mapping;
     return sb_prepare_operator(ctx, *op);
+}
+
+int saena_b200_set_coarsest_solver(saena_b200_ctx *ctx, int use_cg) {
+    if (!ctx) return 1;
+    ctx->coarsest_cg = use_cg != 0;
+    return 0;
 }
 
 int saena_b200_get_mapping(const saena_b200_ctx *ctx, int level, int kind) {

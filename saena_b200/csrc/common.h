@@ -129,6 +129,7 @@ struct RepartPlan {
 struct DevLevel {
     DevOperator A, P, R;
     double *inv_diag = nullptr;
+    double *inv_sq_diag = nullptr;  // inv_sq_diag_orig, only for scale=true hierarchies
     double eig_max = 0.0;
     int M = 0;             // A.M
     int M_coarse_old = 0;  // Ac.M_old
@@ -155,6 +156,8 @@ struct saena_b200_ctx {
     int sm_count = 148;
     std::vector<DevLevel> levels;
     bool finalized = false;
+    bool scale = false;  // saena_object::scale
+    int apply_mode = 0;  // measurement only: 0 full, 1 local kernels only (no exchange), 2 pack + exchange only
     int64_t launches = 0;
 
     // coarsest dense factor
@@ -162,6 +165,9 @@ struct saena_b200_ctx {
     double *coarse_A = nullptr;     // [n*n] row-major
     double *coarse_Ainv = nullptr;  // [n*n] row-major
     double *coarse_tmp = nullptr;   // [2n]
+    bool coarsest_cg = false;       // direct_solver == "CG": solve_coarsest_CG instead of the dense factor
+    double *ccg_res = nullptr, *ccg_dir = nullptr, *ccg_mv = nullptr;
+    int ccg_cap = 0;
 
     // reductions
     double *red_partials = nullptr;  // [RED_MAX_BLOCKS * 4]
@@ -183,7 +189,9 @@ struct saena_b200_ctx {
 };
 
 // scalar slots
-enum { S_RHO_RES = 0, S_PDOTH = 1, S_RR = 2, S_BETA_NUM = 3, S_TMP = 4, S_COUNT = 8 };
+enum { S_RHO_RES = 0, S_PDOTH = 1, S_RR = 2, S_BETA_NUM = 3, S_TMP = 4,
+       S_C_RR = 8, S_C_DEN = 9, S_C_RRNEW = 10,  // coarsest-level CG (must not clobber the outer loop's)
+       S_COUNT = 16 };
 
 static const int SB_MAPPING_SELL = 100;   // forced_mapping / set_mapping code of the sliced layout
 static const int STREAM_TILE = 2048;      // nnz per row block of the streaming kernel (16 KB of products)
@@ -218,7 +226,9 @@ int sb_pcg_p_update(saena_b200_ctx *ctx, int n, double *p, const double *rho);
 int sb_cg_p_update(saena_b200_ctx *ctx, int n, double *p, const double *r, int num_slot, int den_slot);
 int sb_negate_copy(saena_b200_ctx *ctx, int n, const double *src, double *dst);              // dst = -src
 int sb_fill_zero(saena_b200_ctx *ctx, double *p, size_t n);
+int sb_scale_vector(saena_b200_ctx *ctx, int n, double *v, const double *w);                   // v *= w (scale_vector)
 int sb_coarsest_apply(saena_b200_ctx *ctx, const double *rhs, double *u);
+int sb_coarsest_cg(saena_b200_ctx *ctx, const double *rhs, double *u);  // u: initial guess in, solution out
 int sb_read_scalars(saena_b200_ctx *ctx);  // device scalars -> scalars_host (synchronises the stream)
 
 // ---- solve.cu

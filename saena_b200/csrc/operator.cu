@@ -13,6 +13,15 @@
 
 #include "spmv_kernels.cuh"
 
+__global__ void localise_cols_kernel(long long n, int *__restrict__ col, int col_offset, int n_local_cols,
+                                     int *__restrict__ bad) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int c = col[k] - col_offset;
+        if (c < 0 || c >= n_local_cols) *bad = 1;
+        col[k] = c;
+    }
+}
+
 template <typename T>
 static int dev_upload(saena_b200_ctx *ctx, T **dst, const T *src, size_t n) {
     *dst = nullptr;
@@ -71,13 +80,18 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
             SB_TRY(dev_upload(ctx, &p, rp32.data(), rp32.size()));
             op.rowptr = p;
         }
-        std::vector<int> lc((size_t)d->nnz_local);
-        for (int64_t k = 0; k < d->nnz_local; ++k) {
-            const int c = d->col_local[k] - d->col_offset;
-            if (c < 0 || c >= d->n_local_cols) SB_FAIL("upload_operator: col_local outside this rank's column block");
-            lc[k] = c;
+        // columns arrive as GLOBAL ids; make them local on the device and range-check there
+        SB_TRY(dev_upload(ctx, &op.col, d->col_local, (size_t)d->nnz_local));
+        if (d->nnz_local) {
+            int *d_bad = nullptr;
+            SB_CUDA(cudaMalloc((void **)&d_bad, sizeof(int)));
+            SB_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
+            localise_cols_kernel<<<1184, 256>>>(d->nnz_local, op.col, d->col_offset, d->n_local_cols, d_bad);
+            int bad = 0;
+            SB_CUDA(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+            cudaFree(d_bad);
+            if (bad) SB_FAIL("upload_operator: col_local outside this rank's column block");
         }
-        SB_TRY(dev_upload(ctx, &op.col, lc.data(), lc.size()));
         SB_TRY(dev_upload(ctx, &op.val, d->val_local, (size_t)d->nnz_local));
 
         // row blocks of the streaming kernel (LPR is fixed later; blocks are cut for the largest
@@ -164,7 +178,6 @@ static int pow2_at_most(double v) {
 }
 
 void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op) {
-    (void)ctx;
     const double avg = op.M ? double(op.nnz_local) / op.M : 0.0;
     int m = op.forced_mapping;
     if (m == 0) {
@@ -172,8 +185,12 @@ void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op) {
         // with ~4+ elements per lane.  Crossovers measured on B200, see DESIGN.md.
         // measured on B200 (profiles/r01_mapping_sweep.md): the sliced layout wins whenever its
         // padding is small (7-pt Poisson 5.9 TB/s vs 5.6 best sub-warp; band 61/row 6.8 vs 5.3)
+        // ... provided one lane per row still fills the chip: >= ~2 resident threads per lane slot
+        // (the 5 416-row x 4 342-nnz level 5 of the 256^3 hierarchy ran at 0.23 TB/s sliced,
+        //  profiles/r01_bench_levels.md)
         const bool regular = op.nnz_local > 0 && double(op.sell_padded_est) <= 1.20 * double(op.nnz_local);
-        if (regular) m = SB_MAPPING_SELL;
+        const bool enough_rows = op.M >= 2 * 2048 * ctx->sm_count / 4;  // 151 552 rows on B200
+        if (regular && enough_rows) m = SB_MAPPING_SELL;
         else {
             // ~4+ elements per lane; rows of hundreds..thousands of entries get 32..256 threads
             m = 1;
@@ -221,55 +238,77 @@ static int build_row_blocks(saena_b200_ctx *ctx, DevOperator &op, int rows_per_b
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// sliced layout, built on the device from the CSR arrays (one-time, at finalize):
 // 32-row slices, column-major inside a slice, padded to the slice's longest row
+// ---------------------------------------------------------------------------------------------
+template <typename OffT>
+__global__ void sell_slice_len_kernel(int M, const OffT *__restrict__ rowptr, int *__restrict__ slice_len) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    int len = row < M ? (int)(rowptr[row + 1] - rowptr[row]) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && (row >> 5) < (M + 31) / 32) slice_len[row >> 5] = len;
+}
+
+template <typename OffT>
+__global__ void sell_fill_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+                                 const double *__restrict__ val, const long long *__restrict__ slice_ptr,
+                                 int *__restrict__ scol, double *__restrict__ sval) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slice = row >> 5, lane = row & 31;
+    if ((slice << 5) >= M) return;
+    const long long base = slice_ptr[slice];
+    const int len = (int)((slice_ptr[slice + 1] - base) >> 5);
+    OffT a = 0, b = 0;
+    if (row < M) { a = rowptr[row]; b = rowptr[row + 1]; }
+    const int pad_col = (b > a) ? col[b - 1] : 0;  // padding: val 0.0, a column the row already touches
+    for (int j = 0; j < len; ++j) {
+        const long long dst = base + (long long)j * 32 + lane;
+        if (a + j < b) {
+            scol[dst] = col[a + j];
+            sval[dst] = val[a + j];
+        } else {
+            scol[dst] = pad_col;
+            sval[dst] = 0.0;
+        }
+    }
+}
+
 static int build_sell(saena_b200_ctx *ctx, DevOperator &op) {
     if (op.sell_ptr) return 0;
     const int M = op.M;
-    std::vector<int64_t> rp(M + 1);
-    if (op.wide_offsets) {
-        SB_CUDA(cudaMemcpy(rp.data(), op.rowptr, sizeof(int64_t) * (M + 1), cudaMemcpyDeviceToHost));
-    } else {
-        std::vector<int> rp32(M + 1);
-        SB_CUDA(cudaMemcpy(rp32.data(), op.rowptr, sizeof(int) * (M + 1), cudaMemcpyDeviceToHost));
-        std::copy(rp32.begin(), rp32.end(), rp.begin());
-    }
-    std::vector<int> col((size_t)op.nnz_local);
-    std::vector<double> val((size_t)op.nnz_local);
-    if (op.nnz_local) {
-        SB_CUDA(cudaMemcpy(col.data(), op.col, sizeof(int) * col.size(), cudaMemcpyDeviceToHost));
-        SB_CUDA(cudaMemcpy(val.data(), op.val, sizeof(double) * val.size(), cudaMemcpyDeviceToHost));
-    }
     const int ns = (M + 31) / 32;
+    int *d_len = nullptr;
+    SB_CUDA(cudaMalloc((void **)&d_len, sizeof(int) * std::max(ns, 1)));
+    const int blocks = (ns * 32 + 255) / 256;
+    if (ns) {
+        if (op.wide_offsets)
+            sell_slice_len_kernel<int64_t><<<blocks, 256, 0, ctx->stream>>>(M, (const int64_t *)op.rowptr, d_len);
+        else
+            sell_slice_len_kernel<int><<<blocks, 256, 0, ctx->stream>>>(M, (const int *)op.rowptr, d_len);
+    }
+    std::vector<int> len(ns);
+    SB_CUDA(cudaMemcpyAsync(len.data(), d_len, sizeof(int) * ns, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_len);
     std::vector<long long> sp(ns + 1, 0);
-    for (int s0 = 0; s0 < ns; ++s0) {
-        int64_t mx = 0;
-        for (int i = s0 * 32; i < std::min(M, s0 * 32 + 32); ++i) mx = std::max(mx, rp[i + 1] - rp[i]);
-        sp[s0 + 1] = sp[s0] + mx * 32;
-    }
+    for (int s0 = 0; s0 < ns; ++s0) sp[s0 + 1] = sp[s0] + (long long)len[s0] * 32;
     const int64_t padded = sp[ns];
-    std::vector<int> scol((size_t)padded, 0);
-    std::vector<double> sval((size_t)padded, 0.0);
-    for (int s0 = 0; s0 < ns; ++s0) {
-        const int len = (int)((sp[s0 + 1] - sp[s0]) / 32);
-        for (int t = 0; t < 32; ++t) {
-            const int i = s0 * 32 + t;
-            const int64_t a = i < M ? rp[i] : 0, b = i < M ? rp[i + 1] : 0;
-            const int pad_col = (b > a) ? col[b - 1] : 0;  // a column this row (or any row) already touches
-            for (int j = 0; j < len; ++j) {
-                const int64_t dst = sp[s0] + (int64_t)j * 32 + t;
-                if (a + j < b) {
-                    scol[dst] = col[a + j];
-                    sval[dst] = val[a + j];
-                } else {
-                    scol[dst] = pad_col;
-                }
-            }
-        }
-    }
     op.sell_padded = padded;
     SB_TRY(dev_upload(ctx, &op.sell_ptr, sp.data(), sp.size()));
-    SB_TRY(dev_upload(ctx, &op.sell_col, scol.data(), scol.size()));
-    SB_TRY(dev_upload(ctx, &op.sell_val, sval.data(), sval.size()));
+    SB_CUDA(cudaMalloc((void **)&op.sell_col, sizeof(int) * std::max<int64_t>(padded, 1)));
+    SB_CUDA(cudaMalloc((void **)&op.sell_val, sizeof(double) * std::max<int64_t>(padded, 1)));
+    if (ns) {
+        if (op.wide_offsets)
+            sell_fill_kernel<int64_t><<<blocks, 256, 0, ctx->stream>>>(M, (const int64_t *)op.rowptr, op.col, op.val,
+                                                                       op.sell_ptr, op.sell_col, op.sell_val);
+        else
+            sell_fill_kernel<int><<<blocks, 256, 0, ctx->stream>>>(M, (const int *)op.rowptr, op.col, op.val,
+                                                                   op.sell_ptr, op.sell_col, op.sell_val);
+    }
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -347,7 +386,9 @@ static void launch_boundary(saena_b200_ctx *ctx, DevOperator &op, const double *
 
 template <int EPI>
 static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, const EpiArgs &e) {
-    const bool halo = !op.sends.empty() || !op.recvs.empty();
+    const bool has_halo = !op.sends.empty() || !op.recvs.empty();
+    const bool halo = has_halo && ctx->apply_mode != 1;
+    const bool compute = ctx->apply_mode != 2;
     if (halo) {
         // pack -> exchange on the comm stream, overlapped with the interior rows
         if (op.vIndexSize) {
@@ -365,10 +406,12 @@ static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, cons
         SB_TRY(sb_halo_exchange(ctx, op, ctx->comm_stream));
         SB_CUDA(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
     }
-    if (op.wide_offsets) launch_local<EPI, int64_t>(ctx, op, x, e);
-    else launch_local<EPI, int>(ctx, op, x, e);
-    if (halo) {
-        SB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+    if (compute) {
+        if (op.wide_offsets) launch_local<EPI, int64_t>(ctx, op, x, e);
+        else launch_local<EPI, int>(ctx, op, x, e);
+    }
+    if (halo) SB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+    if (has_halo && compute) {
         if (op.wide_offsets) launch_boundary<EPI, int64_t>(ctx, op, x, e);
         else launch_boundary<EPI, int>(ctx, op, x, e);
     }

@@ -86,7 +86,12 @@ int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const
     DevLevel &lv = ctx->levels[l];
     // solve.cpp:991-1057 coarsest level: direct solve on the rank that owns it
     if (l == max_level) {
-        if (lv.M > 0) {
+        if (lv.M > 0 && ctx->coarsest_cg) {
+            // direct_solver == "CG" (:998-999): u is the initial guess of solve_coarsest_CG
+            if (!lv.A.sends.empty() || !lv.A.recvs.empty()) SB_FAIL("vcycle: the coarsest level must live on one rank");
+            if (u_is_zero) SB_TRY(sb_fill_zero(ctx, lv.u[lv.cur], lv.M));
+            SB_TRY(sb_coarsest_cg(ctx, rhs, lv.u[lv.cur]));
+        } else if (lv.M > 0) {
             if (ctx->coarse_n != lv.M) SB_FAIL("vcycle: no coarsest factor was uploaded for the coarsest level");
             SB_TRY(sb_coarsest_apply(ctx, rhs, lv.u[lv.cur]));
         }
@@ -113,8 +118,12 @@ int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const
         SB_TRY(sb_apply(ctx, lv.R, lv.res, EPI_PLAIN, e));
         if (!ident) SB_TRY(sb_repart(ctx, lv.repart, false, lv.xfer_old, cl.rhs, ctx->stream));  // :1201-1203
     }
+    // scale the next level's rhs (:1245-1247)
+    if (ctx->scale) SB_TRY(sb_scale_vector(ctx, cl.M, cl.rhs, cl.inv_sq_diag));
     // 4. recurse with a zero initial correction (:1249, :1256)
     SB_TRY(sb_vcycle(ctx, l + 1, smoother, pre, post, cl.rhs, true));
+    // scale the coarse correction (:1264-1266)
+    if (ctx->scale) SB_TRY(sb_scale_vector(ctx, cl.M, cl.u[cl.cur], cl.inv_sq_diag));
     // 5. + 6. prolong and correct: u -= P e_c (:1301-1303, :1325, :1360-1361)
     {
         const double *ec = cl.u[cl.cur];

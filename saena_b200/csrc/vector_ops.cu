@@ -103,6 +103,24 @@ cg_p_update_kernel(int n, double *__restrict__ p, const double *__restrict__ r, 
         p[i] = r[i] + beta * p[i];
 }
 
+// solve_coarsest_CG's update (saena_object_solve.cpp:58-72): u += f dir; res -= f A dir; <res,res>
+__global__ void __launch_bounds__(256)
+ccg_update_kernel(int n, double *__restrict__ u, double *__restrict__ res, const double *__restrict__ dir,
+                  const double *__restrict__ mv, const double *__restrict__ scal, double *partials,
+                  unsigned int *counter, double *out_rr) {
+    __shared__ double s_w[8];
+    const double factor = scal[S_C_RR] / scal[S_C_DEN];
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        u[i] += factor * dir[i];
+        const double ri = res[i] - factor * mv[i];
+        res[i] = ri;
+        acc += ri * ri;
+    }
+    const double t = block_sum_256(acc, s_w);
+    finalize_sum(t, partials, counter, out_rr);
+}
+
 // first Chebyshev sweep from a zero iterate: A*0 = 0, so d = (1/theta) D^-1 rhs and u = d
 // (saena_matrix.cpp:1099-1109 with u == 0; bit-identical to running the SpMV on zeros)
 __global__ void __launch_bounds__(256)
@@ -113,6 +131,12 @@ cheb_first_zero_kernel(int n, const double *__restrict__ rhs, const double *__re
         d[i] = v;
         u[i] = v;
     }
+}
+
+// saena_object::scale_vector (src/saena_object.cpp:563-569)
+__global__ void __launch_bounds__(256)
+scale_vector_kernel(int n, double *__restrict__ v, const double *__restrict__ w) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] *= w[i];
 }
 
 __global__ void __launch_bounds__(256)
@@ -214,6 +238,15 @@ int sb_negate_copy(saena_b200_ctx *ctx, int n, const double *src, double *dst) {
     return 0;
 }
 
+int sb_scale_vector(saena_b200_ctx *ctx, int n, double *v, const double *w) {
+    if (n == 0) return 0;
+    if (!w) SB_FAIL("scale=true but a level has no inv_sq_diag_orig (saena_b200_upload_level_scale)");
+    ++ctx->launches;
+    scale_vector_kernel<<<red_blocks(ctx, n), 256, 0, ctx->stream>>>(n, v, w);
+    SB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int sb_fill_zero(saena_b200_ctx *ctx, double *p, size_t n) {
     if (n) SB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), ctx->stream));
     return 0;
@@ -228,6 +261,51 @@ int sb_coarsest_apply(saena_b200_ctx *ctx, const double *rhs, double *u) {
     coarsest_kernel<<<1, threads, (size_t)n * sizeof(double), ctx->stream>>>(n, ctx->coarse_A, ctx->coarse_Ainv, rhs,
                                                                             u, ctx->coarse_tmp);
     SB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// saena_object::solve_coarsest_CG (src/saena_object_solve.cpp:14-114): plain CG on the coarsest
+// operator, at most CG_coarsest_max_iter - 1 = 149 iterations, stop at <res,res> < <rhs,rhs> * 1e-24.
+// Not the default (direct_solver = "SuperLU", saena_object.h:165); one host read per iteration.
+int sb_coarsest_cg(saena_b200_ctx *ctx, const double *rhs, double *u) {
+    DevLevel &lv = ctx->levels.back();
+    const int n = lv.M;
+    if (n == 0) return 0;
+    if (ctx->ccg_cap < n) {
+        cudaFree(ctx->ccg_res); cudaFree(ctx->ccg_dir); cudaFree(ctx->ccg_mv);
+        SB_CUDA(cudaMalloc((void **)&ctx->ccg_res, sizeof(double) * n));
+        SB_CUDA(cudaMalloc((void **)&ctx->ccg_dir, sizeof(double) * n));
+        SB_CUDA(cudaMalloc((void **)&ctx->ccg_mv, sizeof(double) * n));
+        ctx->ccg_cap = n;
+    }
+    const double tol = 1e-12;  // CG_coarsest_tol, saena_object.h:156
+    int max_iter = 150;        // CG_coarsest_max_iter, saena_object.h:155
+    double *res = ctx->ccg_res, *dir = ctx->ccg_dir, *mv = ctx->ccg_mv;
+    SB_CUDA(cudaMemcpyAsync(res, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    SB_CUDA(cudaMemcpyAsync(dir, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    SB_TRY(sb_dot(ctx, res, res, n, S_C_RR));
+    SB_TRY(sb_read_scalars(ctx));
+    const double initial_dot = ctx->scalars_host[S_C_RR];
+    const double thres = initial_dot * tol * tol;
+    if (initial_dot < tol * tol) max_iter = 0;
+    int i = 1;
+    while (i < max_iter) {
+        EpiArgs e{};
+        e.out = mv;
+        SB_TRY(sb_apply(ctx, lv.A, dir, EPI_PLAIN, e));
+        SB_TRY(sb_dot(ctx, dir, mv, n, S_C_DEN));
+        ++ctx->launches;
+        ccg_update_kernel<<<red_blocks(ctx, n), 256, 0, ctx->stream>>>(n, u, res, dir, mv, ctx->scalars,
+                                                                      ctx->red_partials, ctx->red_counter,
+                                                                      ctx->scalars + S_C_RRNEW);
+        SB_CUDA(cudaGetLastError());
+        SB_TRY(sb_read_scalars(ctx));
+        if (ctx->scalars_host[S_C_RRNEW] < thres) break;
+        SB_TRY(sb_cg_p_update(ctx, n, dir, res, S_C_RRNEW, S_C_RR));  // dir = res + (dot/dot_prev) dir
+        SB_CUDA(cudaMemcpyAsync(ctx->scalars + S_C_RR, ctx->scalars + S_C_RRNEW, sizeof(double),
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+        i++;
+    }
     return 0;
 }
 

@@ -119,6 +119,9 @@ class Level:
     M_coarse: int = 0                    # Ac.M     : length of the coarse grid's vectors on this rank
     repart_send: List[tuple] = field(default_factory=list)  # (peer, offset_in_old, count)
     repart_recv: List[tuple] = field(default_factory=list)  # (peer, offset_in_new, count)
+    # D^-1/2 of this level's operator before it was scaled (saena_matrix::inv_sq_diag_orig); only
+    # when the hierarchy was set up with scale=true (saena_object_solve.cpp:1245-1247,1264-1266,2709-2711)
+    inv_sq_diag: Optional[np.ndarray] = None
 
 
 @dataclass
@@ -134,6 +137,7 @@ class Hierarchy:
     coarse_val: np.ndarray = field(default_factory=lambda: np.zeros(0, F64))
     nprocs: int = 1
     rank: int = 0
+    scale: bool = False   # saena_object::scale
 
     @property
     def max_level(self) -> int:
@@ -273,7 +277,7 @@ def partition_hierarchy(h: Hierarchy, nprocs: int, agglomerate_below: int = 0) -
         splits.append(sp)
     # the partition R writes into (split_old of level l+1): balanced unless level l itself is agglomerated
     out = [Hierarchy(levels=[], coarse_n=h.coarse_n, coarse_row=h.coarse_row, coarse_col=h.coarse_col,
-                     coarse_val=h.coarse_val, nprocs=nprocs, rank=r) for r in range(nprocs)]
+                     coarse_val=h.coarse_val, nprocs=nprocs, rank=r, scale=h.scale) for r in range(nprocs)]
     for l, lv in enumerate(h.levels):
         ip, ix, dv = operator_to_global_csr(lv.A)
         A_parts = split_operator(KIND_A, l, ip, ix, dv, lv.A.Nbig, splits[l], splits[l], lv.A.use_double)
@@ -294,7 +298,8 @@ def partition_hierarchy(h: Hierarchy, nprocs: int, agglomerate_below: int = 0) -
             r0, r1 = int(splits[l][r]), int(splits[l][r + 1])
             level = Level(level=l, A=A_parts[r], inv_diag=lv.inv_diag[r0:r1].copy(), eig_max=lv.eig_max,
                           P=P_parts[r] if P_parts else None, R=R_parts[r] if R_parts else None,
-                          active=(r1 > r0))
+                          active=(r1 > r0),
+                          inv_sq_diag=None if lv.inv_sq_diag is None else lv.inv_sq_diag[r0:r1].copy())
             if lv.P is not None:
                 so, sn = split_old_next, splits[l + 1]
                 level.M_coarse_old = int(so[r + 1] - so[r])
@@ -324,11 +329,13 @@ _OP_SCALARS = ("kind", "level", "M", "Mbig", "Nbig", "row_offset", "col_offset",
 
 
 def hierarchy_to_arrays(h: Hierarchy) -> dict:
-    out = {"meta": np.array([len(h.levels), h.coarse_n, h.nprocs, h.rank], I64),
+    out = {"meta": np.array([len(h.levels), h.coarse_n, h.nprocs, h.rank, int(h.scale)], I64),
            "coarse_row": h.coarse_row, "coarse_col": h.coarse_col, "coarse_val": h.coarse_val}
     for lv in h.levels:
         p = f"L{lv.level}."
         out[p + "inv_diag"] = lv.inv_diag
+        if lv.inv_sq_diag is not None:
+            out[p + "inv_sq_diag"] = lv.inv_sq_diag
         out[p + "scalars"] = np.array([lv.eig_max, float(lv.active), lv.M_coarse_old, lv.M_coarse,
                                        float(lv.P is not None)], F64)
         out[p + "repart_send"] = np.array(lv.repart_send, I32).reshape(-1, 3)
@@ -344,7 +351,10 @@ def hierarchy_to_arrays(h: Hierarchy) -> dict:
 
 
 def hierarchy_from_arrays(d) -> Hierarchy:
-    nlev, coarse_n, nprocs, rank = (int(x) for x in d["meta"])
+    meta = [int(x) for x in d["meta"]]
+    nlev, coarse_n, nprocs, rank = meta[:4]
+    scale = bool(meta[4]) if len(meta) > 4 else False
+    keys = set(d.files) if hasattr(d, "files") else set(d.keys())
     levels = []
     for l in range(nlev):
         p = f"L{l}."
@@ -359,10 +369,11 @@ def hierarchy_from_arrays(d) -> Hierarchy:
         lv = Level(level=l, A=op("A"), inv_diag=np.array(d[p + "inv_diag"]), eig_max=float(eig), active=bool(active),
                    M_coarse_old=int(mco), M_coarse=int(mc),
                    repart_send=[tuple(int(x) for x in r) for r in d[p + "repart_send"]],
-                   repart_recv=[tuple(int(x) for x in r) for r in d[p + "repart_recv"]])
+                   repart_recv=[tuple(int(x) for x in r) for r in d[p + "repart_recv"]],
+                   inv_sq_diag=np.array(d[p + "inv_sq_diag"]) if (p + "inv_sq_diag") in keys else None)
         if has_p:
             lv.P, lv.R = op("P"), op("R")
         levels.append(lv)
     return Hierarchy(levels=levels, coarse_n=coarse_n, coarse_row=np.array(d["coarse_row"]),
                      coarse_col=np.array(d["coarse_col"]), coarse_val=np.array(d["coarse_val"]), nprocs=nprocs,
-                     rank=rank)
+                     rank=rank, scale=scale)

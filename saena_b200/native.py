@@ -61,7 +61,9 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_destroy.argtypes = [vp]
     L.saena_b200_upload_operator.argtypes = [vp, ctypes.POINTER(OperatorDesc)]
     L.saena_b200_upload_level_aux.argtypes = [vp, i, dp, d, i, i, i, ctypes.POINTER(Block), i, ctypes.POINTER(Block)]
+    L.saena_b200_upload_level_scale.argtypes = [vp, i, dp]
     L.saena_b200_upload_coarsest.argtypes = [vp, i, ctypes.c_int64, c_i32_p, c_i32_p, dp]
+    L.saena_b200_set_coarsest_solver.argtypes = [vp, i]
     L.saena_b200_finalize.argtypes = [vp]
     solve_args = [vp, vp, vp, i, d, i, i, i, ip, dp, i, ip]
     L.saena_b200_solve_pcg.argtypes = solve_args
@@ -76,6 +78,7 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_dot.argtypes = [vp, vp, vp, i, dp]
     L.saena_b200_time_matvec.argtypes = [vp, i, i, i, i, ctypes.POINTER(ctypes.c_float)]
     L.saena_b200_time_smooth_sweep.argtypes = [vp, i, i, i, i, ctypes.POINTER(ctypes.c_float)]
+    L.saena_b200_time_matvec_parts.argtypes = [vp, i, i, i] + [ctypes.POINTER(ctypes.c_float)] * 3
     L.saena_b200_timer_start.argtypes = [vp]
     L.saena_b200_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.saena_b200_launch_count.restype = ctypes.c_int64
@@ -90,11 +93,12 @@ def load_library(path: Optional[str] = None):
 
 EXPORTED_SYMBOLS = [
     "saena_b200_nccl_unique_id", "saena_b200_init", "saena_b200_destroy", "saena_b200_last_error",
-    "saena_b200_upload_operator", "saena_b200_upload_level_aux", "saena_b200_upload_coarsest",
-    "saena_b200_finalize", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
+    "saena_b200_upload_operator", "saena_b200_upload_level_aux", "saena_b200_upload_level_scale",
+    "saena_b200_upload_coarsest",
+    "saena_b200_set_coarsest_solver", "saena_b200_finalize", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
-    "saena_b200_time_smooth_sweep", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_set_mapping", "saena_b200_get_mapping",
+    "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_set_mapping", "saena_b200_get_mapping",
     "saena_b200_operator_bytes",
 ]
 
@@ -191,6 +195,12 @@ class Context:
             self._ck(self._L.saena_b200_upload_level_aux(self._h, lv.level, _f64p(inv), float(lv.eig_max),
                                                         lv.M_coarse_old, lv.M_coarse, len(lv.repart_send), send,
                                                         len(lv.repart_recv), recv))
+        if h.scale:
+            for lv in h.levels:
+                if lv.inv_sq_diag is None:
+                    raise ValueError("scale=true hierarchy without inv_sq_diag on a level")
+                isq = np.ascontiguousarray(lv.inv_sq_diag, F64)
+                self._ck(self._L.saena_b200_upload_level_scale(self._h, lv.level, _f64p(isq)))
         owns_coarsest = h.levels[-1].A.M > 0
         if owns_coarsest:
             r, c = np.ascontiguousarray(h.coarse_row, I32), np.ascontiguousarray(h.coarse_col, I32)
@@ -201,6 +211,12 @@ class Context:
         self._ck(self._L.saena_b200_finalize(self._h))
         self.hier = h
         self.level_rows = [lv.A.M for lv in h.levels]
+
+    def set_coarsest_solver(self, name: str):
+        """'SuperLU' (default: direct solve) or 'CG' -- saena_object::direct_solver"""
+        if name not in ("SuperLU", "CG"):
+            raise ValueError("Error: Unknown direct solver!")   # saena_object_solve.cpp:1011-1013
+        self._ck(self._L.saena_b200_set_coarsest_solver(self._h, int(name == "CG")))
 
     # ---- solvers ----
     def _solve(self, fn, rhs, u, max_iter, tol, smoother, pre, post):
@@ -290,6 +306,13 @@ class Context:
         self._ck(self._L.saena_b200_time_smooth_sweep(self._h, level, smoother_id(smoother), reps, int(flush_l2),
                                                       ctypes.byref(ms)))
         return ms.value
+
+    def time_matvec_parts(self, level, kind, reps=20):
+        """-> (full_ms, local_only_ms, halo_only_ms); collective when nranks > 1"""
+        f, l, h = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(0)
+        self._ck(self._L.saena_b200_time_matvec_parts(self._h, level, kind, reps, ctypes.byref(f), ctypes.byref(l),
+                                                      ctypes.byref(h)))
+        return f.value, l.value, h.value
 
     def timer_start(self):
         self._ck(self._L.saena_b200_timer_start(self._h))

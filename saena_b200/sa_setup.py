@@ -34,6 +34,7 @@ plumbing for the setup only; nothing in the solve path imports this module.
 from __future__ import annotations
 
 import math
+import time
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -62,6 +63,11 @@ class SetupOptions:
     row_reduction_up_thrshld: float = 0.90   # saena_object.h:46
     lanczos_iters: int = 20
     seed: int = 2024
+
+
+def _sync(dev):
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
 
 
 class _Csr:
@@ -136,6 +142,33 @@ def _spgemm(A: _Csr, B: _Csr, chunk_products: int = 300_000_000) -> _Csr:
     return _Csr(A.n_rows, B.n_cols, torch.cat(rows_out), torch.cat(cols_out), torch.cat(vals_out))
 
 
+def _to_torch_csr(A: _Csr) -> torch.Tensor:
+    crow = torch.zeros(A.n_rows + 1, dtype=torch.int64, device=A.val.device)
+    crow[1:] = torch.cumsum(A.counts(), 0)
+    return torch.sparse_csr_tensor(crow, A.col, A.val, size=(A.n_rows, A.n_cols))
+
+
+def _galerkin(R: _Csr, A: _Csr, P: _Csr, dense_budget_bytes: float = 48e9) -> _Csr:
+    """Ac = R A P.  On the deep levels of a 3D hierarchy the product is nearly dense (256^3 Poisson,
+    level 3 -> 4: rows of A P have ~20 000 entries, 8e11 scalar products) and the sparse expansion
+    drowns; there the two products are done as sparse x dense (R (A P_dense)) and the result is
+    re-sparsified.  Structural zeros stay exact zeros, so the pattern is the sparse product's
+    (barring exact cancellation)."""
+    nc = P.n_cols
+    dense_bytes = 8.0 * A.n_rows * nc
+    avg_prod_per_row = (A.nnz / max(A.n_rows, 1)) * (P.nnz / max(P.n_rows, 1))
+    if A.val.is_cuda and 2 * dense_bytes <= dense_budget_bytes and avg_prod_per_row > 4 * nc:
+        Pd = torch.zeros(P.n_rows, nc, dtype=torch.float64, device=A.val.device)
+        Pd[P.row, P.col] = P.val
+        AP = torch.sparse.mm(_to_torch_csr(A), Pd)
+        del Pd
+        Ac = torch.sparse.mm(_to_torch_csr(R), AP)
+        del AP
+        idx = torch.nonzero(Ac, as_tuple=True)
+        return _Csr(nc, nc, idx[0], idx[1], Ac[idx])
+    return _spgemm(R, _spgemm(A, P))
+
+
 def _transpose(A: _Csr) -> _Csr:
     key = A.col * A.n_rows + A.row
     key, order = torch.sort(key)
@@ -161,38 +194,64 @@ def strength_graph(A: _Csr, conn_str: float):
     return A.row[strong], A.col[strong]
 
 
+def _expand_segments(ptr: torch.Tensor, rows: torch.Tensor):
+    """entry indices of the CSR segments of `rows` and, per entry, the position of its row in `rows`"""
+    dev = rows.device
+    start = ptr[rows]
+    deg = ptr[rows + 1] - start
+    total = int(deg.sum())
+    seg = torch.repeat_interleave(torch.arange(rows.numel(), device=dev), deg, output_size=total)
+    first = torch.cumsum(deg, 0) - deg
+    e = start[seg] + (torch.arange(total, device=dev) - first[seg])
+    return e, seg
+
+
 def aggregate(n: int, s_row: torch.Tensor, s_col: torch.Tensor):
-    """aggregation_1_dist on one rank, round for round.  Returns (aggregate id per node in coarse
-    numbering, number of aggregates, rounds)."""
+    """aggregation_1_dist on one rank.  The reference sweeps every undecided node in every round;
+    a node's outcome can only change when one of its neighbours was decided in the round before,
+    so only those nodes are re-evaluated here (same rule, same synchronous updates, hence the same
+    aggregates -- tests/test_sa_setup.py compares with the reference's).  Returns (aggregate id per
+    node in coarse numbering, number of aggregates, rounds)."""
     dev = s_row.device
-    idx = torch.arange(n, dtype=torch.int64, device=dev)
-    agg = idx.clone()
+    # CSR of the strength graph by row (s_row is ascending: A is row-major sorted) and by column
+    ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    ptr[1:] = torch.cumsum(torch.bincount(s_row, minlength=n), 0)
+    order = torch.argsort(s_col, stable=True)
+    t_nb = s_row[order]                      # rows that list node j as a neighbour, grouped by j
+    tptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    tptr[1:] = torch.cumsum(torch.bincount(s_col, minlength=n), 0)
+    del order
+    agg = torch.arange(n, dtype=torch.int64, device=dev)
     decided = torch.zeros(n, dtype=torch.bool, device=dev)
     is_root = torch.zeros(n, dtype=torch.bool, device=dev)
+    F = torch.arange(n, dtype=torch.int64, device=dev)   # undecided nodes to evaluate this round
     rounds = 0
-    act_row, act_col = s_row, s_col
-    while True:
+    while F.numel():
         rounds += 1
+        e, seg = _expand_segments(ptr, F)
+        nb = s_col[e]
         # eligible neighbours: undecided or root; their aggregate value is their own index
-        elig = (~decided[act_col]) | is_root[act_col]
-        cand = torch.where(elig, act_col, torch.full_like(act_col, BIG))
-        m = torch.full((n,), BIG, dtype=torch.int64, device=dev)
-        m.scatter_reduce_(0, act_row, cand, reduce="amin")
-        take = m < idx                                   # a smaller eligible neighbour exists
-        mc = torch.where(take, m, idx)
-        dec_nei = torch.where(take, decided[mc], torch.ones_like(decided))
+        elig = (~decided[nb]) | is_root[nb]
+        cand = torch.where(elig, nb, torch.full_like(nb, BIG))
+        m = torch.full((F.numel(),), BIG, dtype=torch.int64, device=dev)
+        m.scatter_reduce_(0, seg, cand, reduce="amin")
+        take = m < F                                     # a smaller eligible neighbour exists
+        mc = torch.where(take, m, F)
+        dec_nei = torch.where(take, decided[mc], torch.ones_like(take))
         root_nei = take & is_root[mc]
-        upd = (~decided) & dec_nei
-        new_root = upd & (~take)
-        join = upd & root_nei
-        agg = torch.where(join, mc, agg)
-        is_root |= new_root
-        decided |= upd
-        if bool(decided.all()):
-            break
-        if rounds % 8 == 0:                              # drop the entries of decided rows
-            keep = ~decided[act_row]
-            act_row, act_col = act_row[keep], act_col[keep]
+        new_root = dec_nei & (~take)
+        join = dec_nei & root_nei
+        newly = F[dec_nei]
+        # synchronous update: everything above read the state of the previous round
+        agg[F[join]] = mc[join]
+        is_root[F[new_root]] = True
+        decided[newly] = True
+        # next round: undecided nodes one of whose neighbours was just decided
+        te, _ = _expand_segments(tptr, newly)
+        cand_rows = t_nb[te]
+        cand_rows = cand_rows[~decided[cand_rows]]
+        F = torch.unique(cand_rows)
+    assert bool(decided.all())
     # aggregate_index_update: coarse id = rank of the root among the sorted roots
     coarse_of_root = torch.cumsum(is_root.to(torch.int64), 0) - 1
     return coarse_of_root[agg], int(is_root.sum()), rounds
@@ -406,11 +465,14 @@ def build_device_hierarchy(n: int, row, col, val, opts: Optional[SetupOptions] =
             print(f"level {l}: rows {A.n_rows} nnz {A.nnz} ({A.nnz / A.n_rows:.1f}/row) eig {eig:.4f}", flush=True)
         if l >= opts.max_level or last_level:
             break
+        t_ag = time.perf_counter()
         s_r, s_c = strength_graph(A, opts.conn_str)
         agg_c, nc, rounds = aggregate(A.n_rows, s_r, s_c)
         del s_r, s_c
         if verbose:
-            print(f"   aggregation: {nc} aggregates in {rounds} rounds", flush=True)
+            _sync(dev)
+            print(f"   aggregation: {nc} aggregates in {rounds} rounds, {time.perf_counter() - t_ag:.1f}s", flush=True)
+        t_rap = time.perf_counter()
         # find_aggregation's dynamic-level rule: the level about to be created is the last one
         if opts.dynamic_levels:
             last_level = bool(nc <= opts.least_row_threshold or
@@ -419,12 +481,15 @@ def build_device_hierarchy(n: int, row, col, val, opts: Optional[SetupOptions] =
             last_level = (l + 1 == opts.max_level)
         P = prolongator(A, agg_c, nc, inv_diag)
         R = _transpose(P)
-        Ac = _spgemm(R, _spgemm(A, P))
+        Ac = _galerkin(R, A, P)
         filter_it += 1
         if filter_it >= opts.filter_start:
             filter_thre = min(filter_thre, opts.filter_max)
             Ac = filter_entries(Ac, filter_thre)
             filter_thre *= 10 ** opts.filter_rate
+        if verbose:
+            _sync(dev)
+            print(f"   P, R, RAP, filter: {time.perf_counter() - t_rap:.1f}s", flush=True)
         lv.P, lv.R = P, R
         lv.pr_use_double = not (l >= opts.float_level)     # saena_object.cpp:277-280
         a_use_double = not (l + 1 >= opts.float_level)     # :281-284

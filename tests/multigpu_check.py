@@ -1,0 +1,109 @@
+"""Multi-GPU parity check, one process per GPU (torchrun):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29544 tests/multigpu_check.py
+
+Every rank partitions the golden (reference-built) hierarchy, uploads ITS share and runs the
+distributed operators / V-cycle / PCG over NCCL; rank 0 gathers the pieces and compares with the
+CPU oracle's emulation of the same partition (same float halo truncation, same agglomeration).
+Also run (on one box with >= 2 GPUs) by tests/test_multigpu.py.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.oracle import Oracle  # noqa: E402
+from saena_b200 import native  # noqa: E402
+from saena_b200.distributed import exchange_nccl_id  # noqa: E402
+from saena_b200.hierarchy import KIND_A, KIND_P, KIND_R, partition_hierarchy  # noqa: E402
+from tests.util import GOLDEN, TOL_HIST, TOL_OP, Golden, rel  # noqa: E402
+
+
+def gather(x, sizes, rank, world):
+    """concatenate per-rank numpy vectors on every rank"""
+    out = [torch.zeros(s, dtype=torch.float64, device="cuda") for s in sizes]
+    dist.all_gather(out, torch.from_numpy(np.ascontiguousarray(x)).cuda()) if len(set(sizes)) == 1 else None
+    if len(set(sizes)) != 1:
+        mx = max(sizes)
+        pad = torch.zeros(mx, dtype=torch.float64, device="cuda")
+        pad[:len(x)] = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        bufs = [torch.zeros(mx, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(bufs, pad)
+        out = [b[:s] for b, s in zip(bufs, sizes)]
+    return [o.cpu().numpy() for o in out]
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    nccl_id = exchange_nccl_id(native.nccl_unique_id)
+    ctx = native.Context(device=local, rank=rank, nranks=world, nccl_id=nccl_id)
+    worst = {}
+    for name, agg in ((GOLDEN[1], 150), (GOLDEN[1], 0), (GOLDEN[0], 10 ** 9)):
+        g = Golden(name)
+        hs = partition_hierarchy(g.hier, world, agglomerate_below=agg)
+        mine = hs[rank]
+        ctx.upload_hierarchy(mine)
+        o = Oracle(hs)
+        rng = np.random.default_rng(17)
+        tag = f"{name}/agg{agg}"
+        for l in range(len(mine.levels)):
+            sizes = [h.levels[l].A.M for h in hs]
+            off = np.concatenate(([0], np.cumsum(sizes)))
+            full_v, full_b = rng.standard_normal(off[-1]), rng.standard_normal(off[-1])
+            v_parts = [full_v[off[i]:off[i + 1]] for i in range(world)]
+            b_parts = [full_b[off[i]:off[i + 1]] for i in range(world)]
+            want = o.matvec(l, KIND_A, v_parts)
+            got = ctx.matvec(l, KIND_A, v_parts[rank])
+            worst[f"{tag}.L{l}.A"] = rel(np.concatenate(gather(got, sizes, rank, world)), np.concatenate(want))
+            want = o.smooth(l, "chebyshev", 3, v_parts, b_parts)
+            got = ctx.smooth(l, "chebyshev", 3, v_parts[rank], b_parts[rank])
+            worst[f"{tag}.L{l}.cheb3"] = rel(np.concatenate(gather(got, sizes, rank, world)), np.concatenate(want))
+            if mine.levels[l].P is not None:
+                csz = [h.levels[l].P.n_local_cols for h in hs]
+                coff = np.concatenate(([0], np.cumsum(csz)))
+                full_c = rng.standard_normal(coff[-1])
+                c_parts = [full_c[coff[i]:coff[i + 1]] for i in range(world)]
+                want = o.matvec(l, KIND_P, c_parts)
+                got = ctx.matvec(l, KIND_P, c_parts[rank])
+                worst[f"{tag}.L{l}.P"] = rel(np.concatenate(gather(got, sizes, rank, world)), np.concatenate(want))
+                want = o.matvec(l, KIND_R, v_parts)
+                got = ctx.matvec(l, KIND_R, v_parts[rank])
+                worst[f"{tag}.L{l}.R"] = rel(np.concatenate(gather(got, csz, rank, world)), np.concatenate(want))
+            want = o.vcycle(l, [np.zeros(s) for s in sizes], b_parts)
+            got = ctx.vcycle(l, np.zeros(sizes[rank]), b_parts[rank])
+            worst[f"{tag}.L{l}.vcycle"] = rel(np.concatenate(gather(got, sizes, rank, world)), np.concatenate(want)) / 10
+        sizes = [h.levels[0].A.M for h in hs]
+        off = np.concatenate(([0], np.cumsum(sizes)))
+        rhs_parts = [g.rhs[off[i]:off[i + 1]] for i in range(world)]
+        u_o, it_o, h_o = o.solve_pcg(rhs_parts, g.max_iter, g.tol, "chebyshev", g.pre, g.post)
+        u, it, h = ctx.solve_pcg(rhs_parts[rank], g.max_iter, g.tol, "chebyshev", g.pre, g.post)
+        assert abs(it - it_o) <= 1, (tag, it, it_o)
+        n = min(len(h), len(h_o))
+        herr = float(np.max(np.abs(h[:n] - h_o[:n]) / h_o[:n]))
+        assert herr <= TOL_HIST, (tag, herr)
+        uerr = rel(np.concatenate(gather(u, sizes, rank, world)), np.concatenate(u_o))
+        assert uerr < 1e-8, (tag, uerr)
+        d = ctx.dot(rhs_parts[rank], rhs_parts[rank])
+        assert abs(d - float(g.rhs @ g.rhs)) <= 1e-12 * float(g.rhs @ g.rhs)
+        if rank == 0:
+            print(f"{tag}: pcg iters {it} (oracle {it_o}), history err {herr:.2e}, u err {uerr:.2e}", flush=True)
+    bad = {k: e for k, e in worst.items() if not e <= TOL_OP}
+    assert not bad, bad
+    dist.barrier()
+    if rank == 0:
+        print(f"MULTIGPU_OK world={world} worst={max(worst.values()):.2e}", flush=True)
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

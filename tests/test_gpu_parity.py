@@ -88,9 +88,11 @@ def test_other_solvers_and_option_sets_against_oracle(golden_ctx):
         u, it, h = ctx.solve_pcg(g.rhs, 50, 1e-8, "chebyshev", pre, post)
         check_pcg(it, h, u, it_o, h_o, u_o, tol_hist=1e-7)
     # saena_object::solve (stationary V-cycles)
+    # (its residual is recomputed as A u - rhs every cycle: near convergence that difference
+    #  cancels ~8 digits, so two correct evaluations of ||r|| agree only to eps*||rhs||/||r|| ~ 1e-8)
     u_o, it_o, h_o = o.solve_vcycle(g.rhs, 50, 1e-8)
     u, it, h = ctx.solve_vcycle(g.rhs, 50, 1e-8)
-    check_pcg(it, h, u, it_o, h_o, u_o)
+    check_pcg(it, h, u, it_o, h_o, u_o, tol_hist=1e-6)
     # saena_object::solve_CG (unpreconditioned): must converge to the same solution
     u_cg, it_cg, h_cg = ctx.solve_cg(g.rhs, 2000, 1e-10)
     assert h_cg[-1] / h_cg[0] < 1e-10
@@ -98,7 +100,7 @@ def test_other_solvers_and_option_sets_against_oracle(golden_ctx):
 
 
 def _random_csr(rng, n_rows, n_cols, row_nnz):
-    counts = np.asarray(row_nnz, np.int32)
+    counts = np.minimum(np.asarray(row_nnz, np.int32), n_cols)
     cols = np.concatenate([np.sort(rng.choice(n_cols, c, replace=False)) for c in counts]) if counts.sum() else \
         np.zeros(0, np.int64)
     return counts, cols.astype(np.int32), rng.uniform(-1, 1, counts.sum())
@@ -158,6 +160,49 @@ def test_edge_case_row_shapes(case):
         assert rel(ctx.matvec(0, KIND_P, vc), o.matvec(0, KIND_P, vc)) < TOL_OP
         assert rel(ctx.matvec(0, KIND_R, v), o.matvec(0, KIND_R, v)) < TOL_OP
         assert rel(ctx.vcycle(0, v, b), o.vcycle(0, v, b)) < 1e-11
+    finally:
+        ctx.close()
+
+
+def test_coarsest_cg_option(golden_ctx):
+    """direct_solver == "CG": solve_coarsest_CG (saena_object_solve.cpp:14-114) instead of the direct solve"""
+    g, ctx = golden_ctx
+    o = Oracle(g.hier, coarsest_cg=True)
+    ctx.set_coarsest_solver("CG")
+    try:
+        b = np.random.default_rng(4).standard_normal(g.hier.levels[0].A.M)
+        assert rel(ctx.vcycle(0, np.zeros_like(b), b), o.vcycle(0, np.zeros_like(b), b)) < 1e-11
+        u_o, it_o, h_o = o.solve_pcg(g.rhs, g.max_iter, g.tol)
+        u, it, h = ctx.solve_pcg(g.rhs, g.max_iter, g.tol)
+        check_pcg(it, h, u, it_o, h_o, u_o)
+    finally:
+        ctx.set_coarsest_solver("SuperLU")
+
+
+def test_scale_hooks():
+    """saena_object::scale == true: the V-cycle multiplies the restricted residual and the coarse
+    correction by the coarse level's D^-1/2 and the solvers scale the final u
+    (saena_object_solve.cpp:1245-1247, :1264-1266, :2709-2711).  Checked against the oracle's
+    restatement: the reference itself cannot run this path (see oracle/ref.py)."""
+    g = Golden(GOLDEN[1])
+    h = g.hier
+    rng = np.random.default_rng(8)
+    h.scale = True
+    for lv in h.levels:
+        lv.inv_sq_diag = rng.uniform(0.8, 1.25, lv.A.M)
+    o = Oracle(h)
+    ctx = Context()
+    try:
+        ctx.upload_hierarchy(h)
+        b = rng.standard_normal(h.levels[0].A.M)
+        assert rel(ctx.vcycle(0, np.zeros_like(b), b), o.vcycle(0, np.zeros_like(b), b)) < 1e-11
+        u_o, it_o, h_o = o.solve_pcg(g.rhs, 50, 1e-8)
+        u, it, hist = ctx.solve_pcg(g.rhs, 50, 1e-8)
+        check_pcg(it, hist, u, it_o, h_o, u_o, tol_hist=1e-7)   # scaled V-cycle is not symmetric
+        # and it differs from the unscaled solve, i.e. the hooks really ran
+        h.scale = False
+        u_plain, _, _ = Oracle(h).solve_pcg(g.rhs, 50, 1e-8)
+        assert rel(u, u_plain) > 1e-3
     finally:
         ctx.close()
 

@@ -48,6 +48,21 @@ def test_pcg_iterations_and_history(poisson16):
     check_pcg(it, hist, u, it_ref, hist_ref, u_ref, TOL_HIST)
 
 
+def test_coarsest_cg_direct_solver_option(poisson16):
+    s, h = poisson16
+    o = Oracle(h, coarsest_cg=True)
+    b = np.random.default_rng(3).standard_normal(h.coarse_n)
+    assert rel(o.coarsest_cg(b), s.coarsest_cg(b)) < TOL_OP
+    s.set_direct_solver("CG")
+    try:
+        u_ref, it_ref, hist_ref = s.solve_pcg()
+        u, it, hist = o.solve_pcg(s.rhs(), s.opts.max_iter, s.opts.tol, "chebyshev", s.opts.pre, s.opts.post)
+        assert it == it_ref
+        check_pcg(it, hist, u, it_ref, hist_ref, u_ref, TOL_HIST)
+    finally:
+        s.set_direct_solver("SuperLU")
+
+
 def test_pcg_jacobi_smoother_and_max_iter_cap(poisson16):
     s, h = poisson16
     # jacobi 2/1 converges slower; cap the iterations to exercise the `i == max_iter` exit
