@@ -34,6 +34,7 @@ plumbing for the setup only; nothing in the solve path imports this module.
 from __future__ import annotations
 
 import math
+import sys
 import time
 from dataclasses import dataclass
 from typing import List, Optional
@@ -462,7 +463,7 @@ def build_device_hierarchy(n: int, row, col, val, opts: Optional[SetupOptions] =
         lv = DeviceLevel(A=A, inv_diag=inv_diag, eig_max=eig, a_use_double=a_use_double)
         levels.append(lv)
         if verbose:
-            print(f"level {l}: rows {A.n_rows} nnz {A.nnz} ({A.nnz / A.n_rows:.1f}/row) eig {eig:.4f}", flush=True)
+            print(f"level {l}: rows {A.n_rows} nnz {A.nnz} ({A.nnz / A.n_rows:.1f}/row) eig {eig:.4f}", file=sys.stderr, flush=True)
         if l >= opts.max_level or last_level:
             break
         t_ag = time.perf_counter()
@@ -471,7 +472,7 @@ def build_device_hierarchy(n: int, row, col, val, opts: Optional[SetupOptions] =
         del s_r, s_c
         if verbose:
             _sync(dev)
-            print(f"   aggregation: {nc} aggregates in {rounds} rounds, {time.perf_counter() - t_ag:.1f}s", flush=True)
+            print(f"   aggregation: {nc} aggregates in {rounds} rounds, {time.perf_counter() - t_ag:.1f}s", file=sys.stderr, flush=True)
         t_rap = time.perf_counter()
         # find_aggregation's dynamic-level rule: the level about to be created is the last one
         if opts.dynamic_levels:
@@ -489,7 +490,7 @@ def build_device_hierarchy(n: int, row, col, val, opts: Optional[SetupOptions] =
             filter_thre *= 10 ** opts.filter_rate
         if verbose:
             _sync(dev)
-            print(f"   P, R, RAP, filter: {time.perf_counter() - t_rap:.1f}s", flush=True)
+            print(f"   P, R, RAP, filter: {time.perf_counter() - t_rap:.1f}s", file=sys.stderr, flush=True)
         lv.P, lv.R = P, R
         lv.pr_use_double = not (l >= opts.float_level)     # saena_object.cpp:277-280
         a_use_double = not (l + 1 >= opts.float_level)     # :281-284
