@@ -35,7 +35,8 @@ import numpy as np  # noqa: E402
 METRIC = "AMG-PCG solve throughput, 3D 7-pt Poisson, rel. residual 1e-8 (unknowns solved per second)"
 UNIT = "Munknowns/s"
 OPTS = dict(max_iter=50, tol=1e-8, smoother="chebyshev", pre=3, post=3)   # data/options006_poisson.xml
-CPU_SAMPLE_MX = 50                                                         # reference arm: 48^3 unknowns
+# reference arm: laplacian3D(mx) -> (mx-2)^3 = 48^3 unknowns (env override only for the contract test)
+CPU_SAMPLE_MX = int(os.environ.get("SAENA_BENCH_CPU_MX", 50))
 
 
 def log(*a):
@@ -160,7 +161,8 @@ def main():
     ap.add_argument("--n", type=int, default=int(os.environ.get("SAENA_BENCH_N", 256)),
                     help="unknowns per dimension (256 = BASELINE.json configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--agglomerate-below", type=int, default=200_000)
+    ap.add_argument("--agglomerate-below", type=int, default=10_000,
+                    help="N>1: levels with fewer global rows live on rank 0 (the reference's shrink-to-one-rank)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -280,7 +282,7 @@ def main():
     _, dl, dbytes, dms = dominant
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         traffic = json.load(open(tp)).get(f"n{n}_level{dl}_cheb_sweep")
     roofline = {"bound": "hbm", "achieved": dbytes / dms / 1e6, "peak": peak, "unit": "GB/s",
                 "frac": dbytes / dms / 1e6 / peak, "traffic": traffic,

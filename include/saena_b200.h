@@ -114,6 +114,10 @@ int saena_b200_upload_coarsest(saena_b200_ctx *ctx, int n, int64_t nnz, const in
  * in the reference, the dense factor here), 1 = solve_coarsest_CG (src/saena_object_solve.cpp:14-114). */
 int saena_b200_set_coarsest_solver(saena_b200_ctx *ctx, int use_cg);
 
+/* The preconditioner's V-cycle is replayed from a CUDA graph (captured on first use) when it
+ * contains no communication and no host-side decision; 0 switches that off (eager launches). */
+int saena_b200_set_graphs(saena_b200_ctx *ctx, int on);
+
 /* Seal the hierarchy: allocates the per-level work vectors (Grid::allocate_mem, grid.cpp:165-172)
  * and picks each operator's kernel mapping from its nnz/row. */
 int saena_b200_finalize(saena_b200_ctx *ctx);

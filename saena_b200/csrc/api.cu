@@ -72,6 +72,7 @@ int saena_b200_destroy(saena_b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
+    sb_invalidate_graphs(ctx);
     for (size_t l = 0; l < ctx->levels.size(); ++l) {
         DevLevel &lv = ctx->levels[l];
         sb_free_operator(lv.A); sb_free_operator(lv.P); sb_free_operator(lv.R);
@@ -139,6 +140,7 @@ int saena_b200_upload_level_scale(saena_b200_ctx *ctx, int level, const double *
     SB_CUDA(cudaMalloc((void **)&lv.inv_sq_diag, sizeof(double) * std::max(lv.M, 1)));
     if (lv.M) SB_CUDA(cudaMemcpy(lv.inv_sq_diag, inv_sq_diag_orig, sizeof(double) * lv.M, cudaMemcpyHostToDevice));
     if (level == 0) ctx->scale = true;
+    sb_invalidate_graphs(ctx);
     return 0;
 }
 
@@ -216,6 +218,7 @@ int saena_b200_finalize(saena_b200_ctx *ctx) {
     SB_CUDA(cudaSetDevice(ctx->device));
     const int L = (int)ctx->levels.size();
     if (L == 0) SB_FAIL("finalize: no level uploaded");
+    sb_invalidate_graphs(ctx);
     for (int l = 0; l < L; ++l) {
         DevLevel &lv = ctx->levels[l];
         if (!lv.A.present) SB_FAIL("finalize: a level has no A");
@@ -331,7 +334,7 @@ static int pcg_device(saena_b200_ctx *ctx, const double *rhs, double *u, int max
         return 0;
     }
     // rho = 0; vcycle(rho, r) (:2535-2537); rho lives in level 0's iterate buffers
-    SB_TRY(sb_vcycle(ctx, 0, smoother, pre, post, r, true));
+    SB_TRY(sb_vcycle_from_zero(ctx, smoother, pre, post, r));
     // p = rho (:2554)
     if (n) SB_CUDA(cudaMemcpyAsync(p, l0.u[l0.cur], sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
     const double THRSHLD = init_dot * tol * tol;  // :2558
@@ -346,7 +349,7 @@ static int pcg_device(saena_b200_ctx *ctx, const double *rhs, double *u, int max
         current_dot = ctx->scalars_host[S_RR];
         push_hist(current_dot, hist, hist_cap, nh);
         if (!(current_dot >= THRSHLD)) break;          // :2620 (NaN also stops)
-        SB_TRY(sb_vcycle(ctx, 0, smoother, pre, post, r, true));  // :2640-2641
+        SB_TRY(sb_vcycle_from_zero(ctx, smoother, pre, post, r));  // :2640-2641
         SB_TRY(sb_dot(ctx, r, l0.u[l0.cur], n, S_BETA_NUM));      // :2655
         SB_TRY(sb_pcg_p_update(ctx, n, p, l0.u[l0.cur]));          // :2662-2667
     }
@@ -636,12 +639,21 @@ int saena_b200_set_mapping(saena_b200_ctx *ctx, int level, int kind, int mapping
     DevOperator *op = get_op(ctx, level, kind);
     if (!op) SB_FAIL("set_mapping: no such operator");
     op->forced_mapping = mapping;
+    sb_invalidate_graphs(ctx);
     return sb_prepare_operator(ctx, *op);
 }
 
 int saena_b200_set_coarsest_solver(saena_b200_ctx *ctx, int use_cg) {
     if (!ctx) return 1;
     ctx->coarsest_cg = use_cg != 0;
+    sb_invalidate_graphs(ctx);
+    return 0;
+}
+
+int saena_b200_set_graphs(saena_b200_ctx *ctx, int on) {
+    if (!ctx) return 1;
+    ctx->use_graphs = on != 0;
+    if (!on) sb_invalidate_graphs(ctx);
     return 0;
 }
 

@@ -98,12 +98,24 @@ struct DevOperator {
     int64_t sell_padded_est = 0;    // what the padding would be (computed at upload)
 
     // remote block re-sorted by row at upload: boundary rows only
+    // interior rows = the contiguous range [int_lo, int_hi) (multiples of 32) that holds no row with
+    // remote entries: for a slab partition the rows touching ghosts sit at the two ends of the
+    // block.  The overlapped kernel runs on that range only; everything outside is a "boundary
+    // row" finished after the halo arrives -- nothing is computed twice.
+    int int_lo = 0, int_hi = 0;
     int n_brows = 0;
     int *brow = nullptr;       // [n_brows] local row id, ascending
     int *brow_ptr = nullptr;   // [n_brows+1]
     int *bcol = nullptr;       // [nnz_remote] index into the ghost buffer
     double *bval = nullptr;    // [nnz_remote]
     uint32_t *brow_mask = nullptr;  // bit i set <=> row i has remote entries (local kernel skips its epilogue)
+
+    // merged mode: when most rows touch ghost columns (deep coarse levels: every row couples to
+    // every rank) the local/remote split degenerates.  The operator is then stored ONCE over the
+    // extended column space [local columns | ghost columns] and applied to x_ext = [x | ghosts]
+    // after the exchange, with the ordinary kernels.
+    bool merged = false;
+    double *x_ext = nullptr;  // [n_local_cols + recvSize]
 
     // halo plan
     int vIndexSize = 0, recvSize = 0;
@@ -146,6 +158,17 @@ struct DevLevel {
     double *xfer_old = nullptr;  // coarse vector in the old partition (Ac.M_old), used when repart is not identity
 };
 
+// A V-cycle from a zero iterate is the same launch sequence every time (same buffers, same
+// per-level Chebyshev constants): it is captured once per (rhs, smoother, pre, post) into a CUDA
+// graph and replayed -- the coarse levels are launch-latency-bound, ~90 launches per V-cycle.
+struct VcycleGraph {
+    const double *rhs;
+    int smoother, pre, post;
+    cudaGraphExec_t exec;
+    int64_t launches;
+    std::vector<int> cur_after;  // each level's ping-pong parity when the V-cycle ends
+};
+
 struct saena_b200_ctx {
     int device = 0, rank = 0, nranks = 1;
     std::string error;
@@ -156,6 +179,8 @@ struct saena_b200_ctx {
     int sm_count = 148;
     std::vector<DevLevel> levels;
     bool finalized = false;
+    bool use_graphs = true;
+    std::vector<VcycleGraph> graphs;
     bool scale = false;  // saena_object::scale
     int apply_mode = 0;  // measurement only: 0 full, 1 local kernels only (no exchange), 2 pack + exchange only
     int64_t launches = 0;
@@ -234,3 +259,6 @@ int sb_read_scalars(saena_b200_ctx *ctx);  // device scalars -> scalars_host (sy
 // ---- solve.cu
 int sb_smooth(saena_b200_ctx *ctx, int l, int smoother, int iters, const double *rhs, bool u_is_zero);
 int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const double *rhs, bool u_is_zero);
+// level-0 V-cycle from a zero iterate, replayed from a CUDA graph when nothing in it needs the host
+int sb_vcycle_from_zero(saena_b200_ctx *ctx, int smoother, int pre, int post, const double *rhs);
+void sb_invalidate_graphs(saena_b200_ctx *ctx);

@@ -33,7 +33,9 @@ static int dev_upload(saena_b200_ctx *ctx, T **dst, const T *src, size_t n) {
 void sb_free_operator(DevOperator &op) {
     cudaFree(op.rowptr); cudaFree(op.col); cudaFree(op.val); cudaFree(op.blk_row);
     cudaFree(op.brow); cudaFree(op.brow_ptr); cudaFree(op.bcol); cudaFree(op.bval); cudaFree(op.brow_mask);
-    cudaFree(op.vIndex); cudaFree(op.send_buf); cudaFree(op.ghost_buf);
+    cudaFree(op.vIndex); cudaFree(op.send_buf);
+    if (!(op.merged && op.use_double)) cudaFree(op.ghost_buf);
+    cudaFree(op.x_ext);
     cudaFree(op.sell_ptr); cudaFree(op.sell_col); cudaFree(op.sell_val);
     op = DevOperator();
 }
@@ -50,6 +52,8 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
     op.kind = d->kind;
     op.level = d->level;
     op.M = d->M;
+    op.int_lo = 0;
+    op.int_hi = d->M;
     op.n_local_cols = d->n_local_cols;
     op.col_offset = d->col_offset;
     op.nnz_local = d->nnz_local;
@@ -59,8 +63,66 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
     if (d->kind == SAENA_B200_KIND_A) lv.M = d->M;
     const int M = d->M;
 
+    // ---- halo-dominated operator: one CSR over [local | ghost] columns (see DevOperator::merged)
+    int n_rows_with_remote = 0;
+    if (d->nnz_remote > 0) {
+        std::vector<char> has(M, 0);
+        for (int64_t k = 0; k < d->nnz_remote; ++k)
+            if (d->row_remote[k] >= 0 && d->row_remote[k] < M && !has[d->row_remote[k]]) { has[d->row_remote[k]] = 1; ++n_rows_with_remote; }
+    }
+    op.merged = d->nnz_remote > 0 && n_rows_with_remote * 4 >= M;
+    if (op.merged) {
+        const int64_t nl = d->nnz_local, nr = d->nnz_remote, nt = nl + nr;
+        std::vector<int64_t> rp(M + 1, 0);
+        for (int i = 0; i < M; ++i) rp[i + 1] = d->nnzPerRow_local[i];
+        for (int64_t k = 0; k < nr; ++k) ++rp[d->row_remote[k] + 1];
+        for (int i = 0; i < M; ++i) rp[i + 1] += rp[i];
+        if (rp[M] != nt) SB_FAIL("upload_operator: inconsistent local/remote counts");
+        std::vector<int> mc((size_t)nt);
+        std::vector<double> mv((size_t)nt);
+        std::vector<int64_t> fill(rp.begin(), rp.end() - 1);
+        int64_t k = 0;
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < d->nnzPerRow_local[i]; ++j, ++k) {
+                const int c = d->col_local[k] - d->col_offset;
+                if (c < 0 || c >= d->n_local_cols) SB_FAIL("upload_operator: col_local outside this rank's column block");
+                mc[fill[i]] = c;
+                mv[fill[i]++] = d->val_local[k];
+            }
+        k = 0;
+        for (int g = 0; g < d->col_remote_size; ++g)
+            for (int t = 0; t < d->nnzPerCol_remote[g]; ++t, ++k) {
+                const int i = d->row_remote[k];
+                mc[fill[i]] = d->n_local_cols + g;
+                mv[fill[i]++] = d->val_remote[k];
+            }
+        if (k != nr) SB_FAIL("upload_operator: sum(nnzPerCol_remote) != nnz_remote");
+        op.nnz_local = nt;   // the kernels see one block
+        op.nnz_remote = 0;
+        op.wide_offsets = nt >= (int64_t)INT32_MAX;
+        op.sell_padded_est = 0;
+        for (int s0 = 0; s0 < M; s0 += 32) {
+            int64_t mx = 0;
+            for (int i = s0; i < std::min(M, s0 + 32); ++i) mx = std::max(mx, rp[i + 1] - rp[i]);
+            op.sell_padded_est += mx * 32;
+        }
+        if (op.wide_offsets) {
+            int64_t *p = nullptr;
+            SB_TRY(dev_upload(ctx, &p, rp.data(), rp.size()));
+            op.rowptr = p;
+        } else {
+            std::vector<int> rp32(rp.begin(), rp.end());
+            int *p = nullptr;
+            SB_TRY(dev_upload(ctx, &p, rp32.data(), rp32.size()));
+            op.rowptr = p;
+        }
+        SB_TRY(dev_upload(ctx, &op.col, mc.data(), mc.size()));
+        SB_TRY(dev_upload(ctx, &op.val, mv.data(), mv.size()));
+        SB_CUDA(cudaMalloc((void **)&op.x_ext, sizeof(double) * std::max<size_t>((size_t)d->n_local_cols + d->col_remote_size, 1)));
+    }
+
     // ---- local block -> CSR with local column ids
-    {
+    if (!op.merged) {
         std::vector<int64_t> rp(M + 1, 0);
         for (int i = 0; i < M; ++i) rp[i + 1] = rp[i] + d->nnzPerRow_local[i];
         if (rp[M] != d->nnz_local) SB_FAIL("upload_operator: sum(nnzPerRow_local) != nnz_local");
@@ -100,7 +162,7 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
 
     // ---- remote block: column-major by sender -> row-major over boundary rows
     op.recvSize = d->col_remote_size;
-    if (d->nnz_remote > 0) {
+    if (d->nnz_remote > 0 && !op.merged) {
         const int64_t nr = d->nnz_remote;
         std::vector<int> ghost_of((size_t)nr);
         {
@@ -114,10 +176,22 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
             if (d->row_remote[k] < 0 || d->row_remote[k] >= M) SB_FAIL("upload_operator: row_remote out of range");
             ++cnt[d->row_remote[k] + 1];
         }
+        // longest run of rows without remote entries -> interior range, trimmed to multiples of 32
+        int best_lo = 0, best_hi = 0;
+        for (int i = 0; i < M;) {
+            if (cnt[i + 1]) { ++i; continue; }
+            int j = i;
+            while (j < M && !cnt[j + 1]) ++j;
+            if (j - i > best_hi - best_lo) { best_lo = i; best_hi = j; }
+            i = j;
+        }
+        op.int_lo = (best_lo + 31) / 32 * 32;
+        op.int_hi = best_hi == M ? M : best_hi / 32 * 32;
+        if (op.int_hi < op.int_lo) op.int_hi = op.int_lo;
         std::vector<int> brow, brow_ptr(1, 0);
         std::vector<int> pos(M, -1);
         for (int i = 0; i < M; ++i)
-            if (cnt[i + 1]) {
+            if (i < op.int_lo || i >= op.int_hi) {   // may hold rows without remote entries: fine
                 pos[i] = (int)brow.size();
                 brow.push_back(i);
                 brow_ptr.push_back(brow_ptr.back() + cnt[i + 1]);
@@ -131,7 +205,7 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
             bval[fill[b]] = d->val_remote[k];
             ++fill[b];
         }
-        std::vector<uint32_t> mask((size_t)(M + 31) / 32, 0u);
+        std::vector<uint32_t> mask((size_t)(M + 31) / 32, 0u);   // used by the streaming kernel only
         for (int r : brow) mask[r >> 5] |= 1u << (r & 31);
         op.n_brows = (int)brow.size();
         SB_TRY(dev_upload(ctx, &op.brow, brow.data(), brow.size()));
@@ -150,7 +224,8 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
     }
     const size_t esz = op.use_double ? sizeof(double) : sizeof(float);
     if (op.vIndexSize) SB_CUDA(cudaMalloc(&op.send_buf, (size_t)op.vIndexSize * esz));
-    if (op.recvSize) SB_CUDA(cudaMalloc(&op.ghost_buf, (size_t)op.recvSize * esz));
+    if (op.recvSize && !(op.merged && op.use_double)) SB_CUDA(cudaMalloc(&op.ghost_buf, (size_t)op.recvSize * esz));
+    if (op.merged && op.use_double) op.ghost_buf = op.x_ext + d->n_local_cols;  // received in place
     for (int i = 0; i < d->numSendProc; ++i) {
         const int p = d->sendProcRank[i];
         if (p < 0 || p >= ctx->nranks) SB_FAIL("upload_operator: sendProcRank out of range");
@@ -327,11 +402,14 @@ template <int EPI, typename OffT>
 static void launch_local(saena_b200_ctx *ctx, DevOperator &op, const double *x, const EpiArgs &e) {
     const OffT *rp = (const OffT *)op.rowptr;
     cudaStream_t s = ctx->stream;
-    if (op.M == 0) return;
+    // rows [lo, hi): everything when there is no halo, else the interior range
+    const int lo = op.use_stream ? 0 : op.int_lo, hi = op.use_stream ? op.M : op.int_hi;
+    const int nrows = hi - lo;
+    if (nrows <= 0) return;
     ++ctx->launches;
     if (op.use_sell) {
-        const int blocks = (op.M + 255) / 256;
-        spmv_sell_kernel<EPI><<<blocks, 256, 0, s>>>(op.M, op.sell_ptr, op.sell_col, op.sell_val, x, e, op.brow_mask);
+        const int blocks = (nrows + 255) / 256;
+        spmv_sell_kernel<EPI><<<blocks, 256, 0, s>>>(lo, hi, op.sell_ptr, op.sell_col, op.sell_val, x, e, nullptr);
     } else if (op.use_stream) {
         switch (op.lanes) {
 #define SB_STREAM_CASE(L)                                                                          \
@@ -347,19 +425,19 @@ static void launch_local(saena_b200_ctx *ctx, DevOperator &op, const double *x, 
         switch (op.lanes) {
 #define SB_RG_CASE(T)                                                                              \
     case T:                                                                                        \
-        spmv_rowgroup_kernel<T, EPI, OffT><<<(op.M + 256 / T - 1) / (256 / T), 256, 0, s>>>(       \
-            op.M, rp, op.col, op.val, x, e, op.brow_mask);                                         \
+        spmv_rowgroup_kernel<T, EPI, OffT><<<(nrows + 256 / T - 1) / (256 / T), 256, 0, s>>>(      \
+            lo, hi, rp, op.col, op.val, x, e, nullptr);                                            \
         break;
             SB_RG_CASE(32) SB_RG_CASE(64) SB_RG_CASE(128) SB_RG_CASE(256)
 #undef SB_RG_CASE
         }
     } else {
-        const int blocks = (op.M + 255) / 256;  // 8 warps x 32 rows
+        const int blocks = (nrows + 255) / 256;  // 8 warps x 32 rows
         switch (op.lanes) {
 #define SB_VEC_CASE(L)                                                                             \
     case L:                                                                                        \
-        spmv_vec_kernel<L, EPI, OffT><<<blocks, 256, 0, s>>>(op.M, rp, op.col, op.val, x, e,       \
-                                                             op.brow_mask);                        \
+        spmv_vec_kernel<L, EPI, OffT><<<blocks, 256, 0, s>>>(lo, hi, rp, op.col, op.val, x, e,     \
+                                                             nullptr);                             \
         break;
             SB_VEC_CASE(1) SB_VEC_CASE(2) SB_VEC_CASE(4) SB_VEC_CASE(8) SB_VEC_CASE(16)
 #undef SB_VEC_CASE
@@ -371,17 +449,18 @@ template <int EPI, typename OffT>
 static void launch_boundary(saena_b200_ctx *ctx, DevOperator &op, const double *x, const EpiArgs &e) {
     if (op.n_brows == 0) return;
     ++ctx->launches;
-    const int threads = 256, rows_per_block = threads / 8;
-    const int blocks = (op.n_brows + rows_per_block - 1) / rows_per_block;
     const OffT *rp = (const OffT *)op.rowptr;
-    if (op.use_double)
-        spmv_boundary_kernel<EPI, OffT, double><<<blocks, threads, 0, ctx->stream>>>(
-            op.n_brows, op.brow, rp, op.col, op.val, op.brow_ptr, op.bcol, op.bval, x,
-            (const double *)op.ghost_buf, e);
-    else
-        spmv_boundary_kernel<EPI, OffT, float><<<blocks, threads, 0, ctx->stream>>>(
-            op.n_brows, op.brow, rp, op.col, op.val, op.brow_ptr, op.bcol, op.bval, x,
-            (const float *)op.ghost_buf, e);
+    // a warp per boundary row once rows are long (coarse levels, R), 8 lanes for stencil rows
+    const bool wide = op.avg_nnz_row() >= 48.0;
+    const int threads = 256, rows_per_block = threads / (wide ? 32 : 8);
+    const int blocks = (op.n_brows + rows_per_block - 1) / rows_per_block;
+#define SB_BND(L, G)                                                                               \
+    spmv_boundary_kernel<L, EPI, OffT, G><<<blocks, threads, 0, ctx->stream>>>(                    \
+        op.n_brows, op.brow, rp, op.col, op.val, op.brow_ptr, op.bcol, op.bval, x,                 \
+        (const G *)op.ghost_buf, e)
+    if (op.use_double) { if (wide) SB_BND(32, double); else SB_BND(8, double); }
+    else { if (wide) SB_BND(32, float); else SB_BND(8, float); }
+#undef SB_BND
 }
 
 template <int EPI>
@@ -390,21 +469,40 @@ static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, cons
     const bool halo = has_halo && ctx->apply_mode != 1;
     const bool compute = ctx->apply_mode != 2;
     if (halo) {
-        // pack -> exchange on the comm stream, overlapped with the interior rows
+        // pack + exchange on the comm stream, both overlapped with the interior rows: the comm
+        // stream only waits for x to be ready (ev_packed marks that point of the compute stream),
+        // the compute stream goes straight on to the interior kernel
+        SB_CUDA(cudaEventRecord(ctx->ev_packed, ctx->stream));
+        SB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
         if (op.vIndexSize) {
             ++ctx->launches;
             const int blocks = (op.vIndexSize + 255) / 256;
             if (op.use_double)
-                halo_pack_kernel<double><<<blocks, 256, 0, ctx->stream>>>(op.vIndexSize, op.vIndex, x,
-                                                                          (double *)op.send_buf);
+                halo_pack_kernel<double><<<blocks, 256, 0, ctx->comm_stream>>>(op.vIndexSize, op.vIndex, x,
+                                                                               (double *)op.send_buf);
             else
-                halo_pack_kernel<float><<<blocks, 256, 0, ctx->stream>>>(op.vIndexSize, op.vIndex, x,
-                                                                         (float *)op.send_buf);
+                halo_pack_kernel<float><<<blocks, 256, 0, ctx->comm_stream>>>(op.vIndexSize, op.vIndex, x,
+                                                                              (float *)op.send_buf);
         }
-        SB_CUDA(cudaEventRecord(ctx->ev_packed, ctx->stream));
-        SB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
         SB_TRY(sb_halo_exchange(ctx, op, ctx->comm_stream));
         SB_CUDA(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
+    }
+    if (op.merged) {
+        // x_ext = [x | ghosts], then one ordinary SpMV over the extended columns
+        if (compute && op.n_local_cols)
+            SB_CUDA(cudaMemcpyAsync(op.x_ext, x, sizeof(double) * op.n_local_cols, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (halo) SB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+        if (compute) {
+            if (!op.use_double && op.recvSize) {
+                ++ctx->launches;
+                widen_ghost_kernel<<<(op.recvSize + 255) / 256, 256, 0, ctx->stream>>>(
+                    op.recvSize, (const float *)op.ghost_buf, op.x_ext + op.n_local_cols);
+            }
+            if (op.wide_offsets) launch_local<EPI, int64_t>(ctx, op, op.x_ext, e);
+            else launch_local<EPI, int>(ctx, op, op.x_ext, e);
+        }
+        SB_CUDA(cudaGetLastError());
+        return 0;
     }
     if (compute) {
         if (op.wide_offsets) launch_local<EPI, int64_t>(ctx, op, x, e);

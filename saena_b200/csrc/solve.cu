@@ -140,3 +140,52 @@ int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const
     if (post) SB_TRY(sb_smooth(ctx, l, smoother, post, rhs, false));
     return 0;
 }
+
+void sb_invalidate_graphs(saena_b200_ctx *ctx) {
+    for (VcycleGraph &g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+}
+
+int sb_vcycle_from_zero(saena_b200_ctx *ctx, int smoother, int pre, int post, const double *rhs) {
+    // a zero iterate is overwritten, so every level may start in buffer 0: the launch sequence
+    // (pointers included) is then identical from one V-cycle to the next
+    for (DevLevel &lv : ctx->levels) lv.cur = 0;
+    const bool capturable = ctx->use_graphs && ctx->nranks == 1 && !ctx->coarsest_cg;
+    if (!capturable) return sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
+    for (VcycleGraph &g : ctx->graphs)
+        if (g.rhs == rhs && g.smoother == smoother && g.pre == pre && g.post == post) {
+            SB_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+            ctx->launches += g.launches;
+            for (size_t l = 0; l < ctx->levels.size(); ++l) ctx->levels[l].cur = g.cur_after[l];
+            return 0;
+        }
+    // first use of this configuration: capture, instantiate, launch
+    const int64_t before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    SB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ctx->use_graphs = false;  // run eagerly from now on (the capture executed nothing)
+        ctx->launches = before;
+        for (DevLevel &lv : ctx->levels) lv.cur = 0;
+        if (rc) return rc;
+        return sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
+    }
+    VcycleGraph g{rhs, smoother, pre, post, nullptr, ctx->launches - before, {}};
+    const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+        cudaGetLastError();
+        ctx->use_graphs = false;
+        ctx->launches = before;
+        for (DevLevel &lv : ctx->levels) lv.cur = 0;
+        return sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
+    }
+    for (DevLevel &lv : ctx->levels) g.cur_after.push_back(lv.cur);
+    ctx->graphs.push_back(g);
+    SB_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+    return 0;
+}

@@ -45,6 +45,9 @@ __device__ __forceinline__ void sb_epilogue(int i, double ax, const EpiArgs &e) 
     }
 }
 
+// (Fetching the epilogue's vector inputs before the row loop was tried in round 1: +3 % on the
+// 7-point level, -12 %/-20 % on the 68 and 267 nnz/row levels -- the extra live registers cost the
+// loop its load batching at 32 registers/thread.  Not adopted.)
 __device__ __forceinline__ bool sb_row_skipped(const uint32_t *__restrict__ mask, int row) {
     return mask != nullptr && ((mask[row >> 5] >> (row & 31)) & 1u);
 }
@@ -60,13 +63,13 @@ constexpr int VEC_UNROLL = 4;
 
 template <int LANES, int EPI, typename OffT>
 __global__ void __launch_bounds__(256)
-spmv_vec_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+spmv_vec_kernel(int row_begin, int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
                 const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
                 const uint32_t *__restrict__ skip_mask) {
     constexpr int G = 32 / LANES;  // rows in flight per warp per step
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int row0 = warp * 32;
+    const int row0 = row_begin + warp * 32;  // rows [row_begin, M)
     if (row0 >= M) return;
     const int my_row = row0 + lane;
     // lane j fetches the extent of row j (coalesced), shuffled to the cooperating lanes below
@@ -115,14 +118,14 @@ spmv_vec_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 template <int TPR, int EPI, typename OffT>
 __global__ void __launch_bounds__(256)
-spmv_rowgroup_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+spmv_rowgroup_kernel(int row_begin, int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
                      const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
                      const uint32_t *__restrict__ skip_mask) {
     constexpr int ROWS = 256 / TPR;
     constexpr int WPR = TPR / 32;  // warps per row
     __shared__ double s_part[8];
     const int g = threadIdx.x / TPR, sub = threadIdx.x % TPR;
-    const int row = blockIdx.x * ROWS + g;
+    const int row = row_begin + blockIdx.x * ROWS + g;  // rows [row_begin, M)
     double sum = 0.0;
     if (row < M) {
         const OffT start = rowptr[row], end = rowptr[row + 1];
@@ -254,10 +257,10 @@ spmv_stream_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict
 // ---------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(256)
-spmv_sell_kernel(int M, const long long *__restrict__ slice_ptr, const int *__restrict__ col,
+spmv_sell_kernel(int row_begin, int M, const long long *__restrict__ slice_ptr, const int *__restrict__ col,
                  const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
                  const uint32_t *__restrict__ skip_mask) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x;  // rows [row_begin, M), row_begin % 32 == 0
     const int lane = threadIdx.x & 31;
     const int slice = row >> 5;
     if ((slice << 5) >= M) return;
@@ -283,19 +286,18 @@ spmv_sell_kernel(int M, const long long *__restrict__ slice_ptr, const int *__re
 }
 
 // ---------------------------------------------------------------------------------------------
-// boundary rows: rows with entries in other ranks' columns.  8 lanes per row: local segment
+// boundary rows: rows with entries in other ranks' columns.  8 or 32 lanes per row: local segment
 // (recomputed -- these rows are a few percent of the block) + remote segment read from the ghost
 // buffer the halo exchange filled (float when the operator's use_double is false:
 // matvec_sparse_float, saena_matrix_matvec.cpp:531-538 widens on use).
 // ---------------------------------------------------------------------------------------------
-template <int EPI, typename OffT, typename GhostT>
+template <int LANES, int EPI, typename OffT, typename GhostT>
 __global__ void __launch_bounds__(256)
 spmv_boundary_kernel(int n_brows, const int *__restrict__ brow, const OffT *__restrict__ rowptr,
                      const int *__restrict__ col, const double *__restrict__ val,
                      const int *__restrict__ brow_ptr, const int *__restrict__ bcol,
                      const double *__restrict__ bval, const double *__restrict__ x,
                      const GhostT *__restrict__ ghost, EpiArgs e) {
-    constexpr int LANES = 8;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = gid / LANES, sub = gid % LANES;
     double sum = 0.0;
@@ -303,13 +305,31 @@ spmv_boundary_kernel(int n_brows, const int *__restrict__ brow, const OffT *__re
     if (b < n_brows) {
         row = brow[b];
         const OffT s = rowptr[row], t = rowptr[row + 1];
-        for (OffT k = s + sub; k < t; k += LANES) sum += val[k] * __ldg(x + col[k]);
+        for (OffT k = s + sub; k < t; k += LANES * VEC_UNROLL) {
+            int c[VEC_UNROLL];
+            double a[VEC_UNROLL];
+#pragma unroll
+            for (int q = 0; q < VEC_UNROLL; ++q) {
+                const OffT kk = k + q * LANES;
+                const bool in = kk < t;
+                c[q] = in ? col[kk] : 0;
+                a[q] = in ? val[kk] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < VEC_UNROLL; ++q) sum += a[q] * __ldg(x + c[q]);
+        }
         const int rs = brow_ptr[b], rt = brow_ptr[b + 1];
         for (int k = rs + sub; k < rt; k += LANES) sum += bval[k] * (double)ghost[bcol[k]];
     }
 #pragma unroll
     for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (sub == 0 && row >= 0) sb_epilogue<EPI>(row, sum, e);
+}
+
+// merged mode: ghost values that travelled as float are widened into the tail of x_ext
+__global__ void widen_ghost_kernel(int n, const float *__restrict__ in, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
 }
 
 // halo pack: vSend[i] = v[vIndex[i]] (saena_matrix_matvec.cpp:25-26; :463-464 casts to float)

@@ -174,6 +174,31 @@ def balanced_split(indptr: np.ndarray, nprocs: int) -> np.ndarray:
     return np.maximum.accumulate(split).astype(I32)
 
 
+def aligned_coarse_split(r_indptr: np.ndarray, r_indices: np.ndarray, r_data: np.ndarray,
+                         fine_split: Sequence[int]) -> np.ndarray:
+    """Coarse row partition that follows the fine one: coarse row c goes to the rank that owns the
+    fine column carrying its largest |R[c, :]| entry (the aggregate's own nodes), made monotone.
+    This is the reference's rule -- an aggregate lives where its root lives, splitNew in
+    aggregate_index_update, /root/reference/src/saena_object_setup1.cpp:2124-2132 -- recovered from
+    R alone; it keeps the transfer operators' remote parts thin."""
+    fine_split = np.asarray(fine_split, I64)
+    nprocs = len(fine_split) - 1
+    nc = len(r_indptr) - 1
+    if nc == 0:
+        return np.zeros(nprocs + 1, I64)
+    starts = np.asarray(r_indptr[:-1], I64)
+    if np.any(np.diff(r_indptr) == 0):
+        raise ValueError("restriction operator with an empty row")
+    a = np.abs(np.asarray(r_data, F64))
+    row_max = np.maximum.reduceat(a, starts)
+    rows = np.repeat(np.arange(nc, dtype=I64), np.diff(r_indptr))
+    cand = np.where(a == row_max[rows], np.asarray(r_indices, I64), np.iinfo(I64).max)
+    arg_col = np.minimum.reduceat(cand, starts)
+    owner = np.searchsorted(fine_split, arg_col, side="right") - 1
+    owner = np.maximum.accumulate(np.clip(owner, 0, nprocs - 1))
+    return np.searchsorted(owner, np.arange(nprocs + 1), side="left").astype(I64)
+
+
 def split_operator(kind: int, level: int, indptr: np.ndarray, indices: np.ndarray, data: np.ndarray,
                    n_cols: int, row_split: Sequence[int], col_split: Sequence[int],
                    use_double: bool = True) -> List[Operator]:
@@ -251,30 +276,48 @@ def operator_to_global_csr(op: Operator):
     return csr_from_counts(op.nnzPerRow_local), op.col_local.astype(I32), op.val_local
 
 
-def partition_hierarchy(h: Hierarchy, nprocs: int, agglomerate_below: int = 0) -> List[Hierarchy]:
+def partition_hierarchy(h: Hierarchy, nprocs: int, agglomerate_below: int = 0,
+                        align_coarse: bool = True) -> List[Hierarchy]:
     """Row-partition a one-rank hierarchy over `nprocs` ranks, keeping Saena's layout per rank.
 
-    Level 0 uses nnz-balanced contiguous row blocks; each coarse level is split the same way, so
-    a level's vectors never change partition between R's output and the coarse grid
+    Level 0 uses nnz-balanced contiguous row blocks; each coarse level follows the level above
+    (`aligned_coarse_split`: an aggregate lives where its root lives), so a level's vectors never
+    change partition between R's output and the coarse grid
     (Ac.split_old == Ac.split: Grid::repart_u is the identity) -- except below
     `agglomerate_below` global rows, where the level and everything coarser lives on rank 0 and
     the repart plan gathers/scatters the coarse vector (the reference's shrink-to-one-rank case,
     /root/reference/src/saena_matrix_shrink.cpp:67-96).  The coarsest level is always on rank 0
     (decide_shrinking_c, same file), where the direct solve runs.
+
+    `align_coarse=False` splits every coarse level by its own nnz balance instead (what the
+    reference's `repart` may do after coarsening): coarse and fine blocks then do not line up, the
+    transfer operators get fat remote parts and whole rows without a single local entry -- kept
+    as a stress case for the tests.
     """
     assert h.nprocs == 1
     L = len(h.levels)
     splits = []
     agglomerated = []
+    aligned = []   # partition R of level l-1 writes into: follows level l-1's rows
     for l, lv in enumerate(h.levels):
         indptr = csr_from_counts(lv.A.nnzPerRow_local)
         agg = l > 0 and (lv.A.Mbig < agglomerate_below or agglomerated[-1] or l == L - 1)
         agglomerated.append(bool(agg))
-        if agg:
-            sp = np.concatenate(([0], np.full(nprocs, lv.A.Mbig))).astype(I32)
-        else:
+        if l == 0:
+            aligned.append(None)
             sp = balanced_split(indptr, nprocs)
-        splits.append(sp)
+        else:
+            Rp = h.levels[l - 1].R
+            if agglomerated[l - 1]:
+                al = np.concatenate(([0], np.full(nprocs, lv.A.Mbig))).astype(I64)
+            elif not align_coarse:
+                al = np.asarray(balanced_split(indptr, nprocs), I64)
+            else:
+                al = aligned_coarse_split(csr_from_counts(Rp.nnzPerRow_local), Rp.col_local, Rp.val_local,
+                                          splits[l - 1])
+            aligned.append(al)
+            sp = np.concatenate(([0], np.full(nprocs, lv.A.Mbig))).astype(I64) if agg else al
+        splits.append(np.asarray(sp, I64))
     # the partition R writes into (split_old of level l+1): balanced unless level l itself is agglomerated
     out = [Hierarchy(levels=[], coarse_n=h.coarse_n, coarse_row=h.coarse_row, coarse_col=h.coarse_col,
                      coarse_val=h.coarse_val, nprocs=nprocs, rank=r, scale=h.scale) for r in range(nprocs)]
@@ -284,12 +327,9 @@ def partition_hierarchy(h: Hierarchy, nprocs: int, agglomerate_below: int = 0) -
         P_parts = R_parts = None
         split_old_next = None
         if lv.P is not None:
-            nxt = h.levels[l + 1]
-            if agglomerated[l + 1] and not agglomerated[l]:
-                # R still produces a distributed coarse vector; balance it by rows of Ac
-                split_old_next = balanced_split(csr_from_counts(nxt.A.nnzPerRow_local), nprocs)
-            else:
-                split_old_next = splits[l + 1]
+            # R produces the coarse vector in the aligned partition; it differs from the coarse
+            # grid's own partition only where that grid is agglomerated onto rank 0
+            split_old_next = aligned[l + 1]
             ip, ix, dv = operator_to_global_csr(lv.P)
             P_parts = split_operator(KIND_P, l, ip, ix, dv, lv.P.Nbig, splits[l], split_old_next, lv.P.use_double)
             ip, ix, dv = operator_to_global_csr(lv.R)

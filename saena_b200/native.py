@@ -64,6 +64,7 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_upload_level_scale.argtypes = [vp, i, dp]
     L.saena_b200_upload_coarsest.argtypes = [vp, i, ctypes.c_int64, c_i32_p, c_i32_p, dp]
     L.saena_b200_set_coarsest_solver.argtypes = [vp, i]
+    L.saena_b200_set_graphs.argtypes = [vp, i]
     L.saena_b200_finalize.argtypes = [vp]
     solve_args = [vp, vp, vp, i, d, i, i, i, ip, dp, i, ip]
     L.saena_b200_solve_pcg.argtypes = solve_args
@@ -95,7 +96,7 @@ EXPORTED_SYMBOLS = [
     "saena_b200_nccl_unique_id", "saena_b200_init", "saena_b200_destroy", "saena_b200_last_error",
     "saena_b200_upload_operator", "saena_b200_upload_level_aux", "saena_b200_upload_level_scale",
     "saena_b200_upload_coarsest",
-    "saena_b200_set_coarsest_solver", "saena_b200_finalize", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
+    "saena_b200_set_coarsest_solver", "saena_b200_set_graphs", "saena_b200_finalize", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
     "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_set_mapping", "saena_b200_get_mapping",
@@ -217,6 +218,9 @@ class Context:
         if name not in ("SuperLU", "CG"):
             raise ValueError("Error: Unknown direct solver!")   # saena_object_solve.cpp:1011-1013
         self._ck(self._L.saena_b200_set_coarsest_solver(self._h, int(name == "CG")))
+
+    def set_graphs(self, on: bool):
+        self._ck(self._L.saena_b200_set_graphs(self._h, int(on)))
 
     # ---- solvers ----
     def _solve(self, fn, rhs, u, max_iter, tol, smoother, pre, post):

@@ -342,17 +342,40 @@ class DeviceHierarchy:
         from .hierarchy import balanced_split, csr_from_counts
         return balanced_split(csr_from_counts(M.counts().cpu().numpy()), nprocs)
 
+    @staticmethod
+    def _aligned_coarse_split(R: _Csr, fine_split: np.ndarray) -> np.ndarray:
+        """hierarchy.aligned_coarse_split on device tensors"""
+        dev = R.val.device
+        nprocs = len(fine_split) - 1
+        nc = R.n_rows
+        a = R.val.abs()
+        row_max = torch.zeros(nc, dtype=torch.float64, device=dev)
+        row_max.scatter_reduce_(0, R.row, a, reduce="amax", include_self=False)
+        cand = torch.where(a == row_max[R.row], R.col, torch.full_like(R.col, BIG))
+        arg_col = torch.full((nc,), BIG, dtype=torch.int64, device=dev)
+        arg_col.scatter_reduce_(0, R.row, cand, reduce="amin")
+        fs = torch.as_tensor(np.asarray(fine_split, np.int64), device=dev)
+        owner = torch.clamp(torch.searchsorted(fs, arg_col, right=True) - 1, 0, nprocs - 1)
+        owner = torch.cummax(owner, 0).values
+        return torch.searchsorted(owner, torch.arange(nprocs + 1, device=dev), right=False).cpu().numpy().astype(np.int64)
+
     def splits(self, nprocs: int, agglomerate_below: int):
+        """(row partition of every level, partition R of the level above writes into, agglomerated?)
+        -- hierarchy.partition_hierarchy's rules"""
         L = len(self.levels)
-        splits, agglomerated = [], []
+        splits, aligned, agglomerated = [], [], []
         for l, lv in enumerate(self.levels):
             agg = l > 0 and (lv.A.n_rows < agglomerate_below or agglomerated[-1] or l == L - 1) and nprocs > 1
             agglomerated.append(bool(agg))
-            if agg:
-                splits.append(np.concatenate(([0], np.full(nprocs, lv.A.n_rows))).astype(np.int64))
-            else:
+            all_on_0 = np.concatenate(([0], np.full(nprocs, lv.A.n_rows))).astype(np.int64)
+            if l == 0:
+                aligned.append(None)
                 splits.append(self._balanced_split(lv.A, nprocs).astype(np.int64))
-        return splits, agglomerated
+                continue
+            al = all_on_0 if agglomerated[l - 1] else self._aligned_coarse_split(self.levels[l - 1].R, splits[l - 1])
+            aligned.append(al)
+            splits.append(all_on_0 if agg else al)
+        return splits, aligned, agglomerated
 
     @staticmethod
     def _rank_operator(kind, level, M: _Csr, row_split, col_split, rank, use_double) -> Operator:
@@ -405,7 +428,7 @@ class DeviceHierarchy:
     def to_rank(self, rank: int = 0, nprocs: int = 1, agglomerate_below: int = 0) -> Hierarchy:
         """This rank's share (hierarchy.partition_hierarchy semantics: nnz-balanced row blocks per
         level, levels below `agglomerate_below` global rows -- and always the coarsest -- on rank 0)."""
-        splits, agglomerated = self.splits(nprocs, agglomerate_below)
+        splits, aligned, agglomerated = self.splits(nprocs, agglomerate_below)
         levels = []
         for l, lv in enumerate(self.levels):
             sp = splits[l]
@@ -413,12 +436,7 @@ class DeviceHierarchy:
             A = self._rank_operator(KIND_A, l, lv.A, sp, sp, rank, lv.a_use_double)
             out = Level(level=l, A=A, inv_diag=lv.inv_diag[r0:r1].cpu().numpy(), eig_max=lv.eig_max, active=r1 > r0)
             if lv.P is not None:
-                nxt = self.levels[l + 1]
-                if agglomerated[l + 1] and not agglomerated[l]:
-                    so = self._balanced_split(nxt.A, nprocs).astype(np.int64)
-                else:
-                    so = splits[l + 1]
-                sn = splits[l + 1]
+                so, sn = aligned[l + 1], splits[l + 1]
                 out.P = self._rank_operator(KIND_P, l, lv.P, sp, so, rank, lv.pr_use_double)
                 out.R = self._rank_operator(KIND_R, l, lv.R, so, sp, rank, lv.pr_use_double)
                 out.M_coarse_old = int(so[rank + 1] - so[rank])

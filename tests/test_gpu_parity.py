@@ -164,6 +164,20 @@ def test_edge_case_row_shapes(case):
         ctx.close()
 
 
+def test_cuda_graph_replay_is_bitwise_the_eager_solve(golden_ctx):
+    g, ctx = golden_ctx
+    ctx.set_graphs(False)
+    u0, it0, h0 = ctx.solve_pcg(g.rhs, g.max_iter, g.tol)
+    ctx.set_graphs(True)
+    n0 = ctx.launch_count()
+    u1, it1, h1 = ctx.solve_pcg(g.rhs, g.max_iter, g.tol)   # captures on the first V-cycle, replays after
+    u2, it2, h2 = ctx.solve_pcg(g.rhs, g.max_iter, g.tol)   # replays only
+    assert it0 == it1 == it2
+    assert np.array_equal(h0, h1) and np.array_equal(h0, h2)
+    assert np.array_equal(u0, u1) and np.array_equal(u0, u2)
+    assert ctx.launch_count() > n0
+
+
 def test_coarsest_cg_option(golden_ctx):
     """direct_solver == "CG": solve_coarsest_CG (saena_object_solve.cpp:14-114) instead of the direct solve"""
     g, ctx = golden_ctx

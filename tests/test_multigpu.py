@@ -23,5 +23,6 @@ def test_distributed_path_matches_multirank_oracle(world):
                           "--master-addr", "127.0.0.1", "--master-port", str(29540 + world),
                           os.path.join(ROOT, "tests", "multigpu_check.py")],
                          capture_output=True, text=True, timeout=900, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    fails = [l for l in out.stdout.splitlines() if "FAILED" in l or "Error" in l or "assert" in l.lower()]
+    assert out.returncode == 0, "\n".join(fails[:40]) + "\n" + out.stdout[-6000:]
     assert "MULTIGPU_OK" in out.stdout
