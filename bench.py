@@ -177,7 +177,7 @@ def main():
     import torch
     import torch.distributed as dist
     from saena_b200 import native
-    from saena_b200.distributed import exchange_nccl_id
+    from saena_b200.distributed import exchange_nccl_id, setup_p2p_halo
     from saena_b200.hierarchy import KIND_A, KIND_P, KIND_R
     from saena_b200.sa_setup import build_device_hierarchy, poisson3d_coo, poisson3d_rhs
 
@@ -202,6 +202,14 @@ def main():
     torch.cuda.empty_cache()
     ctx = native.Context(device=local, rank=rank, nranks=world, nccl_id=nccl_id)
     ctx.upload_hierarchy(hier)
+    halo_transport = "none"
+    if world > 1:
+        halo_transport = "nccl"
+        if os.environ.get("SAENA_B200_HALO", "p2p") == "p2p" and setup_p2p_halo(ctx):
+            halo_transport = "nvlink peer memory (pack kernel stores into the neighbour's ghost buffer)"
+    for spec in filter(None, os.environ.get("SAENA_BENCH_MAP", "").split(",")):   # tuning: "level:kind:mapping"
+        lvl, kind, mp = (int(x) for x in spec.split(":"))
+        ctx.set_mapping(lvl, kind, mp)
     if rank == 0:
         log(f"[setup] uploaded in {time.perf_counter() - t0:.1f}s total")
     l0 = hier.levels[0].A
@@ -225,14 +233,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler starts here: nvidia-smi needs ~0.2 s before its first sample,
+    #      longer than a multi-GPU timed region; every sample is taken under the same solve load)
     iters = hist = None
-    for _ in range(args.warmup):
-        iters, hist = ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
-    # ---- timed: K solves, inputs resident in HBM, CUDA events on the library's compute stream
-    launches0 = ctx.launch_count()
-    barrier()
     with ClockSampler(local) as clocks:
+        for _ in range(args.warmup):
+            iters, hist = ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+        # ---- timed: K solves, inputs resident in HBM, CUDA events on the library's compute stream
+        launches0 = ctx.launch_count()
+        barrier()
         ctx.timer_start()
         for _ in range(args.steps):
             iters, hist = ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
@@ -311,6 +320,7 @@ def main():
         full_ms, local_ms, halo_ms = max_over_ranks(full_ms), max_over_ranks(local_ms), max_over_ranks(halo_ms)
         halo = {"level": 0, "spmv_full_ms": full_ms, "spmv_local_only_ms": local_ms, "pack_exchange_only_ms": halo_ms,
                 "hidden_frac": max(0.0, min(1.0, 1.0 - (full_ms - local_ms) / halo_ms)) if halo_ms > 0 else None,
+                "transport": halo_transport,
                 "ghost_values_per_rank": int(hier.levels[0].A.col_remote_size),
                 "ghost_dtype": "f64" if hier.levels[0].A.use_double else "f32 (float_level 0)"}
 
@@ -339,6 +349,8 @@ def main():
             line["cpu_baseline"]["iterations"] = cpu_iters
         except Exception as e:  # the bench line must still come out
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(e)}
+    if world > 1:
+        dist.barrier()   # nobody unmaps a peer's arena while that peer may still write into it
     ctx.close()
     if rank == 0:
         print(json.dumps(line), flush=True)

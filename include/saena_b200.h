@@ -122,6 +122,18 @@ int saena_b200_set_graphs(saena_b200_ctx *ctx, int on);
  * and picks each operator's kernel mapping from its nnz/row. */
 int saena_b200_finalize(saena_b200_ctx *ctx);
 
+/* ---- peer-memory halo (nranks > 1, all ranks on one NVLink/NVSwitch node) ----------------------
+ * After finalize every rank exports a small blob (IPC handle of its halo arena + where each
+ * sender's values land), the host all-gathers the blobs over whatever channel it has
+ * (MPI_Allgather in the adaptor, torch.distributed in bench.py) and every rank imports the
+ * concatenation (rank order, `blob_bytes` each).  From then on the ghost values of the distributed
+ * SpMV are stored by the sender's pack kernel straight into the receiver's memory over NVLink;
+ * without the import (or after saena_b200_p2p_enable(ctx, 0)) the exchange uses ncclSend/ncclRecv.
+ * p2p_export with buf == NULL only reports the size. */
+int saena_b200_p2p_export(saena_b200_ctx *ctx, void *buf, int64_t cap, int64_t *size_out);
+int saena_b200_p2p_import(saena_b200_ctx *ctx, const void *blobs, int64_t blob_bytes);
+int saena_b200_p2p_enable(saena_b200_ctx *ctx, int on);
+
 /* ---- solvers -----------------------------------------------------------------------------
  * rhs / u are this rank's block (grids[0].A->M entries).  u is overwritten (zero initial
  * guess, as the reference does: saena_object_solve.cpp:2482).  `iters` receives the count
@@ -151,7 +163,8 @@ int saena_b200_dot(saena_b200_ctx *ctx, const double *a, const double *b, int n,
 
 /* ---- measurement ---------------------------------------------------------------------------
  * Device-resident timing loops for bench.py: `reps` applications of one operator / smoother
- * sweep with CUDA events on the launching stream; returns average milliseconds per launch. */
+ * sweep, each launch bracketed by CUDA events on the launching stream; returns the median
+ * milliseconds per launch. */
 int saena_b200_time_matvec(saena_b200_ctx *ctx, int level, int kind, int reps, int flush_l2, float *ms_out);
 int saena_b200_time_smooth_sweep(saena_b200_ctx *ctx, int level, int smoother, int reps, int flush_l2,
                                  float *ms_out);

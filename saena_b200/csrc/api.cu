@@ -73,6 +73,7 @@ int saena_b200_destroy(saena_b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
     sb_invalidate_graphs(ctx);
+    sb_arena_free(ctx);
     for (size_t l = 0; l < ctx->levels.size(); ++l) {
         DevLevel &lv = ctx->levels[l];
         sb_free_operator(lv.A); sb_free_operator(lv.P); sb_free_operator(lv.R);
@@ -219,6 +220,7 @@ int saena_b200_finalize(saena_b200_ctx *ctx) {
     const int L = (int)ctx->levels.size();
     if (L == 0) SB_FAIL("finalize: no level uploaded");
     sb_invalidate_graphs(ctx);
+    SB_TRY(sb_arena_build(ctx));  // ghost buffers of every operator, one allocation (p2p_halo.cu)
     for (int l = 0; l < L; ++l) {
         DevLevel &lv = ctx->levels[l];
         if (!lv.A.present) SB_FAIL("finalize: a level has no A");
@@ -543,6 +545,14 @@ int saena_b200_dot(saena_b200_ctx *ctx, const double *a, const double *b, int n,
 // ---------------------------------------------------------------------------------------------
 // measurement
 // ---------------------------------------------------------------------------------------------
+// median over the launches of a timing loop: robust against the odd launch that waits for a peer
+static float median_of(std::vector<float> &t) {
+    if (t.empty()) return 0.f;
+    std::sort(t.begin(), t.end());
+    const size_t n = t.size();
+    return n % 2 ? t[n / 2] : 0.5f * (t[n / 2 - 1] + t[n / 2]);
+}
+
 static int flush_l2(saena_b200_ctx *ctx) {
     const size_t bytes = (size_t)256 << 20;  // > 126 MB L2
     if (!ctx->flush_buf) {
@@ -562,7 +572,7 @@ int saena_b200_time_matvec(saena_b200_ctx *ctx, int level, int kind, int reps, i
     SB_CUDA(cudaMemsetAsync(ctx->stage[0], 0, sizeof(double) * op->n_local_cols, ctx->stream));
     EpiArgs e{};
     e.out = ctx->stage[1];
-    float total = 0.f;
+    std::vector<float> t;
     for (int it = 0; it < reps; ++it) {
         if (do_flush) SB_TRY(flush_l2(ctx));
         SB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
@@ -571,9 +581,9 @@ int saena_b200_time_matvec(saena_b200_ctx *ctx, int level, int kind, int reps, i
         SB_CUDA(cudaEventSynchronize(ctx->ev_t1));
         float ms = 0.f;
         SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
-        total += ms;
+        t.push_back(ms);
     }
-    *ms_out = reps ? total / reps : 0.f;
+    *ms_out = median_of(t);
     return 0;
 }
 
@@ -599,7 +609,7 @@ int saena_b200_time_smooth_sweep(saena_b200_ctx *ctx, int level, int smoother, i
     DevLevel &lv = ctx->levels[level];
     SB_TRY(stage_buf(ctx, 1, lv.M));
     SB_CUDA(cudaMemsetAsync(ctx->stage[1], 0, sizeof(double) * lv.M, ctx->stream));
-    float total = 0.f;
+    std::vector<float> t;
     for (int it = 0; it < reps; ++it) {
         if (do_flush) SB_TRY(flush_l2(ctx));
         SB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
@@ -608,9 +618,9 @@ int saena_b200_time_smooth_sweep(saena_b200_ctx *ctx, int level, int smoother, i
         SB_CUDA(cudaEventSynchronize(ctx->ev_t1));
         float ms = 0.f;
         SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
-        total += ms;
+        t.push_back(ms);
     }
-    *ms_out = reps ? total / reps : 0.f;
+    *ms_out = median_of(t);
     return 0;
 }
 

@@ -13,9 +13,6 @@
 // ---------------------------------------------------------------------------------------------
 // error plumbing: every ABI entry point returns int and records a message in the context
 // ---------------------------------------------------------------------------------------------
-struct SbError {
-    std::string msg;
-};
 extern thread_local std::string g_sb_init_error;
 
 #define SB_CUDA(call)                                                                              \
@@ -73,6 +70,15 @@ struct HaloPeer {
     int count;
 };
 
+// Peer-memory halo (csrc/p2p_halo.cu): one segment of the packed send order and where it lands
+// in the receiving rank's ghost buffer (IPC-mapped), plus the flag the sender raises there.
+struct P2PSegment {
+    long long start;              // first packed element of this receiver's slice
+    long long count;
+    void *dst;                    // peer ghost slice (double* or float*)
+    unsigned long long *arrived;  // flag in the PEER's arena: "epoch e of this operator has landed"
+};
+
 struct DevOperator {
     bool present = false;
     int kind = 0, level = 0;
@@ -123,6 +129,16 @@ struct DevOperator {
     void *send_buf = nullptr;  // double[vIndexSize] or float[vIndexSize]
     void *ghost_buf = nullptr; // double[recvSize] or float[recvSize]
     std::vector<HaloPeer> sends, recvs;
+
+    // peer-memory path (set by saena_b200_p2p_import; the NCCL path stays as the fallback)
+    bool p2p = false;
+    unsigned long long epoch = 0;                 // applications so far
+    P2PSegment *p2p_segs = nullptr;               // device copy, [sends.size()]
+    unsigned int *p2p_ticket = nullptr;           // last-block detection of the pack kernel
+    std::vector<unsigned long long *> p2p_wait_arrived;    // my arena: one flag per sender
+    std::vector<unsigned long long *> p2p_wait_consumed;   // my arena: one flag per receiver of mine
+    unsigned long long **p2p_signal_consumed = nullptr;    // device array of peers' flags, [recvs.size()]
+    size_t ghost_arena_off = 0;                   // where this operator's ghost area starts in the arena
 
     // kernel mapping
     int lanes = 0;            // lanes per row (vec) / lanes per row in the reduce phase (stream)
@@ -208,6 +224,13 @@ struct saena_b200_ctx {
     double *stage[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t stage_cap[4] = {0, 0, 0, 0};
 
+    // halo arena (nranks > 1): flags + every operator's ghost area in ONE allocation, so that one
+    // IPC handle per rank maps everything a neighbour needs to write into
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<void *> peer_arena;  // [nranks] IPC mappings of the peers' arenas (nullptr: not opened)
+    bool p2p_ready = false;
+
     // L2 flush buffer for the timing loops
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
@@ -241,6 +264,13 @@ int sb_allreduce_sum(saena_b200_ctx *ctx, double *dev_vals, int count, cudaStrea
 // moves blocks of `src` to the peers' `dst`; forward: send plan -> recv plan, backward: reversed
 int sb_repart(saena_b200_ctx *ctx, const RepartPlan &plan, bool backward, const double *src, double *dst,
               cudaStream_t s);
+
+// ---- p2p_halo.cu
+int sb_arena_build(saena_b200_ctx *ctx);     // at finalize: allocate the arena, point ghost buffers into it
+void sb_arena_free(saena_b200_ctx *ctx);
+int sb_p2p_pack_and_signal(saena_b200_ctx *ctx, DevOperator &op, const double *x, cudaStream_t s);
+int sb_p2p_wait_arrived(saena_b200_ctx *ctx, DevOperator &op, cudaStream_t s);
+int sb_p2p_signal_consumed(saena_b200_ctx *ctx, DevOperator &op, cudaStream_t s);
 
 // ---- vector_ops.cu
 int sb_dot(saena_b200_ctx *ctx, const double *a, const double *b, int n, int slot);           // scalars[slot] = <a,b> (global)

@@ -34,8 +34,8 @@ void sb_free_operator(DevOperator &op) {
     cudaFree(op.rowptr); cudaFree(op.col); cudaFree(op.val); cudaFree(op.blk_row);
     cudaFree(op.brow); cudaFree(op.brow_ptr); cudaFree(op.bcol); cudaFree(op.bval); cudaFree(op.brow_mask);
     cudaFree(op.vIndex); cudaFree(op.send_buf);
-    if (!(op.merged && op.use_double)) cudaFree(op.ghost_buf);
-    cudaFree(op.x_ext);
+    cudaFree(op.p2p_segs); cudaFree(op.p2p_ticket); cudaFree(op.p2p_signal_consumed);
+    // ghost_buf / x_ext belong to the context's halo arena
     cudaFree(op.sell_ptr); cudaFree(op.sell_col); cudaFree(op.sell_val);
     op = DevOperator();
 }
@@ -47,6 +47,7 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
     if ((int)ctx->levels.size() <= d->level) ctx->levels.resize(d->level + 1);
     DevLevel &lv = ctx->levels[d->level];
     DevOperator &op = d->kind == SAENA_B200_KIND_A ? lv.A : (d->kind == SAENA_B200_KIND_P ? lv.P : lv.R);
+    if (ctx->arena) sb_arena_free(ctx);  // ghost areas are re-carved at the next finalize
     if (op.present) sb_free_operator(op);
     op.present = true;
     op.kind = d->kind;
@@ -118,7 +119,7 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
         }
         SB_TRY(dev_upload(ctx, &op.col, mc.data(), mc.size()));
         SB_TRY(dev_upload(ctx, &op.val, mv.data(), mv.size()));
-        SB_CUDA(cudaMalloc((void **)&op.x_ext, sizeof(double) * std::max<size_t>((size_t)d->n_local_cols + d->col_remote_size, 1)));
+        // x_ext itself lives in the halo arena (allocated at finalize)
     }
 
     // ---- local block -> CSR with local column ids
@@ -224,8 +225,7 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
     }
     const size_t esz = op.use_double ? sizeof(double) : sizeof(float);
     if (op.vIndexSize) SB_CUDA(cudaMalloc(&op.send_buf, (size_t)op.vIndexSize * esz));
-    if (op.recvSize && !(op.merged && op.use_double)) SB_CUDA(cudaMalloc(&op.ghost_buf, (size_t)op.recvSize * esz));
-    if (op.merged && op.use_double) op.ghost_buf = op.x_ext + d->n_local_cols;  // received in place
+    // ghost_buf / x_ext are carved out of the halo arena at finalize (sb_arena_build)
     for (int i = 0; i < d->numSendProc; ++i) {
         const int p = d->sendProcRank[i];
         if (p < 0 || p >= ctx->nranks) SB_FAIL("upload_operator: sendProcRank out of range");
@@ -463,6 +463,13 @@ static void launch_boundary(saena_b200_ctx *ctx, DevOperator &op, const double *
 #undef SB_BND
 }
 
+// the compute stream may not touch the ghost values before they have landed
+static int wait_halo(saena_b200_ctx *ctx, DevOperator &op) {
+    if (op.p2p) return sb_p2p_wait_arrived(ctx, op, ctx->stream);
+    SB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+    return 0;
+}
+
 template <int EPI>
 static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, const EpiArgs &e) {
     const bool has_halo = !op.sends.empty() || !op.recvs.empty();
@@ -474,24 +481,30 @@ static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, cons
         // the compute stream goes straight on to the interior kernel
         SB_CUDA(cudaEventRecord(ctx->ev_packed, ctx->stream));
         SB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
-        if (op.vIndexSize) {
-            ++ctx->launches;
-            const int blocks = (op.vIndexSize + 255) / 256;
-            if (op.use_double)
-                halo_pack_kernel<double><<<blocks, 256, 0, ctx->comm_stream>>>(op.vIndexSize, op.vIndex, x,
-                                                                               (double *)op.send_buf);
-            else
-                halo_pack_kernel<float><<<blocks, 256, 0, ctx->comm_stream>>>(op.vIndexSize, op.vIndex, x,
-                                                                              (float *)op.send_buf);
+        if (op.p2p) {
+            // peer-memory path: the pack kernel stores straight into the neighbours' ghost buffers
+            // over NVLink and raises their "arrived" flags; no send buffer, no NCCL rendezvous
+            SB_TRY(sb_p2p_pack_and_signal(ctx, op, x, ctx->comm_stream));
+        } else {
+            if (op.vIndexSize) {
+                ++ctx->launches;
+                const int blocks = (op.vIndexSize + 255) / 256;
+                if (op.use_double)
+                    halo_pack_kernel<double><<<blocks, 256, 0, ctx->comm_stream>>>(op.vIndexSize, op.vIndex, x,
+                                                                                   (double *)op.send_buf);
+                else
+                    halo_pack_kernel<float><<<blocks, 256, 0, ctx->comm_stream>>>(op.vIndexSize, op.vIndex, x,
+                                                                                  (float *)op.send_buf);
+            }
+            SB_TRY(sb_halo_exchange(ctx, op, ctx->comm_stream));
+            SB_CUDA(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
         }
-        SB_TRY(sb_halo_exchange(ctx, op, ctx->comm_stream));
-        SB_CUDA(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
     }
     if (op.merged) {
         // x_ext = [x | ghosts], then one ordinary SpMV over the extended columns
         if (compute && op.n_local_cols)
             SB_CUDA(cudaMemcpyAsync(op.x_ext, x, sizeof(double) * op.n_local_cols, cudaMemcpyDeviceToDevice, ctx->stream));
-        if (halo) SB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+        if (halo) SB_TRY(wait_halo(ctx, op));
         if (compute) {
             if (!op.use_double && op.recvSize) {
                 ++ctx->launches;
@@ -501,6 +514,7 @@ static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, cons
             if (op.wide_offsets) launch_local<EPI, int64_t>(ctx, op, op.x_ext, e);
             else launch_local<EPI, int>(ctx, op, op.x_ext, e);
         }
+        if (halo && op.p2p) SB_TRY(sb_p2p_signal_consumed(ctx, op, ctx->stream));
         SB_CUDA(cudaGetLastError());
         return 0;
     }
@@ -508,11 +522,12 @@ static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, cons
         if (op.wide_offsets) launch_local<EPI, int64_t>(ctx, op, x, e);
         else launch_local<EPI, int>(ctx, op, x, e);
     }
-    if (halo) SB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+    if (halo) SB_TRY(wait_halo(ctx, op));
     if (has_halo && compute) {
         if (op.wide_offsets) launch_boundary<EPI, int64_t>(ctx, op, x, e);
         else launch_boundary<EPI, int>(ctx, op, x, e);
     }
+    if (halo && op.p2p) SB_TRY(sb_p2p_signal_consumed(ctx, op, ctx->stream));
     SB_CUDA(cudaGetLastError());
     return 0;
 }

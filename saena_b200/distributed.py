@@ -54,3 +54,18 @@ def halo_exchange_host(op: Operator, v: np.ndarray) -> np.ndarray:
         o = int(op.rdispls[p])
         ghost[o:o + t.numel()] = t.numpy()
     return ghost.astype(np.float64)
+
+
+def setup_p2p_halo(ctx) -> bool:
+    """Switch a multi-rank context's halo exchange to NVLink peer memory: all-gather every rank's
+    export blob and import them (collective).  Returns False (and leaves the NCCL path in place)
+    when the context has a single rank."""
+    import torch.distributed as dist
+
+    if ctx.nranks == 1:
+        return False
+    blobs = [None] * ctx.nranks
+    dist.all_gather_object(blobs, ctx.p2p_export())
+    ctx.p2p_import(blobs)
+    dist.barrier()
+    return True

@@ -66,6 +66,9 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_set_coarsest_solver.argtypes = [vp, i]
     L.saena_b200_set_graphs.argtypes = [vp, i]
     L.saena_b200_finalize.argtypes = [vp]
+    L.saena_b200_p2p_export.argtypes = [vp, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
+    L.saena_b200_p2p_import.argtypes = [vp, vp, ctypes.c_int64]
+    L.saena_b200_p2p_enable.argtypes = [vp, i]
     solve_args = [vp, vp, vp, i, d, i, i, i, ip, dp, i, ip]
     L.saena_b200_solve_pcg.argtypes = solve_args
     L.saena_b200_solve_pcg_dev.argtypes = solve_args
@@ -96,7 +99,8 @@ EXPORTED_SYMBOLS = [
     "saena_b200_nccl_unique_id", "saena_b200_init", "saena_b200_destroy", "saena_b200_last_error",
     "saena_b200_upload_operator", "saena_b200_upload_level_aux", "saena_b200_upload_level_scale",
     "saena_b200_upload_coarsest",
-    "saena_b200_set_coarsest_solver", "saena_b200_set_graphs", "saena_b200_finalize", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
+    "saena_b200_set_coarsest_solver", "saena_b200_set_graphs", "saena_b200_finalize",
+    "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_p2p_enable", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
     "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_set_mapping", "saena_b200_get_mapping",
@@ -218,6 +222,23 @@ class Context:
         if name not in ("SuperLU", "CG"):
             raise ValueError("Error: Unknown direct solver!")   # saena_object_solve.cpp:1011-1013
         self._ck(self._L.saena_b200_set_coarsest_solver(self._h, int(name == "CG")))
+
+    # ---- peer-memory halo ----
+    def p2p_export(self) -> bytes:
+        n = ctypes.c_int64(0)
+        self._ck(self._L.saena_b200_p2p_export(self._h, None, 0, ctypes.byref(n)))
+        buf = ctypes.create_string_buffer(n.value)
+        self._ck(self._L.saena_b200_p2p_export(self._h, buf, n.value, ctypes.byref(n)))
+        return buf.raw
+
+    def p2p_import(self, blobs):
+        """blobs: every rank's p2p_export(), in rank order"""
+        assert len(blobs) == self.nranks and len({len(b) for b in blobs}) == 1
+        joined = b"".join(blobs)
+        self._ck(self._L.saena_b200_p2p_import(self._h, ctypes.create_string_buffer(joined, len(joined)), len(blobs[0])))
+
+    def p2p_enable(self, on: bool):
+        self._ck(self._L.saena_b200_p2p_enable(self._h, int(on)))
 
     def set_graphs(self, on: bool):
         self._ck(self._L.saena_b200_set_graphs(self._h, int(on)))

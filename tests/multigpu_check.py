@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 
 from oracle.oracle import Oracle  # noqa: E402
 from saena_b200 import native  # noqa: E402
-from saena_b200.distributed import exchange_nccl_id  # noqa: E402
+from saena_b200.distributed import exchange_nccl_id, setup_p2p_halo  # noqa: E402
 from saena_b200.hierarchy import KIND_A, KIND_P, KIND_R, partition_hierarchy  # noqa: E402
 from tests.util import GOLDEN, TOL_HIST, TOL_OP, Golden, rel  # noqa: E402
 
@@ -47,6 +47,7 @@ def main():
     nccl_id = exchange_nccl_id(native.nccl_unique_id)
     ctx = native.Context(device=local, rank=rank, nranks=world, nccl_id=nccl_id)
     worst = {}
+    case_no = 0
     # float_level 0 (the Poisson options file): ghost values travel as float.  Two correct
     # implementations feed that cast with values that differ by rounding noise (1e-16..1e-13); now
     # and then one of them sits on a float rounding boundary and the cast flips, a 6e-8 relative
@@ -65,10 +66,17 @@ def main():
         tol_hist = TOL_HIST if dbl else 1e-6
         hs = partition_hierarchy(g.hier, world, agglomerate_below=agg, align_coarse=align)
         mine = hs[rank]
+        dist.barrier()   # no peer is still writing into the arena this upload is about to replace
         ctx.upload_hierarchy(mine)
+        # halo transport: NVLink peer memory on four cases (f32 and f64 halos), ncclSend/ncclRecv on two
+        use_p2p = (case_no % 3 != 2) and os.environ.get("SAENA_B200_HALO", "p2p") == "p2p"
+        case_no += 1
+        if use_p2p:
+            setup_p2p_halo(ctx)
         o = Oracle(hs)
         rng = np.random.default_rng(17)
-        tag = f"{name}/agg{agg}/{'aligned' if align else 'misaligned'}/{'f64' if dbl else 'f32'}-halo"
+        tag = (f"{name}/agg{agg}/{'aligned' if align else 'misaligned'}/{'f64' if dbl else 'f32'}-halo/"
+               f"{'p2p' if use_p2p else 'nccl'}")
         for l in range(len(mine.levels)):
             sizes = [h.levels[l].A.M for h in hs]
             off = np.concatenate(([0], np.cumsum(sizes)))
