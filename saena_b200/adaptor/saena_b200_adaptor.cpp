@@ -193,6 +193,16 @@ DeviceSide &device_side(saena_object *obj) {
         std::exit(EXIT_FAILURE);
     }
     CK(ds.ctx, saena_b200_finalize(ds.ctx), "finalize");
+    if (ds.nprocs > 1 && !std::getenv("SAENA_B200_HALO_NCCL")) {
+        // peer-memory halo: all-gather the ranks' export blobs over MPI and import them
+        int64_t n = 0;
+        CK(ds.ctx, saena_b200_p2p_export(ds.ctx, nullptr, 0, &n), "p2p export");
+        std::vector<char> mine((size_t)n), all((size_t)n * ds.nprocs);
+        CK(ds.ctx, saena_b200_p2p_export(ds.ctx, mine.data(), n, &n), "p2p export");
+        MPI_Allgather(mine.data(), (int)n, MPI_BYTE, all.data(), (int)n, MPI_BYTE, A0->comm);
+        CK(ds.ctx, saena_b200_p2p_import(ds.ctx, all.data(), n), "p2p import");
+        MPI_Barrier(A0->comm);
+    }
     if (g_verbose && ds.rank == 0) std::printf("saena_b200: hierarchy of %d levels uploaded\n", L + 1);
     return g_solvers[obj] = ds;
 }
