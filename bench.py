@@ -163,6 +163,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--agglomerate-below", type=int, default=10_000,
                     help="N>1: levels with fewer global rows live on rank 0 (the reference's shrink-to-one-rank)")
+    ap.add_argument("--rebalance-above", type=float, default=float(os.environ.get("SAENA_BENCH_REBALANCE", 1.10)),
+                    help="N>1: a coarse level whose aligned row blocks leave one rank above this multiple of the mean "
+                         "nnz is split by its own nnz balance (0: never)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -197,8 +200,11 @@ def main():
     del row, col, val
     if rank == 0:
         log(f"[setup] hierarchy built in {time.perf_counter() - t0:.1f}s\n{dh.summary()}")
-    hier = dh.to_rank(rank, world, agglomerate_below=args.agglomerate_below if world > 1 else 0)
-    del dh
+    hier = dh.to_rank(rank, world, agglomerate_below=args.agglomerate_below if world > 1 else 0,
+                      rebalance_above=args.rebalance_above if world > 1 else 0.0)
+    agg_sweep = [int(x) for x in filter(None, os.environ.get("SAENA_BENCH_AGG_SWEEP", "").split(","))] if world > 1 else []
+    if not agg_sweep:
+        del dh
     torch.cuda.empty_cache()
     ctx = native.Context(device=local, rank=rank, nranks=world, nccl_id=nccl_id)
     ctx.upload_hierarchy(hier)
@@ -206,7 +212,11 @@ def main():
     if world > 1:
         halo_transport = "nccl"
         if os.environ.get("SAENA_B200_HALO", "p2p") == "p2p" and setup_p2p_halo(ctx):
-            halo_transport = "nvlink peer memory (pack kernel stores into the neighbour's ghost buffer)"
+            if os.environ.get("SAENA_B200_HALO_FUSED", "1") != "0":
+                halo_transport = ("nvlink peer memory, fused: pack + peer stores + interior rows + ghost rows "
+                                  "in one kernel per operator application")
+            else:
+                halo_transport = "nvlink peer memory (pack kernel stores into the neighbour's ghost buffer)"
     for spec in filter(None, os.environ.get("SAENA_BENCH_MAP", "").split(",")):   # tuning: "level:kind:mapping"
         lvl, kind, mp = (int(x) for x in spec.split(":"))
         ctx.set_mapping(lvl, kind, mp)
@@ -250,6 +260,32 @@ def main():
     launches = ctx.launch_count() - launches0
     ms_step = max_over_ranks(ms_total / args.steps)
     clk = clocks.summary()
+    graph_info = {"vcycles_replayed_from_graph": ctx.graph_replays()}
+    if world > 1 and ctx.graph_replays() > 0 and not os.environ.get("SAENA_BENCH_NO_AB"):
+        # A/B on the same uploaded hierarchy: the same solves with eager launches (not the bench value)
+        ctx.set_graphs(False)
+        ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+        barrier()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+        eager_ms = ctx.timer_stop()
+        barrier()
+        graph_info["eager_ms_per_step"] = max_over_ranks(eager_ms / args.steps)
+        ctx.set_graphs(True)
+        if halo_transport.startswith("nvlink peer memory, fused"):
+            # and with the exchange as separate launches (pack kernel, memory-op flags, boundary kernel)
+            ctx.p2p_enable(1)
+            for _ in range(2):
+                ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+            barrier()
+            ctx.timer_start()
+            for _ in range(args.steps):
+                ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+            unfused_ms = ctx.timer_stop()
+            barrier()
+            graph_info["unfused_halo_ms_per_step"] = max_over_ranks(unfused_ms / args.steps)
+            ctx.p2p_enable(2)
 
     # ---- e2e: host buffers through the reference-facing entry point, copies inside the timed region
     ctx._ck(ctx._L.saena_b200_solve_pcg(ctx._h, rhs_host.data_ptr(), u_host.data_ptr(), OPTS["max_iter"], OPTS["tol"],
@@ -314,6 +350,13 @@ def main():
     solve_bytes = (iters + 1) * vcycle_bytes + iters * krylov_bytes
     solve_gbs = solve_bytes / ms_step / 1e6
 
+    # ---- what each level costs inside a solve: V-cycles entered at level l, consecutive differences
+    vc = [max_over_ranks(ctx.time_vcycle(l, OPTS["smoother"], OPTS["pre"], OPTS["post"], 10))
+          for l in range(len(hier.levels))]
+    vcycle_levels = {"unit": "ms per V-cycle, eager launches, max over ranks",
+                     "entered_at_level": vc,
+                     "level_share": [vc[l] - (vc[l + 1] if l + 1 < len(vc) else 0.0) for l in range(len(vc))]}
+
     halo = None
     if world > 1:
         full_ms, local_ms, halo_ms = ctx.time_matvec_parts(0, KIND_A, 20)
@@ -327,11 +370,14 @@ def main():
     total_unknowns = n ** 3
     line = {"metric": METRIC, "value": total_unknowns / (ms_step / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"3D 7-point Poisson {n}^3 = {total_unknowns} unknowns, AMG-PCG to 1e-8 "
                                    f"(BASELINE.json configs[1] at n=256)",
                        "options": "options006_poisson.xml: chebyshev 3+3, conn_str 0.2, float_level 0, max_iter 50",
-                       "levels": len(hier.levels), "partition": f"{world} row block(s), nnz-balanced",
+                       "levels": len(hier.levels), "partition": f"{world} row block(s), nnz-balanced" + (
+                           f"; coarse levels follow the level above, re-split when a rank exceeds "
+                           f"{args.rebalance_above:g}x the mean nnz; levels under {args.agglomerate_below} rows on rank 0"
+                           if world > 1 else ""),
                        "l2": "inputs larger than L2 (level-0/1 operators are GBs); per-kernel timings of "
                              "L2-sized levels flush L2 between launches"},
             "solve_s": ms_step / 1e3, "iterations": iters, "rel_residual": rel_res,
@@ -340,7 +386,8 @@ def main():
             "e2e": {"value": total_unknowns / (e2e_ms / 1e3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 8 * total_unknowns, "d2h_bytes_per_step": 8 * total_unknowns,
                     "timer": "wall clock between device synchronisations (host copies included)"},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "levels": levels_tbl}
+            "gpu_launches": int(launches), "vcycle_graph": graph_info, "vcycle_levels": vcycle_levels, "clocks": clk, "roofline": roofline,
+            "levels": levels_tbl}
     if halo is not None:
         line["halo_overlap"] = halo
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -349,6 +396,22 @@ def main():
             line["cpu_baseline"]["iterations"] = cpu_iters
         except Exception as e:  # the bench line must still come out
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(e)}
+    # tuning only (SAENA_BENCH_AGG_SWEEP="2000,50000"): the same solves with other agglomeration thresholds
+    for thr in agg_sweep:
+        hier2 = dh.to_rank(rank, world, agglomerate_below=thr, rebalance_above=args.rebalance_above)
+        barrier()
+        ctx.upload_hierarchy(hier2)
+        if halo_transport != "nccl":
+            setup_p2p_halo(ctx)
+        for _ in range(3):
+            ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+        barrier()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            it2, _ = ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+        ms2 = max_over_ranks(ctx.timer_stop() / args.steps)
+        barrier()
+        line.setdefault("agglomerate_sweep", []).append({"agglomerate_below": thr, "ms_per_step": ms2, "iterations": it2})
     if world > 1:
         dist.barrier()   # nobody unmaps a peer's arena while that peer may still write into it
     ctx.close()

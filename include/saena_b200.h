@@ -114,9 +114,14 @@ int saena_b200_upload_coarsest(saena_b200_ctx *ctx, int n, int64_t nnz, const in
  * in the reference, the dense factor here), 1 = solve_coarsest_CG (src/saena_object_solve.cpp:14-114). */
 int saena_b200_set_coarsest_solver(saena_b200_ctx *ctx, int use_cg);
 
-/* The preconditioner's V-cycle is replayed from a CUDA graph (captured on first use) when it
- * contains no communication and no host-side decision; 0 switches that off (eager launches). */
+/* The preconditioner's V-cycle is replayed from a CUDA graph when it contains no host-side
+ * decision: captured on first use on one rank; on several ranks the first V-cycle of a
+ * configuration runs eagerly and the second is captured -- halo flags, peer stores, the comm
+ * stream's fork/join and the ncclSend/ncclRecv of Grid::repart_u included (environment
+ * SAENA_B200_GRAPH_MULTI=0 keeps several ranks eager).  0 switches graphs off. */
 int saena_b200_set_graphs(saena_b200_ctx *ctx, int on);
+/* V-cycles replayed from a graph by this context since init */
+int64_t saena_b200_graph_replays(const saena_b200_ctx *ctx);
 
 /* Seal the hierarchy: allocates the per-level work vectors (Grid::allocate_mem, grid.cpp:165-172)
  * and picks each operator's kernel mapping from its nnz/row. */
@@ -127,9 +132,14 @@ int saena_b200_finalize(saena_b200_ctx *ctx);
  * sender's values land), the host all-gathers the blobs over whatever channel it has
  * (MPI_Allgather in the adaptor, torch.distributed in bench.py) and every rank imports the
  * concatenation (rank order, `blob_bytes` each).  From then on the ghost values of the distributed
- * SpMV are stored by the sender's pack kernel straight into the receiver's memory over NVLink;
- * without the import (or after saena_b200_p2p_enable(ctx, 0)) the exchange uses ncclSend/ncclRecv.
- * p2p_export with buf == NULL only reports the size. */
+ * SpMV are stored by the sender straight into the receiver's memory over NVLink, and the whole
+ * distributed operator application -- pack + peer stores, interior rows, rows that wait for the
+ * ghost values, fused epilogue -- is ONE kernel (csrc/fused_halo.cu; what matvec_sparse,
+ * src/saena_matrix_matvec.cpp:9-113, does with MPI_Isend/Irecv/Waitany around two loops).
+ * saena_b200_p2p_enable selects the transport: 2 = that fused kernel (default after the import),
+ * 1 = peer stores with separate launches (pack kernel, stream memory-op flags, boundary kernel),
+ * 0 = ncclSend/ncclRecv (what runs without the import).  Collective: every rank passes the same
+ * value.  p2p_export with buf == NULL only reports the size. */
 int saena_b200_p2p_export(saena_b200_ctx *ctx, void *buf, int64_t cap, int64_t *size_out);
 int saena_b200_p2p_import(saena_b200_ctx *ctx, const void *blobs, int64_t blob_bytes);
 int saena_b200_p2p_enable(saena_b200_ctx *ctx, int on);
@@ -177,6 +187,9 @@ int saena_b200_time_matvec_parts(saena_b200_ctx *ctx, int level, int kind, int r
  * is launched on): start records an event, stop records a second one, waits for it and returns
  * the device time between them. */
 int saena_b200_timer_start(saena_b200_ctx *ctx);
+/* ms per V-cycle entered at `level` from a zero iterate (reps back-to-back, eager, collective over
+ * the ranks); the difference between consecutive levels is one level's cost inside a solve */
+int saena_b200_time_vcycle(saena_b200_ctx *ctx, int level, int smoother, int pre, int post, int reps, float *ms_out);
 int saena_b200_timer_stop(saena_b200_ctx *ctx, float *ms_out);
 /* kernels launched by this context since init (bench.py's gpu_launches) */
 int64_t saena_b200_launch_count(const saena_b200_ctx *ctx);

@@ -4,6 +4,8 @@
 
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 thread_local std::string g_sb_init_error;
@@ -52,6 +54,8 @@ int saena_b200_init(saena_b200_ctx **ctx_out, int device_id, int rank, int nrank
     ctx->device = device_id;
     ctx->rank = rank;
     ctx->nranks = nranks;
+    if (const char *gm = getenv("SAENA_B200_GRAPH_MULTI")) ctx->use_graphs_multi = atoi(gm) != 0;
+    if (const char *hf = getenv("SAENA_B200_HALO_FUSED")) ctx->fused_default = atoi(hf) != 0;
     if (init_body(ctx, nccl_id)) {
         g_sb_init_error = ctx->error;
         delete ctx;
@@ -624,6 +628,28 @@ int saena_b200_time_smooth_sweep(saena_b200_ctx *ctx, int level, int smoother, i
     return 0;
 }
 
+// `reps` back-to-back V-cycles entered at `level` with a zero iterate (eager launches, collective),
+// CUDA events on the compute stream; ms per V-cycle.  T(level) - T(level+1) is what one level costs
+// inside the flow of a solve (bench.py's per-level share table).
+int saena_b200_time_vcycle(saena_b200_ctx *ctx, int level, int smoother, int pre, int post, int reps, float *ms_out) {
+    SB_ENTER();
+    if (level < 0 || level >= (int)ctx->levels.size() || reps < 1) SB_FAIL("time_vcycle: no such level");
+    DevLevel &lv = ctx->levels[level];
+    const double *rhs = level == 0 ? ctx->pcg_r : lv.rhs;
+    for (int it = -1; it < reps; ++it) {   // one untimed pass first
+        if (it == 0) SB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        for (size_t l = level; l < ctx->levels.size(); ++l) ctx->levels[l].cur = 0;
+        SB_TRY(sb_vcycle(ctx, level, smoother, pre, post, rhs, true));
+    }
+    SB_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    SB_CUDA(cudaEventSynchronize(ctx->ev_t1));
+    SB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+    float ms = 0.f;
+    SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+    *ms_out = ms / reps;
+    return 0;
+}
+
 int saena_b200_timer_start(saena_b200_ctx *ctx) {
     if (!ctx) return 1;
     SB_CUDA(cudaSetDevice(ctx->device));
@@ -666,6 +692,8 @@ int saena_b200_set_graphs(saena_b200_ctx *ctx, int on) {
     if (!on) sb_invalidate_graphs(ctx);
     return 0;
 }
+
+int64_t saena_b200_graph_replays(const saena_b200_ctx *ctx) { return ctx ? ctx->graph_replays : 0; }
 
 int saena_b200_get_mapping(const saena_b200_ctx *ctx, int level, int kind) {
     if (!ctx || level < 0 || level >= (int)ctx->levels.size()) return 0;

@@ -76,7 +76,25 @@ struct P2PSegment {
     long long start;              // first packed element of this receiver's slice
     long long count;
     void *dst;                    // peer ghost slice (double* or float*)
-    unsigned long long *arrived;  // flag in the PEER's arena: "epoch e of this operator has landed"
+    unsigned long long *arrived;  // flag in the PEER's arena: "this operator's ghost values have landed"
+};
+
+// Fused halo kernel (csrc/fused_halo.cu): one slice of the packed send order, where it lands in
+// the receiver's landing area (doubles) and the epoch counter the last pack CTA raises there.
+struct FusedSeg {
+    long long start;
+    long long count;
+    double *dst;
+    unsigned long long *arrived;
+};
+
+struct FusedHaloDev {
+    unsigned long long *epoch = nullptr;  // applications completed (device memory: graph-replayable)
+    unsigned int *tickets = nullptr;      // [2] last-CTA detection: pack CTAs / all hand-shake CTAs
+    FusedSeg *segs = nullptr;                      // [sends.size()]
+    unsigned long long **wait_consumed = nullptr;  // [sends.size()] my arena: receiver r consumed epoch e
+    unsigned long long **wait_arrived = nullptr;   // [recvs.size()] my arena: sender s's epoch e has landed
+    unsigned long long **signal_consumed = nullptr;  // [recvs.size()] the senders' arenas
 };
 
 struct DevOperator {
@@ -132,13 +150,18 @@ struct DevOperator {
 
     // peer-memory path (set by saena_b200_p2p_import; the NCCL path stays as the fallback)
     bool p2p = false;
-    unsigned long long epoch = 0;                 // applications so far
     P2PSegment *p2p_segs = nullptr;               // device copy, [sends.size()]
     unsigned int *p2p_ticket = nullptr;           // last-block detection of the pack kernel
     std::vector<unsigned long long *> p2p_wait_arrived;    // my arena: one flag per sender
     std::vector<unsigned long long *> p2p_wait_consumed;   // my arena: one flag per receiver of mine
     unsigned long long **p2p_signal_consumed = nullptr;    // device array of peers' flags, [recvs.size()]
     size_t ghost_arena_off = 0;                   // where this operator's ghost area starts in the arena
+
+    // fused path (fused_halo.cu): exchange + SpMV in one kernel; default once the peers are imported
+    bool fused = false;
+    double *ghost_d = nullptr;                    // landing area in the arena, recvSize doubles
+    size_t ghost_d_off = 0;
+    FusedHaloDev fh;
 
     // kernel mapping
     int lanes = 0;            // lanes per row (vec) / lanes per row in the reduce phase (stream)
@@ -183,6 +206,7 @@ struct VcycleGraph {
     cudaGraphExec_t exec;
     int64_t launches;
     std::vector<int> cur_after;  // each level's ping-pong parity when the V-cycle ends
+    bool exec_pending;           // multi-rank: seen once (ran eagerly), captured at the next use
 };
 
 struct saena_b200_ctx {
@@ -196,6 +220,8 @@ struct saena_b200_ctx {
     std::vector<DevLevel> levels;
     bool finalized = false;
     bool use_graphs = true;
+    bool use_graphs_multi = true;   // capture with nranks > 1 too (SAENA_B200_GRAPH_MULTI=0 turns it off)
+    int64_t graph_replays = 0;
     std::vector<VcycleGraph> graphs;
     bool scale = false;  // saena_object::scale
     int apply_mode = 0;  // measurement only: 0 full, 1 local kernels only (no exchange), 2 pack + exchange only
@@ -230,6 +256,7 @@ struct saena_b200_ctx {
     size_t arena_bytes = 0;
     std::vector<void *> peer_arena;  // [nranks] IPC mappings of the peers' arenas (nullptr: not opened)
     bool p2p_ready = false;
+    bool fused_default = true;  // p2p_import switches eligible operators to the fused kernel (SAENA_B200_HALO_FUSED=0: no)
 
     // L2 flush buffer for the timing loops
     void *flush_buf = nullptr;
@@ -271,6 +298,10 @@ void sb_arena_free(saena_b200_ctx *ctx);
 int sb_p2p_pack_and_signal(saena_b200_ctx *ctx, DevOperator &op, const double *x, cudaStream_t s);
 int sb_p2p_wait_arrived(saena_b200_ctx *ctx, DevOperator &op, cudaStream_t s);
 int sb_p2p_signal_consumed(saena_b200_ctx *ctx, DevOperator &op, cudaStream_t s);
+
+// ---- fused_halo.cu
+bool sb_fused_eligible(const DevOperator &op);
+int sb_apply_fused(saena_b200_ctx *ctx, DevOperator &op, const double *x, int epi, const EpiArgs &args);
 
 // ---- vector_ops.cu
 int sb_dot(saena_b200_ctx *ctx, const double *a, const double *b, int n, int slot);           // scalars[slot] = <a,b> (global)

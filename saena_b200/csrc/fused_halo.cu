@@ -1,0 +1,247 @@
+// fused_halo.cu -- the distributed SpMV of one rank as ONE kernel: ghost-value exchange over
+// NVLink peer memory + interior rows + rows that need ghost values, with the smoother / residual /
+// correction epilogue fused as everywhere else.
+//
+// What it replaces: saena_matrix::matvec_sparse[_float] in full
+// (/root/reference/src/saena_matrix_matvec.cpp:9-113, :448-550) -- pack (:25-26), MPI_Isend/Irecv
+// (:32-41), local loop (:68-80), MPI_Waitany + remote loop (:87-110) -- and the same structure of
+// prolong_matrix::matvec_sparse / restrict_matrix::matvec_sparse.
+//
+// Why one kernel.  With the exchange as separate launches (pack kernel on a comm stream, stream
+// memory-op waits, boundary kernel, signal kernel: p2p_halo.cu) every operator application of a
+// multi-rank V-cycle carries ~40 us that no bandwidth explains (measured on 8 B200: 256^3 Poisson,
+// levels 2-4, 9 applications per level per V-cycle; replaying the V-cycle from a CUDA graph did
+// not remove it, so it is device-side dependency latency, not launch cost).  Here a CTA's role
+// follows from its index:
+//
+//   [0, n_pack)                  pack: wait until the receivers have consumed my previous values,
+//                                gather x[vIndex[i]] (rounded through float when the operator's
+//                                use_double is false -- the same value matvec_sparse_float widens
+//                                on the receiving side) and store it straight into the receiving
+//                                rank's landing area; the last pack CTA raises `arrived` there
+//   [n_pack, n_pack + n_int)     interior rows: no ghost column, start at once -- this is the part
+//                                of the SpMV that hides the transfer
+//   the rest                     rows with ghost columns: spin (one thread per sender, on this
+//                                rank's OWN memory) until `arrived`, then compute.  Split operators
+//                                run the boundary-row body (local CSR segment + ghost segment);
+//                                merged operators (every row couples to ghosts) run the ordinary
+//                                mapping over [local | ghost] columns, the gather choosing the
+//                                source by column index -- no x_ext copy, no widen pass.
+//   last CTA of the hand-shake   tells every sender its values are consumed, advances the epoch
+//
+// The epoch lives in device memory (read by the CTAs, advanced by the last one), flags are
+// monotonic counters, so a launch carries no host-side state: the kernel replays from a CUDA graph.
+// Progress: CTAs are dispatched in index order, so the pack CTAs of a launch are resident before
+// any CTA of the same launch spins; they wait only on `consumed`, which the peers raised at the
+// end of THEIR previous launch of this operator.  No cycle.
+#include <algorithm>
+
+#include "spmv_kernels.cuh"
+
+struct FusedArgs {
+    // operator (32-bit row offsets only; nnz >= 2^31 keeps the unfused path)
+    const int *rowptr;
+    const int *col;
+    const double *val;
+    const long long *sell_ptr;
+    const int *sell_col;
+    const double *sell_val;
+    int M, int_lo, int_hi, n_local;
+    // rows with remote entries of a split operator
+    int n_brows, bnd_wide;
+    const int *brow;
+    const int *brow_ptr;
+    const int *bcol;
+    const double *bval;
+    const double *x;
+    const double *ghost;  // this rank's landing area (doubles)
+    EpiArgs e;
+    // CTA roles: pack | interior rows | rows that wait for ghosts.  The waiting CTAs are at most a
+    // chip-full (resident all at once) and stride over n_wait_blocks virtual blocks, so the
+    // hand-shake is paid once per CTA, not once per row block
+    int n_pack, n_int, n_wait, n_wait_blocks;
+    int do_sync, do_compute;
+    // pack
+    int vIndexSize, n_segs, round_float;
+    const int *vIndex;
+    const FusedSeg *segs;
+    // hand-shake
+    unsigned long long *epoch;
+    unsigned int *tickets;  // [0] pack CTAs done, [1] pack + waiting CTAs done
+    unsigned long long *const *wait_consumed;    // [n_segs]  my arena
+    unsigned long long *const *wait_arrived;     // [n_recv]  my arena
+    unsigned long long *const *signal_consumed;  // [n_recv]  the senders' arenas
+    int n_recv;
+};
+
+template <int MAP, int EPI, typename XS>
+__device__ __forceinline__ void fused_rows(int vb, int lo, int hi, const FusedArgs &a, const XS xs) {
+    if constexpr (MAP == SB_MAPPING_SELL)
+        spmv_sell_body<EPI>(vb, lo, hi, a.sell_ptr, a.sell_col, a.sell_val, xs, a.e, nullptr);
+    else if constexpr (MAP >= 32)
+        spmv_rowgroup_body<MAP, EPI, int>(vb, lo, hi, a.rowptr, a.col, a.val, xs, a.e, nullptr);
+    else
+        spmv_vec_body<MAP, EPI, int>(vb, lo, hi, a.rowptr, a.col, a.val, xs, a.e, nullptr);
+}
+
+template <int MAP, int EPI, bool MERGED>
+__global__ void __launch_bounds__(256)
+fused_halo_spmv_kernel(const __grid_constant__ FusedArgs a) {
+    __shared__ unsigned long long s_epoch;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (b >= a.n_pack && b < a.n_pack + a.n_int) {
+        // interior rows of a split operator: nothing to wait for
+        fused_rows<MAP, EPI>(b - a.n_pack, a.int_lo, a.int_hi, a, XLocal{a.x});
+        return;
+    }
+    if (a.do_sync) {
+        if (tid == 0) s_epoch = *(volatile unsigned long long *)a.epoch;
+        __syncthreads();
+    }
+    const unsigned long long done = a.do_sync ? s_epoch : 0ull;  // applications completed before this one
+    if (b < a.n_pack) {
+        // ---- pack + peer stores
+        if (tid < a.n_segs) {
+            const volatile unsigned long long *f = a.wait_consumed[tid];
+            while (*f < done) __nanosleep(40);
+        }
+        __syncthreads();
+        const int i = b * 256 + tid;
+        if (i < a.vIndexSize) {
+            int s = 0;
+            while (s + 1 < a.n_segs && i >= a.segs[s + 1].start) ++s;  // a handful of receivers
+            double v = a.x[a.vIndex[i]];
+            if (a.round_float) v = (double)(float)v;  // matvec_sparse_float: the value the receiver would widen
+            a.segs[s].dst[i - a.segs[s].start] = v;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int t = atomicAdd(&a.tickets[0], 1u);
+            if (t == (unsigned int)a.n_pack - 1u) {
+                __threadfence_system();
+                for (int s = 0; s < a.n_segs; ++s) *(volatile unsigned long long *)a.segs[s].arrived = done + 1ull;
+                a.tickets[0] = 0u;
+            }
+        }
+    } else {
+        // ---- rows that read ghost values
+        if (a.do_sync) {
+            if (tid < a.n_recv) {
+                const volatile unsigned long long *f = a.wait_arrived[tid];
+                while (*f < done + 1ull) __nanosleep(40);
+            }
+            __threadfence();
+            __syncthreads();
+        }
+        if (a.do_compute) {
+            for (int vb = b - a.n_pack - a.n_int; vb < a.n_wait_blocks; vb += a.n_wait) {
+                if constexpr (MERGED) {
+                    fused_rows<MAP, EPI>(vb, 0, a.M, a, XGhost{a.x, a.ghost, a.n_local});
+                    if constexpr (MAP >= 64 && MAP != SB_MAPPING_SELL) __syncthreads();  // s_part is reused
+                } else {
+                    if (a.bnd_wide)
+                        spmv_boundary_body<32, EPI, int, double>(vb, a.n_brows, a.brow, a.rowptr, a.col, a.val,
+                                                                 a.brow_ptr, a.bcol, a.bval, a.x, a.ghost, a.e);
+                    else
+                        spmv_boundary_body<8, EPI, int, double>(vb, a.n_brows, a.brow, a.rowptr, a.col, a.val,
+                                                                a.brow_ptr, a.bcol, a.bval, a.x, a.ghost, a.e);
+                }
+            }
+        }
+    }
+    if (!a.do_sync) return;
+    // ---- the last CTA of the hand-shake releases the senders and advances the epoch
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(&a.tickets[1], 1u);
+        if (t == (unsigned int)(a.n_pack + a.n_wait) - 1u) {
+            for (int r = 0; r < a.n_recv; ++r) *(volatile unsigned long long *)a.signal_consumed[r] = done + 1ull;
+            *(volatile unsigned long long *)a.epoch = done + 1ull;
+            a.tickets[1] = 0u;
+            __threadfence_system();
+        }
+    }
+}
+
+static int main_blocks(const DevOperator &op, int nrows) {
+    if (nrows <= 0) return 0;
+    if (op.use_sell || op.lanes < 32) return (nrows + 255) / 256;
+    const int rows_per_block = 256 / op.lanes;
+    return (nrows + rows_per_block - 1) / rows_per_block;
+}
+
+bool sb_fused_eligible(const DevOperator &op) {
+    return op.fused && !op.wide_offsets && !op.use_stream && (!op.sends.empty() || !op.recvs.empty());
+}
+
+template <int EPI, bool MERGED>
+static int launch_fused(saena_b200_ctx *ctx, const DevOperator &op, const FusedArgs &a, int grid) {
+    cudaStream_t s = ctx->stream;
+#define SB_FUSED_CASE(MAP)                                                                          \
+    case MAP: fused_halo_spmv_kernel<MAP, EPI, MERGED><<<grid, 256, 0, s>>>(a); break;
+    switch (op.use_sell ? SB_MAPPING_SELL : op.lanes) {
+        SB_FUSED_CASE(100) SB_FUSED_CASE(1) SB_FUSED_CASE(2) SB_FUSED_CASE(4) SB_FUSED_CASE(8) SB_FUSED_CASE(16)
+        SB_FUSED_CASE(32) SB_FUSED_CASE(64) SB_FUSED_CASE(128) SB_FUSED_CASE(256)
+        default: SB_FAIL("fused apply: unknown mapping");
+    }
+#undef SB_FUSED_CASE
+    SB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int EPI>
+static int apply_fused_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, const EpiArgs &e) {
+    static_assert(SB_MAPPING_SELL == 100, "mapping code");
+    const int mode = ctx->apply_mode;  // 0 full, 1 compute only (stale ghosts), 2 exchange only
+    FusedArgs a{};
+    a.rowptr = (const int *)op.rowptr; a.col = op.col; a.val = op.val;
+    a.sell_ptr = op.sell_ptr; a.sell_col = op.sell_col; a.sell_val = op.sell_val;
+    a.M = op.M; a.int_lo = op.int_lo; a.int_hi = op.int_hi; a.n_local = op.n_local_cols;
+    a.n_brows = op.n_brows; a.bnd_wide = op.avg_nnz_row() >= 48.0;
+    a.brow = op.brow; a.brow_ptr = op.brow_ptr; a.bcol = op.bcol; a.bval = op.bval;
+    a.x = x; a.ghost = op.ghost_d; a.e = e;
+    a.do_sync = mode != 1;
+    a.do_compute = mode != 2;
+    a.vIndexSize = op.vIndexSize; a.vIndex = op.vIndex; a.segs = op.fh.segs; a.n_segs = (int)op.sends.size();
+    a.round_float = !op.use_double;
+    a.epoch = op.fh.epoch; a.tickets = op.fh.tickets;
+    a.wait_consumed = op.fh.wait_consumed; a.wait_arrived = op.fh.wait_arrived;
+    a.signal_consumed = op.fh.signal_consumed; a.n_recv = (int)op.recvs.size();
+    a.n_pack = mode == 1 ? 0 : (op.vIndexSize + 255) / 256;
+    if (op.merged) {
+        a.n_int = 0;
+        a.n_wait_blocks = main_blocks(op, op.M);
+    } else {
+        a.n_int = main_blocks(op, op.int_hi - op.int_lo);
+        const int rows_per_block = 256 / (a.bnd_wide ? 32 : 8);
+        a.n_wait_blocks = (op.n_brows + rows_per_block - 1) / rows_per_block;
+    }
+    if (mode == 2) {
+        a.n_int = 0;
+        a.n_wait_blocks = op.recvs.empty() ? 0 : 1;
+    }
+    // a chip-full of waiting CTAs (8 x 256 threads per SM at <= 32 registers; fewer fit for the
+    // wider sub-warp mappings, the excess simply starts later -- every spinning CTA's producer is
+    // a pack CTA of another rank, never a CTA behind it in this grid)
+    a.n_wait = std::min(a.n_wait_blocks, 8 * ctx->sm_count);
+    if (mode != 1 && a.n_wait == 0 && !op.recvs.empty()) SB_FAIL("fused apply: receives but no row reads them");
+    const int grid = a.n_pack + a.n_int + a.n_wait;
+    if (grid == 0) return 0;
+    ++ctx->launches;
+    if (op.merged) return launch_fused<EPI, true>(ctx, op, a, grid);
+    return launch_fused<EPI, false>(ctx, op, a, grid);
+}
+
+int sb_apply_fused(saena_b200_ctx *ctx, DevOperator &op, const double *x, int epi, const EpiArgs &args) {
+    switch (epi) {
+        case EPI_PLAIN: return apply_fused_epi<EPI_PLAIN>(ctx, op, x, args);
+        case EPI_RESIDUAL: return apply_fused_epi<EPI_RESIDUAL>(ctx, op, x, args);
+        case EPI_CHEB_FIRST: return apply_fused_epi<EPI_CHEB_FIRST>(ctx, op, x, args);
+        case EPI_CHEB_NEXT: return apply_fused_epi<EPI_CHEB_NEXT>(ctx, op, x, args);
+        case EPI_JACOBI: return apply_fused_epi<EPI_JACOBI>(ctx, op, x, args);
+        case EPI_SUB: return apply_fused_epi<EPI_SUB>(ctx, op, x, args);
+    }
+    SB_FAIL("fused apply: unknown epilogue");
+}

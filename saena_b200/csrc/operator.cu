@@ -472,6 +472,8 @@ static int wait_halo(saena_b200_ctx *ctx, DevOperator &op) {
 
 template <int EPI>
 static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, const EpiArgs &e) {
+    // several ranks, peers imported: exchange + SpMV as one kernel (fused_halo.cu)
+    if (sb_fused_eligible(op)) return sb_apply_fused(ctx, op, x, EPI, e);
     const bool has_halo = !op.sends.empty() || !op.recvs.empty();
     const bool halo = has_halo && ctx->apply_mode != 1;
     const bool compute = ctx->apply_mode != 2;

@@ -142,50 +142,90 @@ int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const
 }
 
 void sb_invalidate_graphs(saena_b200_ctx *ctx) {
-    for (VcycleGraph &g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    for (VcycleGraph &g : ctx->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     ctx->graphs.clear();
+}
+
+// Multi-rank capture.  The halo's comm stream is forked from the compute stream by an event at
+// every operator application (operator.cu:apply_epi) and so joins the capture; with the
+// peer-memory halo nothing joins it back (the hand-over is a flag, p2p_halo.cu), so the capture
+// ends with an explicit join.  ncclSend/ncclRecv (Grid::repart_u to the agglomerated levels, or
+// the NCCL halo) are captured as NCCL's own graph nodes; every rank captures in the same call.
+static int join_comm_stream(saena_b200_ctx *ctx) {
+    if (ctx->nranks == 1) return 0;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    SB_CUDA(cudaStreamIsCapturing(ctx->comm_stream, &st));
+    if (st != cudaStreamCaptureStatusActive) return 0;
+    SB_CUDA(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
+    SB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+    return 0;
 }
 
 int sb_vcycle_from_zero(saena_b200_ctx *ctx, int smoother, int pre, int post, const double *rhs) {
     // a zero iterate is overwritten, so every level may start in buffer 0: the launch sequence
     // (pointers included) is then identical from one V-cycle to the next
     for (DevLevel &lv : ctx->levels) lv.cur = 0;
-    const bool capturable = ctx->use_graphs && ctx->nranks == 1 && !ctx->coarsest_cg;
+    const bool capturable = ctx->use_graphs && !ctx->coarsest_cg && (ctx->nranks == 1 || ctx->use_graphs_multi);
     if (!capturable) return sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
     for (VcycleGraph &g : ctx->graphs)
         if (g.rhs == rhs && g.smoother == smoother && g.pre == pre && g.post == post) {
+            // multi-rank: this configuration has run eagerly once (NCCL has opened its
+            // point-to-point channels, every lazy allocation is done) -- capture it now
+            if (!g.exec) break;
             SB_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
             ctx->launches += g.launches;
+            ++ctx->graph_replays;
             for (size_t l = 0; l < ctx->levels.size(); ++l) ctx->levels[l].cur = g.cur_after[l];
             return 0;
         }
-    // first use of this configuration: capture, instantiate, launch
+    if (ctx->nranks > 1) {
+        bool seen = false;
+        for (VcycleGraph &g : ctx->graphs)
+            seen |= (g.rhs == rhs && g.smoother == smoother && g.pre == pre && g.post == post);
+        if (!seen) {
+            VcycleGraph g{rhs, smoother, pre, post, nullptr, 0, {}, true};
+            ctx->graphs.push_back(g);
+            return sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
+        }
+    }
+    // first use of this configuration (second on several ranks): capture, instantiate, launch
     const int64_t before = ctx->launches;
     cudaGraph_t graph = nullptr;
     SB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
+    int rc = sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
+    if (!rc) rc = join_comm_stream(ctx);
     const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    auto drop_pending = [&]() {
+        for (size_t k = 0; k < ctx->graphs.size(); ++k)
+            if (!ctx->graphs[k].exec) { ctx->graphs.erase(ctx->graphs.begin() + k); --k; }
+    };
     if (rc || ce != cudaSuccess || !graph) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
         ctx->use_graphs = false;  // run eagerly from now on (the capture executed nothing)
         ctx->launches = before;
+        drop_pending();
         for (DevLevel &lv : ctx->levels) lv.cur = 0;
         if (rc) return rc;
+        ctx->error.clear();
         return sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
     }
-    VcycleGraph g{rhs, smoother, pre, post, nullptr, ctx->launches - before, {}};
+    VcycleGraph g{rhs, smoother, pre, post, nullptr, ctx->launches - before, {}, false};
     const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) {
         cudaGetLastError();
         ctx->use_graphs = false;
         ctx->launches = before;
+        drop_pending();
         for (DevLevel &lv : ctx->levels) lv.cur = 0;
         return sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
     }
     for (DevLevel &lv : ctx->levels) g.cur_after.push_back(lv.cur);
+    drop_pending();
     ctx->graphs.push_back(g);
     SB_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+    ++ctx->graph_replays;
     return 0;
 }

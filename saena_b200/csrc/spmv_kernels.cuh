@@ -56,19 +56,42 @@ __device__ __forceinline__ bool sb_row_skipped(const uint32_t *__restrict__ mask
 __device__ __forceinline__ double sb_ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int sb_ld_stream(const int *p) { return __ldcs(p); }
 
+// Where the gathered operand comes from.  XLocal: the rank's own vector.  XGhost (merged mode of the
+// fused halo kernel, csrc/fused_halo.cu): columns >= n_local are ghost values the neighbours stored
+// into this rank's landing area over NVLink.  Plain (L1-cached) loads: the gather reuses ghost
+// values across rows as much as local ones (deep levels: thousands of entries per row), and no
+// line of the landing area can be stale in L1 -- L1 is invalidated at every launch and within a
+// launch nothing reads the area before the `arrived` flag has been observed.
+struct XLocal {
+    const double *x;
+    __device__ __forceinline__ double ld(int c) const { return __ldg(x + c); }
+};
+struct XGhost {
+    const double *x;
+    const double *ghost;
+    int n_local;
+    __device__ __forceinline__ double ld(int c) const {
+        return c < n_local ? __ldg(x + c) : ghost[c - n_local];
+    }
+};
+
+// Every mapping is a __device__ body taking the CTA's index as an argument (`vb`), wrapped by a
+// plain __global__ kernel (one operator application on one rank) and reused by the fused halo
+// kernel, where a CTA's role -- pack, interior rows, rows waiting for ghost values -- depends on
+// its index.
 // ---------------------------------------------------------------------------------------------
 // spmv_vec: LANES lanes per row, warp = 32 consecutive rows, transposed epilogue
 // ---------------------------------------------------------------------------------------------
 constexpr int VEC_UNROLL = 4;
 
-template <int LANES, int EPI, typename OffT>
-__global__ void __launch_bounds__(256)
-spmv_vec_kernel(int row_begin, int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
-                const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
-                const uint32_t *__restrict__ skip_mask) {
+template <int LANES, int EPI, typename OffT, typename XS>
+__device__ __forceinline__ void
+spmv_vec_body(int vb, int row_begin, int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+              const double *__restrict__ val, const XS xs, const EpiArgs &e,
+              const uint32_t *__restrict__ skip_mask) {
     constexpr int G = 32 / LANES;  // rows in flight per warp per step
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warp = (vb * blockDim.x + threadIdx.x) >> 5;
     const int row0 = row_begin + warp * 32;  // rows [row_begin, M)
     if (row0 >= M) return;
     const int my_row = row0 + lane;
@@ -99,7 +122,7 @@ spmv_vec_kernel(int row_begin, int M, const OffT *__restrict__ rowptr, const int
                 a[q] = in ? sb_ld_stream(val + kk) : 0.0;
             }
 #pragma unroll
-            for (int q = 0; q < VEC_UNROLL; ++q) sum += a[q] * __ldg(x + c[q]);
+            for (int q = 0; q < VEC_UNROLL; ++q) sum += a[q] * xs.ld(c[q]);
         }
 #pragma unroll
         for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -110,22 +133,30 @@ spmv_vec_kernel(int row_begin, int M, const OffT *__restrict__ rowptr, const int
     if (my_row < M && !sb_row_skipped(skip_mask, my_row)) sb_epilogue<EPI>(my_row, mine, e);
 }
 
+template <int LANES, int EPI, typename OffT>
+__global__ void __launch_bounds__(256)
+spmv_vec_kernel(int row_begin, int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+                const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
+                const uint32_t *__restrict__ skip_mask) {
+    spmv_vec_body<LANES, EPI, OffT>(blockIdx.x, row_begin, M, rowptr, col, val, XLocal{x}, e, skip_mask);
+}
+
 // ---------------------------------------------------------------------------------------------
 // spmv_rowgroup: TPR = 32..256 threads per row, 256/TPR rows per CTA.  For the deep coarse levels
 // of a smoothed-aggregation hierarchy: a few thousand rows with thousands of non-zeros each
 // (256^3 Poisson: level 4 has 21 466 rows x 3025 nnz/row).  One row per warp-group keeps all SMs
 // busy where the 32-rows-per-warp mapping above would leave most of the chip idle.
 // ---------------------------------------------------------------------------------------------
-template <int TPR, int EPI, typename OffT>
-__global__ void __launch_bounds__(256)
-spmv_rowgroup_kernel(int row_begin, int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
-                     const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
-                     const uint32_t *__restrict__ skip_mask) {
+template <int TPR, int EPI, typename OffT, typename XS>
+__device__ __forceinline__ void
+spmv_rowgroup_body(int vb, int row_begin, int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+                   const double *__restrict__ val, const XS xs, const EpiArgs &e,
+                   const uint32_t *__restrict__ skip_mask) {
     constexpr int ROWS = 256 / TPR;
     constexpr int WPR = TPR / 32;  // warps per row
     __shared__ double s_part[8];
     const int g = threadIdx.x / TPR, sub = threadIdx.x % TPR;
-    const int row = row_begin + blockIdx.x * ROWS + g;  // rows [row_begin, M)
+    const int row = row_begin + vb * ROWS + g;  // rows [row_begin, M)
     double sum = 0.0;
     if (row < M) {
         const OffT start = rowptr[row], end = rowptr[row + 1];
@@ -140,7 +171,7 @@ spmv_rowgroup_kernel(int row_begin, int M, const OffT *__restrict__ rowptr, cons
                 a[q] = in ? sb_ld_stream(val + kk) : 0.0;
             }
 #pragma unroll
-            for (int q = 0; q < VEC_UNROLL; ++q) sum += a[q] * __ldg(x + c[q]);
+            for (int q = 0; q < VEC_UNROLL; ++q) sum += a[q] * xs.ld(c[q]);
         }
     }
 #pragma unroll
@@ -157,6 +188,14 @@ spmv_rowgroup_kernel(int row_begin, int M, const OffT *__restrict__ rowptr, cons
             sb_epilogue<EPI>(row, tot, e);
         }
     }
+}
+
+template <int TPR, int EPI, typename OffT>
+__global__ void __launch_bounds__(256)
+spmv_rowgroup_kernel(int row_begin, int M, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+                     const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
+                     const uint32_t *__restrict__ skip_mask) {
+    spmv_rowgroup_body<TPR, EPI, OffT>(blockIdx.x, row_begin, M, rowptr, col, val, XLocal{x}, e, skip_mask);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -255,12 +294,12 @@ spmv_stream_kernel(int M, const OffT *__restrict__ rowptr, const int *__restrict
 // stencil the x gather is coalesced too (neighbour j of 32 consecutive rows = 32 consecutive x).
 // No shuffles, no shared memory; the epilogue streams are coalesced by construction.
 // ---------------------------------------------------------------------------------------------
-template <int EPI>
-__global__ void __launch_bounds__(256)
-spmv_sell_kernel(int row_begin, int M, const long long *__restrict__ slice_ptr, const int *__restrict__ col,
-                 const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
-                 const uint32_t *__restrict__ skip_mask) {
-    const int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x;  // rows [row_begin, M), row_begin % 32 == 0
+template <int EPI, typename XS>
+__device__ __forceinline__ void
+spmv_sell_body(int vb, int row_begin, int M, const long long *__restrict__ slice_ptr, const int *__restrict__ col,
+               const double *__restrict__ val, const XS xs, const EpiArgs &e,
+               const uint32_t *__restrict__ skip_mask) {
+    const int row = row_begin + vb * blockDim.x + threadIdx.x;  // rows [row_begin, M), row_begin % 32 == 0
     const int lane = threadIdx.x & 31;
     const int slice = row >> 5;
     if ((slice << 5) >= M) return;
@@ -279,10 +318,18 @@ spmv_sell_kernel(int row_begin, int M, const long long *__restrict__ slice_ptr, 
             a[q] = sb_ld_stream(vp + (j + q) * 32);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) sum += a[q] * __ldg(x + c[q]);
+        for (int q = 0; q < 4; ++q) sum += a[q] * xs.ld(c[q]);
     }
-    for (; j < len; ++j) sum += sb_ld_stream(vp + j * 32) * __ldg(x + sb_ld_stream(cp + j * 32));
+    for (; j < len; ++j) sum += sb_ld_stream(vp + j * 32) * xs.ld(sb_ld_stream(cp + j * 32));
     if (row < M && !sb_row_skipped(skip_mask, row)) sb_epilogue<EPI>(row, sum, e);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256)
+spmv_sell_kernel(int row_begin, int M, const long long *__restrict__ slice_ptr, const int *__restrict__ col,
+                 const double *__restrict__ val, const double *__restrict__ x, EpiArgs e,
+                 const uint32_t *__restrict__ skip_mask) {
+    spmv_sell_body<EPI>(blockIdx.x, row_begin, M, slice_ptr, col, val, XLocal{x}, e, skip_mask);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -292,13 +339,13 @@ spmv_sell_kernel(int row_begin, int M, const long long *__restrict__ slice_ptr, 
 // matvec_sparse_float, saena_matrix_matvec.cpp:531-538 widens on use).
 // ---------------------------------------------------------------------------------------------
 template <int LANES, int EPI, typename OffT, typename GhostT>
-__global__ void __launch_bounds__(256)
-spmv_boundary_kernel(int n_brows, const int *__restrict__ brow, const OffT *__restrict__ rowptr,
-                     const int *__restrict__ col, const double *__restrict__ val,
-                     const int *__restrict__ brow_ptr, const int *__restrict__ bcol,
-                     const double *__restrict__ bval, const double *__restrict__ x,
-                     const GhostT *__restrict__ ghost, EpiArgs e) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void
+spmv_boundary_body(int vb, int n_brows, const int *__restrict__ brow, const OffT *__restrict__ rowptr,
+                   const int *__restrict__ col, const double *__restrict__ val,
+                   const int *__restrict__ brow_ptr, const int *__restrict__ bcol,
+                   const double *__restrict__ bval, const double *__restrict__ x,
+                   const GhostT *__restrict__ ghost, const EpiArgs &e) {
+    const int gid = vb * blockDim.x + threadIdx.x;
     const int b = gid / LANES, sub = gid % LANES;
     double sum = 0.0;
     int row = -1;
@@ -326,8 +373,19 @@ spmv_boundary_kernel(int n_brows, const int *__restrict__ brow, const OffT *__re
     if (sub == 0 && row >= 0) sb_epilogue<EPI>(row, sum, e);
 }
 
+template <int LANES, int EPI, typename OffT, typename GhostT>
+__global__ void __launch_bounds__(256)
+spmv_boundary_kernel(int n_brows, const int *__restrict__ brow, const OffT *__restrict__ rowptr,
+                     const int *__restrict__ col, const double *__restrict__ val,
+                     const int *__restrict__ brow_ptr, const int *__restrict__ bcol,
+                     const double *__restrict__ bval, const double *__restrict__ x,
+                     const GhostT *__restrict__ ghost, EpiArgs e) {
+    spmv_boundary_body<LANES, EPI, OffT, GhostT>(blockIdx.x, n_brows, brow, rowptr, col, val, brow_ptr, bcol, bval, x,
+                                                 ghost, e);
+}
+
 // merged mode: ghost values that travelled as float are widened into the tail of x_ext
-__global__ void widen_ghost_kernel(int n, const float *__restrict__ in, double *__restrict__ out) {
+static __global__ void widen_ghost_kernel(int n, const float *__restrict__ in, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (double)in[i];
 }

@@ -276,8 +276,15 @@ def operator_to_global_csr(op: Operator):
     return csr_from_counts(op.nnzPerRow_local), op.col_local.astype(I32), op.val_local
 
 
+def split_imbalance(indptr: np.ndarray, split: Sequence[int]) -> float:
+    """max over ranks of a block's nnz / the mean block nnz"""
+    split = np.asarray(split, I64)
+    per = np.asarray(indptr, I64)[split[1:]] - np.asarray(indptr, I64)[split[:-1]]
+    return float(per.max() * len(per) / max(int(per.sum()), 1))
+
+
 def partition_hierarchy(h: Hierarchy, nprocs: int, agglomerate_below: int = 0,
-                        align_coarse: bool = True) -> List[Hierarchy]:
+                        align_coarse: bool = True, rebalance_above: float = 0.0) -> List[Hierarchy]:
     """Row-partition a one-rank hierarchy over `nprocs` ranks, keeping Saena's layout per rank.
 
     Level 0 uses nnz-balanced contiguous row blocks; each coarse level follows the level above
@@ -288,6 +295,14 @@ def partition_hierarchy(h: Hierarchy, nprocs: int, agglomerate_below: int = 0,
     the repart plan gathers/scatters the coarse vector (the reference's shrink-to-one-rank case,
     /root/reference/src/saena_matrix_shrink.cpp:67-96).  The coarsest level is always on rank 0
     (decide_shrinking_c, same file), where the direct solve runs.
+
+    `rebalance_above` > 0: a coarse level whose aligned partition leaves one rank with more than
+    that multiple of the mean nnz is split by its own nnz balance instead -- the monotone aligned
+    rule drifts (256^3 Poisson on 8 ranks: rank 0 keeps 16 % of the mean at level 4, the last rank
+    three times the mean), and the heaviest rank sets the time of every operator application.
+    R and P are then simply partitioned by that split too (what the reference's `repart` achieves
+    by moving Ac after the fact, /root/reference/src/saena_matrix_repart.cpp:728-979); the levels
+    below follow the re-balanced one.  Grid::repart_u stays the identity.
 
     `align_coarse=False` splits every coarse level by its own nnz balance instead (what the
     reference's `repart` may do after coarsening): coarse and fine blocks then do not line up, the
@@ -315,6 +330,8 @@ def partition_hierarchy(h: Hierarchy, nprocs: int, agglomerate_below: int = 0,
             else:
                 al = aligned_coarse_split(csr_from_counts(Rp.nnzPerRow_local), Rp.col_local, Rp.val_local,
                                           splits[l - 1])
+                if rebalance_above > 0 and not agg and split_imbalance(indptr, al) > rebalance_above:
+                    al = np.asarray(balanced_split(indptr, nprocs), I64)
             aligned.append(al)
             sp = np.concatenate(([0], np.full(nprocs, lv.A.Mbig))).astype(I64) if agg else al
         splits.append(np.asarray(sp, I64))

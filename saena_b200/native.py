@@ -83,10 +83,13 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_time_matvec.argtypes = [vp, i, i, i, i, ctypes.POINTER(ctypes.c_float)]
     L.saena_b200_time_smooth_sweep.argtypes = [vp, i, i, i, i, ctypes.POINTER(ctypes.c_float)]
     L.saena_b200_time_matvec_parts.argtypes = [vp, i, i, i] + [ctypes.POINTER(ctypes.c_float)] * 3
+    L.saena_b200_time_vcycle.argtypes = [vp, i, i, i, i, i, ctypes.POINTER(ctypes.c_float)]
     L.saena_b200_timer_start.argtypes = [vp]
     L.saena_b200_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.saena_b200_launch_count.restype = ctypes.c_int64
     L.saena_b200_launch_count.argtypes = [vp]
+    L.saena_b200_graph_replays.restype = ctypes.c_int64
+    L.saena_b200_graph_replays.argtypes = [vp]
     L.saena_b200_set_mapping.argtypes = [vp, i, i, i]
     L.saena_b200_get_mapping.argtypes = [vp, i, i]
     L.saena_b200_operator_bytes.restype = ctypes.c_int64
@@ -103,7 +106,7 @@ EXPORTED_SYMBOLS = [
     "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_p2p_enable", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
-    "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_set_mapping", "saena_b200_get_mapping",
+    "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_time_vcycle", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_graph_replays", "saena_b200_set_mapping", "saena_b200_get_mapping",
     "saena_b200_operator_bytes",
 ]
 
@@ -237,7 +240,8 @@ class Context:
         joined = b"".join(blobs)
         self._ck(self._L.saena_b200_p2p_import(self._h, ctypes.create_string_buffer(joined, len(joined)), len(blobs[0])))
 
-    def p2p_enable(self, on: bool):
+    def p2p_enable(self, on: int):
+        """2: fused halo kernel (default after p2p_import), 1: peer stores with separate launches, 0: NCCL"""
         self._ck(self._L.saena_b200_p2p_enable(self._h, int(on)))
 
     def set_graphs(self, on: bool):
@@ -339,6 +343,11 @@ class Context:
                                                       ctypes.byref(h)))
         return f.value, l.value, h.value
 
+    def time_vcycle(self, level: int, smoother="chebyshev", pre=3, post=3, reps=10) -> float:
+        ms = ctypes.c_float(0)
+        self._ck(self._L.saena_b200_time_vcycle(self._h, level, smoother_id(smoother), pre, post, reps, ctypes.byref(ms)))
+        return ms.value
+
     def timer_start(self):
         self._ck(self._L.saena_b200_timer_start(self._h))
 
@@ -349,6 +358,9 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._L.saena_b200_launch_count(self._h))
+
+    def graph_replays(self) -> int:
+        return int(self._L.saena_b200_graph_replays(self._h))
 
     def set_mapping(self, level, kind, mapping: int):
         """mapping > 0: that many lanes per row (sub-warp mapping); < 0: streaming row blocks with

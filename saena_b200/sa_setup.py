@@ -359,7 +359,7 @@ class DeviceHierarchy:
         owner = torch.cummax(owner, 0).values
         return torch.searchsorted(owner, torch.arange(nprocs + 1, device=dev), right=False).cpu().numpy().astype(np.int64)
 
-    def splits(self, nprocs: int, agglomerate_below: int):
+    def splits(self, nprocs: int, agglomerate_below: int, rebalance_above: float = 0.0):
         """(row partition of every level, partition R of the level above writes into, agglomerated?)
         -- hierarchy.partition_hierarchy's rules"""
         L = len(self.levels)
@@ -373,6 +373,11 @@ class DeviceHierarchy:
                 splits.append(self._balanced_split(lv.A, nprocs).astype(np.int64))
                 continue
             al = all_on_0 if agglomerated[l - 1] else self._aligned_coarse_split(self.levels[l - 1].R, splits[l - 1])
+            if rebalance_above > 0 and not agg and not agglomerated[l - 1]:
+                from .hierarchy import csr_from_counts, split_imbalance
+                indptr = csr_from_counts(lv.A.counts().cpu().numpy())
+                if split_imbalance(indptr, al) > rebalance_above:
+                    al = self._balanced_split(lv.A, nprocs).astype(np.int64)
             aligned.append(al)
             splits.append(all_on_0 if agg else al)
         return splits, aligned, agglomerated
@@ -425,10 +430,11 @@ class DeviceHierarchy:
         op["sendProcCount"] = send_count[send_count != 0]
         return Operator(**op)
 
-    def to_rank(self, rank: int = 0, nprocs: int = 1, agglomerate_below: int = 0) -> Hierarchy:
+    def to_rank(self, rank: int = 0, nprocs: int = 1, agglomerate_below: int = 0,
+                rebalance_above: float = 0.0) -> Hierarchy:
         """This rank's share (hierarchy.partition_hierarchy semantics: nnz-balanced row blocks per
         level, levels below `agglomerate_below` global rows -- and always the coarsest -- on rank 0)."""
-        splits, aligned, agglomerated = self.splits(nprocs, agglomerate_below)
+        splits, aligned, agglomerated = self.splits(nprocs, agglomerate_below, rebalance_above)
         levels = []
         for l, lv in enumerate(self.levels):
             sp = splits[l]

@@ -54,9 +54,9 @@ def main():
     # change of one ghost value.  Over a whole solve that happens with O(1) probability, so with a
     # float halo the residual history can only be compared at ~1e-6; the north_star's 1e-9 is
     # checked on the same partitions with the halo kept in double (use_double forced).
-    for name, agg, align, dbl in ((GOLDEN[1], 150, True, False), (GOLDEN[1], 0, True, True),
-                                  (GOLDEN[0], 10 ** 9, True, False), (GOLDEN[1], 0, False, True),
-                                  (GOLDEN[1], 0, False, False), (GOLDEN[0], 0, False, True)):
+    for name, agg, align, dbl, reb in ((GOLDEN[1], 150, True, False, 0.0), (GOLDEN[1], 0, True, True, 1.02),
+                                       (GOLDEN[0], 10 ** 9, True, False, 0.0), (GOLDEN[1], 0, False, True, 0.0),
+                                       (GOLDEN[1], 0, False, False, 0.0), (GOLDEN[0], 0, False, True, 0.0)):
         g = Golden(name)
         if dbl:
             for lv in g.hier.levels:
@@ -64,19 +64,24 @@ def main():
                     if op_ is not None:
                         op_.use_double = True
         tol_hist = TOL_HIST if dbl else 1e-6
-        hs = partition_hierarchy(g.hier, world, agglomerate_below=agg, align_coarse=align)
+        hs = partition_hierarchy(g.hier, world, agglomerate_below=agg, align_coarse=align, rebalance_above=reb)
         mine = hs[rank]
         dist.barrier()   # no peer is still writing into the arena this upload is about to replace
         ctx.upload_hierarchy(mine)
-        # halo transport: NVLink peer memory on four cases (f32 and f64 halos), ncclSend/ncclRecv on two
-        use_p2p = (case_no % 3 != 2) and os.environ.get("SAENA_B200_HALO", "p2p") == "p2p"
+        # halo transport: the fused kernel (exchange + SpMV in one launch over NVLink peer memory) on
+        # three cases, peer stores with separate launches on two, ncclSend/ncclRecv on one
+        transport = ("fused", "fused", "nccl", "p2p", "fused", "p2p")[case_no % 6]
+        if os.environ.get("SAENA_B200_HALO", "p2p") != "p2p":
+            transport = "nccl"
         case_no += 1
+        use_p2p = transport != "nccl"
         if use_p2p:
             setup_p2p_halo(ctx)
+            ctx.p2p_enable(2 if transport == "fused" else 1)
         o = Oracle(hs)
         rng = np.random.default_rng(17)
-        tag = (f"{name}/agg{agg}/{'aligned' if align else 'misaligned'}/{'f64' if dbl else 'f32'}-halo/"
-               f"{'p2p' if use_p2p else 'nccl'}")
+        tag = (f"{name}/agg{agg}/{'aligned' if align else 'misaligned'}{'+rebalanced' if reb else ''}/{'f64' if dbl else 'f32'}-halo/"
+               f"{transport}")
         for l in range(len(mine.levels)):
             sizes = [h.levels[l].A.M for h in hs]
             off = np.concatenate(([0], np.cumsum(sizes)))
@@ -100,6 +105,22 @@ def main():
                 want = o.matvec(l, KIND_R, v_parts)
                 got = ctx.matvec(l, KIND_R, v_parts[rank])
                 worst[f"{tag}.L{l}.R"] = rel(np.concatenate(gather(got, csz, rank, world)), np.concatenate(want))
+            if transport == "fused" and l <= 1:
+                # every row mapping of the fused kernel (sliced, sub-warp, row-group), A and P; then the
+                # measurement modes (compute only / exchange only) must leave the hand-shake consistent
+                want_a = np.concatenate(o.matvec(l, KIND_A, v_parts))
+                for mp in (100, 1, 4, 16, 32, 256, 0):
+                    ctx.set_mapping(l, KIND_A, mp)
+                    got = ctx.matvec(l, KIND_A, v_parts[rank])
+                    worst[f"{tag}.L{l}.A.map{mp}"] = rel(np.concatenate(gather(got, sizes, rank, world)), want_a)
+                    if mine.levels[l].P is not None:
+                        ctx.set_mapping(l, KIND_P, mp)
+                        got = ctx.matvec(l, KIND_P, c_parts[rank])
+                        worst[f"{tag}.L{l}.P.map{mp}"] = rel(np.concatenate(gather(got, sizes, rank, world)),
+                                                             np.concatenate(o.matvec(l, KIND_P, c_parts)))
+                ctx.time_matvec_parts(l, KIND_A, 3)
+                got = ctx.matvec(l, KIND_A, v_parts[rank])
+                worst[f"{tag}.L{l}.A.after_parts"] = rel(np.concatenate(gather(got, sizes, rank, world)), want_a)
             want = o.vcycle(l, [np.zeros(s) for s in sizes], b_parts)
             got = ctx.vcycle(l, np.zeros(sizes[rank]), b_parts[rank])
             worst[f"{tag}.L{l}.vcycle"] = rel(np.concatenate(gather(got, sizes, rank, world)), np.concatenate(want)) / 10
@@ -107,7 +128,17 @@ def main():
         off = np.concatenate(([0], np.cumsum(sizes)))
         rhs_parts = [g.rhs[off[i]:off[i + 1]] for i in range(world)]
         u_o, it_o, h_o = o.solve_pcg(rhs_parts, g.max_iter, g.tol, "chebyshev", g.pre, g.post)
+        ctx.set_graphs(False)
+        u_e, it_e, h_e = ctx.solve_pcg(rhs_parts[rank], g.max_iter, g.tol, "chebyshev", g.pre, g.post)
+        ctx.set_graphs(True)
+        # first V-cycle of the solve runs eagerly, the second is captured (halo flags, peer stores /
+        # ncclSend/Recv and the comm stream's fork/join included), the rest replay that graph
+        rep0 = ctx.graph_replays()
         u, it, h = ctx.solve_pcg(rhs_parts[rank], g.max_iter, g.tol, "chebyshev", g.pre, g.post)
+        replays = ctx.graph_replays() - rep0
+        if os.environ.get("SAENA_B200_GRAPH_MULTI", "1") != "0":
+            assert replays >= it - 1 >= 1, (tag, "multi-rank V-cycle was not replayed from a graph", replays, it)
+        assert it == it_e and np.array_equal(h, h_e) and np.array_equal(u, u_e), (tag, "graph replay != eager solve")
         assert abs(it - it_o) <= 1, (tag, it, it_o)
         n = min(len(h), len(h_o))
         herr = float(np.max(np.abs(h[:n] - h_o[:n]) / h_o[:n]))
@@ -117,7 +148,8 @@ def main():
         d = ctx.dot(rhs_parts[rank], rhs_parts[rank])
         assert abs(d - float(g.rhs @ g.rhs)) <= 1e-12 * float(g.rhs @ g.rhs)
         if rank == 0:
-            print(f"{tag}: pcg iters {it} (oracle {it_o}), history err {herr:.2e}, u err {uerr:.2e}", flush=True)
+            print(f"{tag}: pcg iters {it} (oracle {it_o}), history err {herr:.2e}, u err {uerr:.2e}, "
+                  f"{replays} V-cycles replayed from a graph", flush=True)
     bad = {k: e for k, e in worst.items() if not e <= TOL_OP}
     assert not bad, bad
     dist.barrier()

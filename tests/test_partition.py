@@ -52,12 +52,17 @@ def test_partitioned_matvec_equals_one_rank(nranks):
     assert sum(hr.levels[0].A.nnz for hr in hs) == h.levels[0].A.nnz
 
 
-@pytest.mark.parametrize("nranks,agg", [(2, 0), (2, 10**9), (4, 150)])
-def test_partitioned_pcg_equals_one_rank_with_double_halo(nranks, agg):
+@pytest.mark.parametrize("nranks,agg,reb", [(2, 0, 0.0), (2, 10**9, 0.0), (4, 150, 0.0), (4, 0, 1.02), (3, 60, 1.05)])
+def test_partitioned_pcg_equals_one_rank_with_double_halo(nranks, agg, reb):
     g = Golden(GOLDEN[1])
     h = _force_double(g.hier)
     u1, it1, h1 = Oracle(h).solve_pcg(g.rhs)
-    hs = partition_hierarchy(h, nranks, agglomerate_below=agg)
+    hs = partition_hierarchy(h, nranks, agglomerate_below=agg, rebalance_above=reb)
+    if reb:
+        # the re-split really happened somewhere, and Grid::repart_u stayed the identity there
+        plain = partition_hierarchy(h, nranks, agglomerate_below=agg)
+        assert any(a.levels[l].A.M != b.levels[l].A.M for a, b in zip(hs, plain) for l in range(len(a.levels)))
+        assert all(lv.M_coarse_old == lv.M_coarse or lv.repart_send for hr in hs for lv in hr.levels if lv.P is not None)
     un, itn, hn = Oracle(hs).solve_pcg(_parts(hs, g.rhs))
     assert itn == it1
     assert np.max(np.abs(hn - h1) / h1) < 1e-9

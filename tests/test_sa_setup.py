@@ -57,13 +57,14 @@ def test_setup_reproduces_the_live_reference_at_32_cubed():
         s.close()
 
 
-@pytest.mark.parametrize("nprocs,agg", [(1, 0), (2, 0), (3, 200), (4, 10**9)])
-def test_device_partitioner_matches_numpy_partitioner(nprocs, agg):
+@pytest.mark.parametrize("nprocs,agg,reb", [(1, 0, 0.0), (2, 0, 0.0), (3, 200, 0.0), (4, 10**9, 0.0), (3, 0, 1.01),
+                                            (4, 50, 1.05)])
+def test_device_partitioner_matches_numpy_partitioner(nprocs, agg, reb):
     dh = build_device_hierarchy(*poisson3d_coo(10), device="cpu")
     one = dh.to_rank(0, 1)
-    want = partition_hierarchy(one, nprocs, agglomerate_below=agg) if nprocs > 1 else [one]
+    want = partition_hierarchy(one, nprocs, agglomerate_below=agg, rebalance_above=reb) if nprocs > 1 else [one]
     for r in range(nprocs):
-        got = dh.to_rank(r, nprocs, agglomerate_below=agg)
+        got = dh.to_rank(r, nprocs, agglomerate_below=agg, rebalance_above=reb)
         assert len(got.levels) == len(want[r].levels)
         for a, b in zip(got.levels, want[r].levels):
             for name in ("A", "P", "R"):
