@@ -215,6 +215,9 @@ def main():
             if os.environ.get("SAENA_B200_HALO_FUSED", "1") != "0":
                 halo_transport = ("nvlink peer memory, fused: pack + peer stores + interior rows + ghost rows "
                                   "in one kernel per operator application")
+                if os.environ.get("SAENA_B200_HALO_AUTOTUNE", "1") != "0":
+                    ctx.autotune_halo(10)   # per operator: fused kernel or separate launches, whichever measured faster
+                    halo_transport += "; per-operator choice fused / separate launches measured at setup"
             else:
                 halo_transport = "nvlink peer memory (pack kernel stores into the neighbour's ghost buffer)"
     for spec in filter(None, os.environ.get("SAENA_BENCH_MAP", "").split(",")):   # tuning: "level:kind:mapping"
@@ -274,18 +277,25 @@ def main():
         graph_info["eager_ms_per_step"] = max_over_ranks(eager_ms / args.steps)
         ctx.set_graphs(True)
         if halo_transport.startswith("nvlink peer memory, fused"):
-            # and with the exchange as separate launches (pack kernel, memory-op flags, boundary kernel)
-            ctx.p2p_enable(1)
-            for _ in range(2):
-                ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
-            barrier()
-            ctx.timer_start()
-            for _ in range(args.steps):
-                ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
-            unfused_ms = ctx.timer_stop()
-            barrier()
-            graph_info["unfused_halo_ms_per_step"] = max_over_ranks(unfused_ms / args.steps)
+            # the autotuner's per-operator choices (rank 0's timings), then the same solves with every
+            # operator on the fused kernel / on the separate launches (pack kernel, memory-op flags, boundary kernel)
+            graph_info["halo_autotune"] = [
+                dict(zip(("level", "kind", "fused", "ms_fused", "ms_separate"), (l, "APR"[k], *ctx.halo_choice(l, k))))
+                for l in range(len(hier.levels)) for k in (KIND_A, KIND_P, KIND_R) if ctx.halo_choice(l, k)[1] > 0]
+            for label, mode in (("all_fused_ms_per_step", 2), ("all_separate_ms_per_step", 1)):
+                ctx.p2p_enable(mode)
+                for _ in range(2):
+                    ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+                barrier()
+                ctx.timer_start()
+                for _ in range(args.steps):
+                    ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+                ab_ms = ctx.timer_stop()
+                barrier()
+                graph_info[label] = max_over_ranks(ab_ms / args.steps)
             ctx.p2p_enable(2)
+            if "per-operator" in halo_transport:
+                ctx.autotune_halo(10)
 
     # ---- e2e: host buffers through the reference-facing entry point, copies inside the timed region
     ctx._ck(ctx._L.saena_b200_solve_pcg(ctx._h, rhs_host.data_ptr(), u_host.data_ptr(), OPTS["max_iter"], OPTS["tol"],
@@ -403,6 +413,8 @@ def main():
         ctx.upload_hierarchy(hier2)
         if halo_transport != "nccl":
             setup_p2p_halo(ctx)
+            if "per-operator" in halo_transport:
+                ctx.autotune_halo(10)
         for _ in range(3):
             ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
         barrier()

@@ -143,6 +143,12 @@ int saena_b200_finalize(saena_b200_ctx *ctx);
 int saena_b200_p2p_export(saena_b200_ctx *ctx, void *buf, int64_t cap, int64_t *size_out);
 int saena_b200_p2p_import(saena_b200_ctx *ctx, const void *blobs, int64_t blob_bytes);
 int saena_b200_p2p_enable(saena_b200_ctx *ctx, int on);
+/* Measures both peer-memory paths on every operator of the uploaded hierarchy (reps back-to-back
+ * applications each, times summed over the ranks) and keeps the faster one per operator.
+ * Collective; call after p2p_import.  saena_b200_halo_choice reports the outcome for one operator
+ * (1 fused kernel, 0 separate launches / NCCL, -1 no such operator) and this rank's two timings. */
+int saena_b200_autotune_halo(saena_b200_ctx *ctx, int reps);
+int saena_b200_halo_choice(const saena_b200_ctx *ctx, int level, int kind, float *ms_fused, float *ms_unfused);
 
 /* ---- solvers -----------------------------------------------------------------------------
  * rhs / u are this rank's block (grids[0].A->M entries).  u is overwritten (zero initial

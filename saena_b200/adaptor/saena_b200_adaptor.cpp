@@ -202,6 +202,8 @@ DeviceSide &device_side(saena_object *obj) {
         MPI_Allgather(mine.data(), (int)n, MPI_BYTE, all.data(), (int)n, MPI_BYTE, A0->comm);
         CK(ds.ctx, saena_b200_p2p_import(ds.ctx, all.data(), n), "p2p import");
         MPI_Barrier(A0->comm);
+        // per operator: the fused halo kernel or the separate launches, whichever measures faster here
+        CK(ds.ctx, saena_b200_autotune_halo(ds.ctx, 10), "halo autotune");
     }
     if (g_verbose && ds.rank == 0) std::printf("saena_b200: hierarchy of %d levels uploaded\n", L + 1);
     return g_solvers[obj] = ds;

@@ -591,6 +591,66 @@ int saena_b200_time_matvec(saena_b200_ctx *ctx, int level, int kind, int reps, i
     return 0;
 }
 
+// Picks, per operator, the faster of the two peer-memory halo paths by measuring both on the
+// uploaded hierarchy: the fused kernel (fused_halo.cu) wins where an application is latency-bound
+// (coarse levels, many ranks), the separate launches (p2p_halo.cu: pack on the comm stream
+// overlapping a plain interior kernel) can win on the big fine levels.  Collective: every rank
+// times `reps` back-to-back applications of each operator both ways, the times are summed over
+// the ranks (ncclAllReduce) and every rank takes the same decision from the same sums.
+int saena_b200_autotune_halo(saena_b200_ctx *ctx, int reps) {
+    SB_ENTER();
+    if (ctx->nranks == 1 || !ctx->p2p_ready) return 0;
+    if (reps < 1) reps = 10;
+    sb_invalidate_graphs(ctx);
+    for (size_t l = 0; l < ctx->levels.size(); ++l) {
+        DevOperator *ops[3] = {&ctx->levels[l].A, &ctx->levels[l].P, &ctx->levels[l].R};
+        for (DevOperator *op : ops) {
+            double ms2[2] = {0.0, 0.0};
+            const bool mine = op->present && op->p2p && op->p2p_segs && (!op->sends.empty() || !op->recvs.empty());
+            if (mine) {
+                SB_TRY(stage_buf(ctx, 0, op->n_local_cols));
+                SB_TRY(stage_buf(ctx, 1, op->M));
+                SB_CUDA(cudaMemsetAsync(ctx->stage[0], 0, sizeof(double) * op->n_local_cols, ctx->stream));
+                EpiArgs e{};
+                e.out = ctx->stage[1];
+                for (int mode = 0; mode < 2; ++mode) {
+                    op->fused = mode == 0;
+                    if (op->fused && !sb_fused_eligible(*op)) { ms2[0] = 1e30; continue; }
+                    for (int it = -2; it < reps; ++it) {
+                        if (it == 0) SB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+                        SB_TRY(sb_apply(ctx, *op, ctx->stage[0], EPI_PLAIN, e));
+                    }
+                    SB_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
+                    SB_CUDA(cudaEventSynchronize(ctx->ev_t1));
+                    SB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+                    float ms = 0.f;
+                    SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+                    ms2[mode] = ms / reps;
+                }
+            }
+            if (op->present) { op->tune_ms[0] = (float)ms2[0]; op->tune_ms[1] = (float)ms2[1]; }
+            // same decision on every rank: sum over ranks (ranks without a halo on this operator add 0)
+            SB_CUDA(cudaMemcpyAsync(ctx->scalars + S_TMP, ms2, sizeof(ms2), cudaMemcpyHostToDevice, ctx->stream));
+            SB_TRY(sb_allreduce_sum(ctx, ctx->scalars + S_TMP, 2, ctx->stream));
+            SB_TRY(sb_read_scalars(ctx));
+            const double f = ctx->scalars_host[S_TMP], u = ctx->scalars_host[S_TMP + 1];
+            if (op->present && op->p2p && op->p2p_segs) op->fused = f <= u;
+        }
+    }
+    return 0;
+}
+
+// 1: fused kernel, 0: separate launches / NCCL, -1: no such operator; ms[2] = this rank's autotune timings
+int saena_b200_halo_choice(const saena_b200_ctx *ctx, int level, int kind, float *ms_fused, float *ms_unfused) {
+    if (!ctx || level < 0 || level >= (int)ctx->levels.size()) return -1;
+    const DevLevel &lv = ctx->levels[level];
+    const DevOperator &op = kind == SAENA_B200_KIND_A ? lv.A : (kind == SAENA_B200_KIND_P ? lv.P : lv.R);
+    if (!op.present) return -1;
+    if (ms_fused) *ms_fused = op.tune_ms[0];
+    if (ms_unfused) *ms_unfused = op.tune_ms[1];
+    return op.fused && sb_fused_eligible(op) ? 1 : 0;
+}
+
 // halo overlap of one operator: full application, local kernels alone, pack + exchange alone
 int saena_b200_time_matvec_parts(saena_b200_ctx *ctx, int level, int kind, int reps, float *full_ms,
                                  float *local_ms, float *halo_ms) {

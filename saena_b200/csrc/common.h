@@ -159,6 +159,7 @@ struct DevOperator {
 
     // fused path (fused_halo.cu): exchange + SpMV in one kernel; default once the peers are imported
     bool fused = false;
+    float tune_ms[2] = {0.f, 0.f};                // saena_b200_autotune_halo: fused / separate launches
     double *ghost_d = nullptr;                    // landing area in the arena, recvSize doubles
     size_t ghost_d_off = 0;
     FusedHaloDev fh;

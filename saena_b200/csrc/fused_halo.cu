@@ -84,8 +84,14 @@ __device__ __forceinline__ void fused_rows(int vb, int lo, int hi, const FusedAr
         spmv_vec_body<MAP, EPI, int>(vb, lo, hi, a.rowptr, a.col, a.val, xs, a.e, nullptr);
 }
 
+// The mappings whose stand-alone kernels fit 32 registers keep 8 CTAs per SM here too (the role
+// dispatch and the stride loop would otherwise push them to 40 and cost a quarter of the loads in
+// flight on the big fine levels); the 4/8/16-lane sub-warp mappings need 40-48 either way.
+template <int MAP>
+constexpr int fused_min_ctas() { return (MAP == 4 || MAP == 8 || MAP == 16) ? 4 : 8; }
+
 template <int MAP, int EPI, bool MERGED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, fused_min_ctas<MAP>())
 fused_halo_spmv_kernel(const __grid_constant__ FusedArgs a) {
     __shared__ unsigned long long s_epoch;
     const int b = blockIdx.x, tid = threadIdx.x;

@@ -71,7 +71,8 @@ struct XGhost {
     const double *ghost;
     int n_local;
     __device__ __forceinline__ double ld(int c) const {
-        return c < n_local ? __ldg(x + c) : ghost[c - n_local];
+        const double *p = c < n_local ? x + c : ghost + (c - n_local);  // one load from a selected address: no branch
+        return *p;
     }
 };
 

@@ -69,6 +69,8 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_p2p_export.argtypes = [vp, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
     L.saena_b200_p2p_import.argtypes = [vp, vp, ctypes.c_int64]
     L.saena_b200_p2p_enable.argtypes = [vp, i]
+    L.saena_b200_autotune_halo.argtypes = [vp, i]
+    L.saena_b200_halo_choice.argtypes = [vp, i, i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
     solve_args = [vp, vp, vp, i, d, i, i, i, ip, dp, i, ip]
     L.saena_b200_solve_pcg.argtypes = solve_args
     L.saena_b200_solve_pcg_dev.argtypes = solve_args
@@ -103,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "saena_b200_upload_operator", "saena_b200_upload_level_aux", "saena_b200_upload_level_scale",
     "saena_b200_upload_coarsest",
     "saena_b200_set_coarsest_solver", "saena_b200_set_graphs", "saena_b200_finalize",
-    "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_p2p_enable", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
+    "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_p2p_enable", "saena_b200_autotune_halo", "saena_b200_halo_choice", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
     "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_time_vcycle", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_graph_replays", "saena_b200_set_mapping", "saena_b200_get_mapping",
@@ -243,6 +245,16 @@ class Context:
     def p2p_enable(self, on: int):
         """2: fused halo kernel (default after p2p_import), 1: peer stores with separate launches, 0: NCCL"""
         self._ck(self._L.saena_b200_p2p_enable(self._h, int(on)))
+
+    def autotune_halo(self, reps: int = 10):
+        """collective: keep, per operator, the faster of the fused kernel and the separate launches"""
+        self._ck(self._L.saena_b200_autotune_halo(self._h, reps))
+
+    def halo_choice(self, level: int, kind: int):
+        """-> (choice, ms_fused, ms_unfused); choice 1 fused kernel, 0 separate launches / NCCL, -1 absent"""
+        a, b = ctypes.c_float(0), ctypes.c_float(0)
+        c = int(self._L.saena_b200_halo_choice(self._h, level, kind, ctypes.byref(a), ctypes.byref(b)))
+        return c, a.value, b.value
 
     def set_graphs(self, on: bool):
         self._ck(self._L.saena_b200_set_graphs(self._h, int(on)))

@@ -24,8 +24,35 @@ from saena_b200.hierarchy import hierarchy_to_arrays  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def make(name: str, mx: int, opts: RefOptions):
-    s = RefSolver.poisson(mx, opts)
+def read_mtx(path):
+    """MatrixMarket coordinate file -> 0-based COO as the reference's own readers take it
+    (saena::matrix::read_file keeps the entries as listed: general storage, no symmetrisation)"""
+    rows, cols, vals, n = [], [], [], None
+    with open(path) as f:
+        for line in f:
+            if line.startswith("%") or not line.strip():
+                continue
+            t = line.split()
+            if n is None:
+                n = int(t[0])
+                assert int(t[1]) == n
+                continue
+            rows.append(int(t[0]) - 1); cols.append(int(t[1]) - 1); vals.append(float(t[2]))
+    return n, np.array(rows, np.int32), np.array(cols, np.int32), np.array(vals)
+
+
+def band_coo(n: int, b: int):
+    """pattern and values of saena::band_matrix (/root/reference/src/aux_functions2.cpp:1296-1381):
+    row i, columns j in [i-b, i+b] inside [0, n), value 1/(i+j+1) (BASELINE.json configs[3] shape)"""
+    i = np.repeat(np.arange(n), 2 * b + 1)
+    j = i + np.tile(np.arange(-b, b + 1), n)
+    keep = (j >= 0) & (j < n)
+    i, j = i[keep], j[keep]
+    return n, i.astype(np.int32), j.astype(np.int32), 1.0 / (i + j + 1.0)
+
+
+def make(name: str, mx, opts: RefOptions, coo=None, rhs=None, with_pcg: bool = True):
+    s = RefSolver.poisson(mx, opts) if coo is None else RefSolver.from_coo(*coo, rhs, opts)
     h = s.hierarchy()
     rng = np.random.default_rng(12345)
     out = {("hier." + k): v for k, v in hierarchy_to_arrays(h).items()}
@@ -51,10 +78,12 @@ def make(name: str, mx: int, opts: RefOptions):
     out["in.coarsest.b"] = bc
     out["out.coarsest.u"] = s.coarsest_solve(bc)
     out["out.dot"] = np.array([s.dot(out["in.L0.v"], out["in.L0.b"])])
-    u, iters, hist = s.solve_pcg()
-    out["out.pcg.u"] = u
-    out["out.pcg.iters"] = np.array([iters])
-    out["out.pcg.hist"] = hist
+    iters = -1
+    if with_pcg:
+        u, iters, hist = s.solve_pcg()
+        out["out.pcg.u"] = u
+        out["out.pcg.iters"] = np.array([iters])
+        out["out.pcg.hist"] = hist
     out["opts"] = np.array([opts.max_iter, opts.tol, opts.pre, opts.post, opts.float_level])
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
@@ -62,6 +91,26 @@ def make(name: str, mx: int, opts: RefOptions):
     s.close()
 
 
+DATA = "/root/reference/data"
+
+
 if __name__ == "__main__":
-    make("poisson12_cheb", 12, RefOptions())
-    make("poisson9_cheb", 9, RefOptions())
+    which = sys.argv[1:] or ["poisson12_cheb", "poisson9_cheb", "helmholtz2d_p8", "homg33", "band8_1500"]
+    rng = np.random.default_rng(2024)
+    if "poisson12_cheb" in which:
+        make("poisson12_cheb", 12, RefOptions())
+    if "poisson9_cheb" in which:
+        make("poisson9_cheb", 9, RefOptions())
+    if "helmholtz2d_p8" in which:
+        # BASELINE.json configs[4]'s shape donor: irregular rows (24..40 non-zeros), general storage
+        coo = read_mtx(f"{DATA}/Helmholtz2D_CG_curved_tri/Helmholtz2D_CG_P8_Modes_curved_tri.mtx")
+        make("helmholtz2d_p8", None, RefOptions(), coo, rng.uniform(-1, 1, coo[0]))
+    if "homg33" in which:
+        coo = read_mtx(f"{DATA}/homg/A.mtx")
+        rhs = np.loadtxt(f"{DATA}/homg/rhs.txt", skiprows=1)[:, 2]   # "i 1 value" lines under a size header
+        make("homg33", None, RefOptions(), coo, rhs)
+    if "band8_1500" in which:
+        # BASELINE.json configs[3]'s pattern (experiments/banded.cpp), small; 1/(i+j+1) is not
+        # diagonally dominant, so only the per-operator outputs are frozen, not a solve
+        coo = band_coo(1500, 8)
+        make("band8_1500", None, RefOptions(), coo, rng.uniform(-1, 1, coo[0]), with_pcg=False)

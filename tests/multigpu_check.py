@@ -78,6 +78,10 @@ def main():
         if use_p2p:
             setup_p2p_halo(ctx)
             ctx.p2p_enable(2 if transport == "fused" else 1)
+            if case_no == 5:
+                # per operator: whichever of the two peer-memory paths measures faster (a mix of both)
+                ctx.autotune_halo(3)
+                transport = "fused/autotuned"
         o = Oracle(hs)
         rng = np.random.default_rng(17)
         tag = (f"{name}/agg{agg}/{'aligned' if align else 'misaligned'}{'+rebalanced' if reb else ''}/{'f64' if dbl else 'f32'}-halo/"
@@ -105,7 +109,7 @@ def main():
                 want = o.matvec(l, KIND_R, v_parts)
                 got = ctx.matvec(l, KIND_R, v_parts[rank])
                 worst[f"{tag}.L{l}.R"] = rel(np.concatenate(gather(got, csz, rank, world)), np.concatenate(want))
-            if transport == "fused" and l <= 1:
+            if transport.startswith("fused") and l <= 1:
                 # every row mapping of the fused kernel (sliced, sub-warp, row-group), A and P; then the
                 # measurement modes (compute only / exchange only) must leave the hand-shake consistent
                 want_a = np.concatenate(o.matvec(l, KIND_A, v_parts))

@@ -9,7 +9,7 @@ import pytest
 from oracle.oracle import Oracle
 from saena_b200.hierarchy import KIND_A, KIND_P, KIND_R, Hierarchy, Level, Operator
 from saena_b200.native import Context
-from tests.util import (GOLDEN, TOL_HIST, TOL_OP, Golden, check_ops_against_golden, check_pcg,
+from tests.util import (GOLDEN, GOLDEN_EXTRA, TOL_HIST, TOL_OP, Golden, check_ops_against_golden, check_pcg,
                         check_vcycle_against_golden, rel)
 
 pytestmark = pytest.mark.gpu
@@ -43,6 +43,27 @@ def test_pcg_matches_reference_golden(golden_ctx):
     A = g.hier.levels[0].A.to_scipy_local()
     assert np.linalg.norm(A @ u - g.rhs) / np.linalg.norm(g.rhs) < g.tol
     assert ctx.launch_count() > 0
+
+
+@pytest.mark.parametrize("name", GOLDEN_EXTRA)
+def test_other_matrix_shapes_match_reference_golden(name):
+    """irregular rows (Helmholtz2D, configs[4]'s shape), a system PCG does not converge on (homg: the
+    whole 50-iteration history must still match), the band pattern of configs[3] (operators only)"""
+    g = Golden(name)
+    ctx = Context()
+    try:
+        ctx.upload_hierarchy(g.hier)
+        check_ops_against_golden(ctx, g)
+        check_vcycle_against_golden(ctx, g)
+        for mp in (1, 8, 64, -4, 100, 0):   # and through the other row mappings
+            for l, lv in enumerate(g.hier.levels):
+                ctx.set_mapping(l, KIND_A, mp)
+                assert rel(ctx.matvec(l, KIND_A, g[f"in.L{l}.v"]), g[f"out.L{l}.A_matvec"]) <= TOL_OP, (name, mp, l)
+        if g.has_pcg:
+            u, iters, hist = ctx.solve_pcg(g.rhs, g.max_iter, g.tol, "chebyshev", g.pre, g.post)
+            check_pcg(iters, hist, u, int(g["out.pcg.iters"][0]), g["out.pcg.hist"], g["out.pcg.u"])
+    finally:
+        ctx.close()
 
 
 def test_every_kernel_mapping_gives_the_same_answer(golden_ctx):

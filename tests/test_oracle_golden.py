@@ -4,33 +4,36 @@ import numpy as np
 import pytest
 
 from oracle.oracle import Oracle
-from tests.util import GOLDEN, Golden, check_ops_against_golden, check_pcg, check_vcycle_against_golden
+from tests.util import GOLDEN, GOLDEN_ALL, Golden, check_ops_against_golden, check_pcg, check_vcycle_against_golden
 
 
 class OracleImpl(Oracle):
     pass
 
 
-@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("name", GOLDEN_ALL)
 def test_oracle_ops_match_reference_golden(name):
     g = Golden(name)
     check_ops_against_golden(Oracle(g.hier), g)
 
 
-@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("name", GOLDEN_ALL)
 def test_oracle_vcycle_matches_reference_golden(name):
     g = Golden(name)
     check_vcycle_against_golden(Oracle(g.hier), g)
 
 
-@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("name", [n for n in GOLDEN_ALL if Golden(n).has_pcg])
 def test_oracle_pcg_matches_reference_golden(name):
     g = Golden(name)
     u, iters, hist = Oracle(g.hier).solve_pcg(g.rhs, g.max_iter, g.tol, "chebyshev", g.pre, g.post)
     check_pcg(iters, hist, u, int(g["out.pcg.iters"][0]), g["out.pcg.hist"], g["out.pcg.u"])
-    # the solve did what it says: ||A u - rhs|| / ||rhs|| below tol
-    A = g.hier.levels[0].A.to_scipy_local()
-    assert np.linalg.norm(A @ u - g.rhs) / np.linalg.norm(g.rhs) < g.tol
+    if hist[-1] < hist[0] * g.tol:
+        # the solve did what it says: ||A u - rhs|| / ||rhs|| below tol
+        A = g.hier.levels[0].A.to_scipy_local()
+        assert np.linalg.norm(A @ u - g.rhs) / np.linalg.norm(g.rhs) < g.tol
+    else:
+        assert iters == g.max_iter   # homg33: the reference runs out of iterations too
 
 
 def test_oracle_stationary_vcycle_converges():

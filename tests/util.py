@@ -14,6 +14,13 @@ from saena_b200.hierarchy import hierarchy_from_arrays
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN = ["poisson9_cheb", "poisson12_cheb"]
+# other matrix shapes frozen from the reference (tests/golden/make_golden.py): the irregular-row
+# Helmholtz matrix BASELINE.json configs[4] takes its shape from (data/Helmholtz2D_CG_curved_tri),
+# data/homg/A.mtx with its own rhs (PCG does not converge on it in the reference either: the whole
+# 50-iteration history is the fixture), and the band pattern of configs[3] (experiments/banded.cpp;
+# per-operator outputs only, 1/(i+j+1) is not a system one solves)
+GOLDEN_EXTRA = ["helmholtz2d_p8", "homg33", "band8_1500"]
+GOLDEN_ALL = GOLDEN + GOLDEN_EXTRA
 
 # tolerances of BASELINE.json's north_star
 TOL_OP = 1e-12       # each SpMV, smoother sweep and transfer: relative error in the 2-norm
@@ -38,6 +45,10 @@ class Golden:
 
     def __getitem__(self, k):
         return self.d[k]
+
+    @property
+    def has_pcg(self):
+        return "out.pcg.hist" in self.d.files
 
 
 def check_ops_against_golden(impl, g: Golden, tol=TOL_OP):
