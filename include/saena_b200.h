@@ -85,6 +85,16 @@ typedef struct saena_b200_operator_desc {
 
 int saena_b200_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *desc);
 
+/* Measurement input (one rank): the A operator of `level` generated on the device with the pattern
+ * and values of saena::band_matrix (src/aux_functions2.cpp:1296-1381, experiments/banded.cpp) --
+ * row i = columns [i-b, i+b] inside [0, n), value 1/(i+j+1).  BASELINE.json configs[3] is 50 M
+ * rows x 129 entries = 77 GB with 64-bit row offsets, more than a host upload can feed a bench run;
+ * the arrays are the ones saena_b200_upload_operator would build from the same matrix.
+ * sliced_only != 0: once finalize has built the sliced (32-row slice, column-major) copy the CSR
+ * entries are released -- CSR + sliced copy of the full-size case would be 156 GB -- and the
+ * operator keeps that one mapping. */
+int saena_b200_upload_band_operator(saena_b200_ctx *ctx, int level, int n, int half_bandwidth, int sliced_only);
+
 /* (peer, offset, count) of Grid::repart_u's plan (src/grid.cpp:3-163): offset is into the
  * old-partition vector for sends and into the new-partition vector for receives. */
 typedef struct saena_b200_block {
@@ -204,6 +214,9 @@ int64_t saena_b200_launch_count(const saena_b200_ctx *ctx);
  * per thread group; -1..-32 = streaming row blocks with that many lanes per row in the reduce
  * phase; 100 = sliced layout (32-row slices, column-major, one lane per row). */
 int saena_b200_set_mapping(saena_b200_ctx *ctx, int level, int kind, int mapping);
+/* The same, taking effect at the next saena_b200_finalize (no layout is built for the mapping that
+ * is being replaced: matters for an operator that fills half the HBM). */
+int saena_b200_set_mapping_deferred(saena_b200_ctx *ctx, int level, int kind, int mapping);
 /* the mapping in use (same codes) */
 int saena_b200_get_mapping(const saena_b200_ctx *ctx, int level, int kind);
 /* algorithmic bytes of one application of an operator (SURVEY.md 8d formula), for the roofline */

@@ -106,6 +106,12 @@ int saena_b200_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_de
     return sb_upload_operator(ctx, desc);
 }
 
+int saena_b200_upload_band_operator(saena_b200_ctx *ctx, int level, int n, int half_bandwidth, int sliced_only) {
+    if (!ctx) return 1;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    return sb_upload_band_operator(ctx, level, n, half_bandwidth, sliced_only);
+}
+
 int saena_b200_upload_level_aux(saena_b200_ctx *ctx, int level, const double *inv_diag, double eig_max,
                                 int M_coarse_old, int M_coarse, int n_send, const saena_b200_block *send,
                                 int n_recv, const saena_b200_block *recv) {
@@ -734,9 +740,22 @@ int saena_b200_set_mapping(saena_b200_ctx *ctx, int level, int kind, int mapping
     SB_CUDA(cudaSetDevice(ctx->device));
     DevOperator *op = get_op(ctx, level, kind);
     if (!op) SB_FAIL("set_mapping: no such operator");
+    if (op->sell_only && mapping != 0 && mapping != SB_MAPPING_SELL)
+        SB_FAIL("set_mapping: this operator kept only its sliced copy");
     op->forced_mapping = mapping;
     sb_invalidate_graphs(ctx);
     return sb_prepare_operator(ctx, *op);
+}
+
+// records the mapping only; the next finalize prepares the operator with it (no layout is built
+// for a mapping that is about to be replaced -- matters when the operator fills half the HBM)
+int saena_b200_set_mapping_deferred(saena_b200_ctx *ctx, int level, int kind, int mapping) {
+    if (!ctx) return 1;
+    DevOperator *op = get_op(ctx, level, kind);
+    if (!op) SB_FAIL("set_mapping_deferred: no such operator");
+    op->forced_mapping = mapping;
+    ctx->finalized = false;
+    return 0;
 }
 
 int saena_b200_set_coarsest_solver(saena_b200_ctx *ctx, int use_cg) {

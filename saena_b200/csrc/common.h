@@ -120,6 +120,7 @@ struct DevOperator {
     double *sell_val = nullptr;
     int64_t sell_padded = 0;        // stored entries incl. padding
     int64_t sell_padded_est = 0;    // what the padding would be (computed at upload)
+    bool sell_only = false;         // the CSR col/val were released once the sliced copy existed (no other mapping)
 
     // remote block re-sorted by row at upload: boundary rows only
     // interior rows = the contiguous range [int_lo, int_hi) (multiples of 32) that holds no row with
@@ -276,6 +277,7 @@ static const int RED_MAX_BLOCKS = 1184;   // 148 SMs x 8
 
 // ---- operator.cu
 int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d);
+int sb_upload_band_operator(saena_b200_ctx *ctx, int level, int n, int half_bandwidth, int sliced_only);
 void sb_free_operator(DevOperator &op);
 void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op);
 int sb_prepare_operator(saena_b200_ctx *ctx, DevOperator &op);

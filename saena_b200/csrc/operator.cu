@@ -243,6 +243,82 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Band operator generated on the device (measurement input, one rank): the pattern and values of
+// saena::band_matrix (/root/reference/src/aux_functions2.cpp:1296-1381; experiments/banded.cpp,
+// BASELINE.json configs[3]) -- row i holds columns [i-b, i+b] inside [0, n), value 1/(i+j+1).
+// 50 M rows x 129 entries are 77 GB: they cannot come through a host upload in a bench run, and
+// need 64-bit row offsets.  Same CSR arrays as sb_upload_operator produces from host data
+// (tests/test_gpu_parity.py compares the two bit for bit at small n).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ static inline long long band_row_start(long long i, long long n, long long b) {
+    // entries in rows < i: i full rows minus what the two matrix edges clip
+    const long long m = i < b ? i : b;                             // rows clipped on the left
+    const long long k = i > n - b ? i - (n - b) : 0;               // rows clipped on the right
+    return i * (2 * b + 1) - (m * b - m * (m - 1) / 2) - k * (k + 1) / 2;
+}
+
+template <typename OffT>
+__global__ void band_fill_kernel(long long n, long long b, OffT *__restrict__ rowptr, int *__restrict__ col,
+                                 double *__restrict__ val) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp; i < n; i += nwarps) {
+        const long long start = band_row_start(i, n, b);
+        const long long j0 = i - b < 0 ? 0 : i - b, j1 = i + b > n - 1 ? n - 1 : i + b;
+        if (lane == 0) {
+            rowptr[i] = (OffT)start;
+            if (i == n - 1) rowptr[n] = (OffT)(start + (j1 - j0 + 1));
+        }
+        for (long long j = j0 + lane; j <= j1; j += 32) {
+            col[start + (j - j0)] = (int)j;
+            val[start + (j - j0)] = 1.0 / (double)(i + j + 1);
+        }
+    }
+}
+
+int sb_upload_band_operator(saena_b200_ctx *ctx, int level, int n, int half_bandwidth, int sliced_only) {
+    if (ctx->nranks != 1) SB_FAIL("upload_band_operator: one rank only (a measurement input)");
+    if (level < 0 || level > 64 || n < 1 || half_bandwidth < 0 || half_bandwidth >= n)
+        SB_FAIL("upload_band_operator: need 0 <= half_bandwidth < n");
+    if ((int)ctx->levels.size() <= level) ctx->levels.resize(level + 1);
+    DevLevel &lv = ctx->levels[level];
+    DevOperator &op = lv.A;
+    if (ctx->arena) sb_arena_free(ctx);
+    if (op.present) sb_free_operator(op);
+    const long long nn = n, b = half_bandwidth;
+    const long long nnz = band_row_start(nn, nn, b);
+    op.present = true;
+    op.kind = SAENA_B200_KIND_A;
+    op.level = level;
+    op.M = n;
+    op.int_lo = 0;
+    op.int_hi = n;
+    op.n_local_cols = n;
+    op.col_offset = 0;
+    op.nnz_local = nnz;
+    op.nnz_remote = 0;
+    op.use_double = true;
+    op.wide_offsets = nnz >= (int64_t)INT32_MAX;
+    // slices of 32 consecutive rows differ in length only at the two matrix edges
+    op.sell_padded_est = nnz + 32 * 2 * b;
+    op.sell_only = sliced_only != 0;
+    lv.M = n;
+    SB_CUDA(cudaMalloc(&op.rowptr, (op.wide_offsets ? sizeof(int64_t) : sizeof(int)) * ((size_t)n + 1)));
+    SB_CUDA(cudaMalloc((void **)&op.col, sizeof(int) * (size_t)nnz));
+    SB_CUDA(cudaMalloc((void **)&op.val, sizeof(double) * (size_t)nnz));
+    const int blocks = 8 * ctx->sm_count;
+    if (op.wide_offsets)
+        band_fill_kernel<int64_t><<<blocks, 256, 0, ctx->stream>>>(nn, b, (int64_t *)op.rowptr, op.col, op.val);
+    else
+        band_fill_kernel<int><<<blocks, 256, 0, ctx->stream>>>(nn, b, (int *)op.rowptr, op.col, op.val);
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->finalized = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // mapping heuristic: lanes per row from nnz/row; short rows stream.  (north_star: "warp-per-row
 // or row-block mapping chosen per level by nnz/row".)  Measured crossovers are in DESIGN.md.
 // ---------------------------------------------------------------------------------------------
@@ -254,7 +330,7 @@ static int pow2_at_most(double v) {
 
 void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op) {
     const double avg = op.M ? double(op.nnz_local) / op.M : 0.0;
-    int m = op.forced_mapping;
+    int m = op.sell_only ? SB_MAPPING_SELL : op.forced_mapping;
     if (m == 0) {
         // short and regular rows: sliced layout (padding <= 15 %); otherwise a sub-warp per row
         // with ~4+ elements per lane.  Crossovers measured on B200, see DESIGN.md.
@@ -384,6 +460,13 @@ static int build_sell(saena_b200_ctx *ctx, DevOperator &op) {
     }
     SB_CUDA(cudaGetLastError());
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (op.sell_only) {
+        // the sliced copy is the operator from here on: give the CSR entries back (half the footprint)
+        cudaFree(op.col);
+        cudaFree(op.val);
+        op.col = nullptr;
+        op.val = nullptr;
+    }
     return 0;
 }
 

@@ -60,6 +60,7 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_init.argtypes = [ctypes.POINTER(vp), i, i, i, vp]
     L.saena_b200_destroy.argtypes = [vp]
     L.saena_b200_upload_operator.argtypes = [vp, ctypes.POINTER(OperatorDesc)]
+    L.saena_b200_upload_band_operator.argtypes = [vp, i, i, i, i]
     L.saena_b200_upload_level_aux.argtypes = [vp, i, dp, d, i, i, i, ctypes.POINTER(Block), i, ctypes.POINTER(Block)]
     L.saena_b200_upload_level_scale.argtypes = [vp, i, dp]
     L.saena_b200_upload_coarsest.argtypes = [vp, i, ctypes.c_int64, c_i32_p, c_i32_p, dp]
@@ -93,6 +94,7 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_graph_replays.restype = ctypes.c_int64
     L.saena_b200_graph_replays.argtypes = [vp]
     L.saena_b200_set_mapping.argtypes = [vp, i, i, i]
+    L.saena_b200_set_mapping_deferred.argtypes = [vp, i, i, i]
     L.saena_b200_get_mapping.argtypes = [vp, i, i]
     L.saena_b200_operator_bytes.restype = ctypes.c_int64
     L.saena_b200_operator_bytes.argtypes = [vp, i, i]
@@ -102,13 +104,13 @@ def load_library(path: Optional[str] = None):
 
 EXPORTED_SYMBOLS = [
     "saena_b200_nccl_unique_id", "saena_b200_init", "saena_b200_destroy", "saena_b200_last_error",
-    "saena_b200_upload_operator", "saena_b200_upload_level_aux", "saena_b200_upload_level_scale",
+    "saena_b200_upload_operator", "saena_b200_upload_band_operator", "saena_b200_upload_level_aux", "saena_b200_upload_level_scale",
     "saena_b200_upload_coarsest",
     "saena_b200_set_coarsest_solver", "saena_b200_set_graphs", "saena_b200_finalize",
     "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_p2p_enable", "saena_b200_autotune_halo", "saena_b200_halo_choice", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
-    "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_time_vcycle", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_graph_replays", "saena_b200_set_mapping", "saena_b200_get_mapping",
+    "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_time_vcycle", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_graph_replays", "saena_b200_set_mapping", "saena_b200_set_mapping_deferred", "saena_b200_get_mapping",
     "saena_b200_operator_bytes",
 ]
 
@@ -221,6 +223,29 @@ class Context:
         self._ck(self._L.saena_b200_finalize(self._h))
         self.hier = h
         self.level_rows = [lv.A.M for lv in h.levels]
+
+    def upload_band(self, n: int, half_bandwidth: int, eig_max: float = 2.0, mapping: int = 0, sliced_only: bool = False):
+        """A lone level-0 operator generated on the device with saena::band_matrix's pattern and values
+        (BASELINE.json configs[3]); matvec / residual / smooth hooks only.  inv_diag = 1/diag = 2i+1."""
+        from .hierarchy import KIND_A, Level
+        self._ck(self._L.saena_b200_upload_band_operator(self._h, 0, int(n), int(half_bandwidth), int(sliced_only)))
+        inv = 2.0 * np.arange(n, dtype=F64) + 1.0
+        none = (Block * 1)()
+        self._ck(self._L.saena_b200_upload_level_aux(self._h, 0, _f64p(inv), float(eig_max), 0, 0, 0, none, 0, none))
+        if mapping:
+            # forced before finalize so that no sliced copy is built first (77 GB at the full size)
+            self._ck(self._L.saena_b200_set_mapping_deferred(self._h, 0, KIND_A, int(mapping)))
+        self._ck(self._L.saena_b200_upload_coarsest(self._h, 0, 0, None, None, None))
+        self._ck(self._L.saena_b200_finalize(self._h))
+        b = int(half_bandwidth)
+        i = np.arange(n, dtype=np.int64)
+        counts = (np.minimum(i + b, n - 1) - np.maximum(i - b, 0) + 1)
+        op = Operator(kind=KIND_A, level=0, M=n, Mbig=n, Nbig=n, row_offset=0, col_offset=0, n_local_cols=n,
+                      nnzPerRow_local=np.zeros(0, I32), col_local=np.zeros(0, I32), val_local=np.zeros(0, F64))
+        self.hier = Hierarchy([Level(0, op, inv_diag=inv, eig_max=eig_max)], coarse_n=0, coarse_row=np.zeros(0, I32),
+                              coarse_col=np.zeros(0, I32), coarse_val=np.zeros(0, F64))
+        self.level_rows = [n]
+        return int(counts.sum())
 
     def set_coarsest_solver(self, name: str):
         """'SuperLU' (default: direct solve) or 'CG' -- saena_object::direct_solver"""
