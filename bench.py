@@ -160,6 +160,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("SAENA_BENCH_N", 256)),
                     help="unknowns per dimension (256 = BASELINE.json configs[1])")
+    ap.add_argument("--workload", default="poisson3d", choices=["poisson3d", "unstructured2d"],
+                    help="poisson3d = BASELINE.json configs[1] (the bench line); unstructured2d = configs[4]'s synthetic "
+                         "2-D Helmholtz-like matrix with irregular rows (same solve, same JSON keys, its own metric name)")
+    ap.add_argument("--g", type=int, default=2828, help="unstructured2d: g*g nodes (2828^2 = 8.0 M rows)")
+    ap.add_argument("--row-lengths", default="6,8,10", help="unstructured2d: entries per row drawn from these "
+                                                            "(donor P2: 6,8,10; P8: 24,32,40)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--agglomerate-below", type=int, default=10_000,
                     help="N>1: levels with fewer global rows live on rank 0 (the reference's shrink-to-one-rank)")
@@ -182,7 +188,8 @@ def main():
     from saena_b200 import native
     from saena_b200.distributed import exchange_nccl_id, setup_p2p_halo
     from saena_b200.hierarchy import KIND_A, KIND_P, KIND_R
-    from saena_b200.sa_setup import build_device_hierarchy, poisson3d_coo, poisson3d_rhs
+    from saena_b200.sa_setup import (build_device_hierarchy, poisson3d_coo, poisson3d_rhs, unstructured2d_coo,
+                                     unstructured2d_rhs)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the solve path has no CPU fallback")
@@ -195,7 +202,12 @@ def main():
     # ---- setup (untimed): hierarchy of the reference's shape, built on this rank's GPU
     n = args.n
     t0 = time.perf_counter()
-    N, row, col, val = poisson3d_coo(n)
+    if args.workload == "poisson3d":
+        N, row, col, val = poisson3d_coo(n)
+    else:
+        lengths = tuple(int(x) for x in args.row_lengths.split(","))
+        weights = (16, 48, 20) if len(lengths) == 3 else (1,) * len(lengths)   # the donors' 16:48:20 proportions
+        N, row, col, val = unstructured2d_coo(args.g, row_lengths=lengths, weights=weights)
     dh = build_device_hierarchy(N, row, col, val, verbose=(rank == 0 and bool(os.environ.get("SAENA_BENCH_VERBOSE"))))
     del row, col, val
     if rank == 0:
@@ -226,7 +238,7 @@ def main():
     if rank == 0:
         log(f"[setup] uploaded in {time.perf_counter() - t0:.1f}s total")
     l0 = hier.levels[0].A
-    rhs_full = poisson3d_rhs(n)
+    rhs_full = poisson3d_rhs(n) if args.workload == "poisson3d" else unstructured2d_rhs(N)
     rhs_host = torch.from_numpy(rhs_full[l0.row_offset:l0.row_offset + l0.M].copy()).pin_memory()
     del rhs_full
     u_host = torch.empty(l0.M, dtype=torch.float64).pin_memory()
@@ -338,7 +350,7 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
     if os.path.exists(tp) and world == 1:
-        traffic = json.load(open(tp)).get(f"n{n}_level{dl}_cheb_sweep")
+        traffic = json.load(open(tp)).get(f"n{n}_level{dl}_cheb_sweep") if args.workload == "poisson3d" else None
     roofline = {"bound": "hbm", "achieved": dbytes / dms / 1e6, "peak": peak, "unit": "GB/s",
                 "frac": dbytes / dms / 1e6 / peak, "traffic": traffic,
                 "kernel": f"fused Chebyshev sweep (SpMV + update epilogue) on level {dl}", "peak_source": peak_src,
@@ -377,12 +389,19 @@ def main():
                 "ghost_values_per_rank": int(hier.levels[0].A.col_remote_size),
                 "ghost_dtype": "f64" if hier.levels[0].A.use_double else "f32 (float_level 0)"}
 
-    total_unknowns = n ** 3
-    line = {"metric": METRIC, "value": total_unknowns / (ms_step / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
+    total_unknowns = int(N)
+    if args.workload == "poisson3d":
+        metric = METRIC
+        workload = (f"3D 7-point Poisson {n}^3 = {total_unknowns} unknowns, AMG-PCG to 1e-8 "
+                    f"(BASELINE.json configs[1] at n=256)")
+    else:
+        metric = "AMG-PCG solve throughput, synthetic 2D Helmholtz-like unstructured matrix, rel. residual 1e-8 (unknowns solved per second)"
+        workload = (f"synthetic 2D Helmholtz-like matrix, unstructured-mesh pattern, {args.g}^2 = {total_unknowns} rows, "
+                    f"row lengths drawn from {args.row_lengths} (BASELINE.json configs[4] shape, seed 2024), AMG-PCG to 1e-8")
+    line = {"metric": metric, "value": total_unknowns / (ms_step / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D 7-point Poisson {n}^3 = {total_unknowns} unknowns, AMG-PCG to 1e-8 "
-                                   f"(BASELINE.json configs[1] at n=256)",
+            "config": {"workload": workload,
                        "options": "options006_poisson.xml: chebyshev 3+3, conn_str 0.2, float_level 0, max_iter 50",
                        "levels": len(hier.levels), "partition": f"{world} row block(s), nnz-balanced" + (
                            f"; coarse levels follow the level above, re-split when a rank exceeds "
@@ -400,7 +419,7 @@ def main():
             "levels": levels_tbl}
     if halo is not None:
         line["halo_overlap"] = halo
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "poisson3d":
         try:
             line["cpu_baseline"], _, cpu_iters, _ = cpu_reference_solve(5)
             line["cpu_baseline"]["iterations"] = cpu_iters

@@ -346,6 +346,13 @@ void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op) {
             // ~4+ elements per lane; rows of hundreds..thousands of entries get 32..256 threads
             m = 1;
             while (m * 2 <= (avg + 1.0) / 4.0 && m < 256) m *= 2;
+            // few rows: the sub-warp mapping walks its 32 rows in `lanes` dependent steps (2 rows at a
+            // time at 16 lanes), and with fewer than ~32 warps per SM nothing hides that chain --
+            // measured on the unstructured 2-D hierarchy (profiles/r01_unstructured.md): levels of
+            // 715 .. 78 839 rows x ~100 entries all took 57 us per application at 16 lanes/row,
+            // 10-18 us with a warp per row, which has no such chain.  (Same row count below which
+            // the sliced layout is not chosen: one lane per row cannot fill the chip either.)
+            if (m < 32 && op.M <= 32 * 32 * ctx->sm_count) m = 32;
         }
     }
     op.use_stream = op.use_sell = false;

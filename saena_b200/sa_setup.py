@@ -553,3 +553,55 @@ def poisson3d_rhs(n: int) -> np.ndarray:
     t = np.arange(1, mx - 1, dtype=np.float64) / (mx - 1)
     s = np.sin(2 * math.pi * t)
     return (12 * math.pi ** 2 * s[None, None, :] * s[None, :, None] * s[:, None, None]).ravel()
+
+
+# forward half of a 2-D neighbourhood ordered by distance: node (x, y) couples to (x+dx, y+dy); the
+# mirrored entries make the pattern symmetric
+_HALF_OFFSETS = [(1, 0), (0, 1), (1, 1), (-1, 1), (2, 0), (0, 2), (2, 1), (1, 2), (-1, 2), (-2, 1), (2, 2), (-2, 2),
+                 (3, 0), (0, 3), (3, 1), (1, 3), (-1, 3), (-3, 1), (3, 2), (2, 3), (-2, 3), (-3, 2), (4, 0), (0, 4)]
+
+
+def unstructured2d_coo(g: int, seed: int = 2024, row_lengths=(6, 8, 10), weights=(16, 48, 20), tile: int = 16,
+                       shift: float = 0.05):
+    """Synthetic 2-D Helmholtz-like matrix with an unstructured-mesh pattern (BASELINE.json configs[4],
+    SURVEY.md 8d): g*g nodes; the number of entries per row is drawn from the empirical distribution of
+    the shape donors data/Helmholtz2D_CG_curved_tri/*.mtx (P2: 6/8/10 entries in proportion 16:48:20;
+    pass row_lengths=(24, 32, 40) for the P8 shape); every node couples to its nearest neighbours until
+    its drawn length is reached, the pattern is then symmetrised; nodes are numbered tile by tile
+    with a random order inside each `tile` x `tile` patch (mesh-generator-like locality, irregular
+    gathers); off-diagonals -(0.5 + u), u uniform, symmetric; diagonal = sum |off-diagonal| * (1 + shift):
+    SPD, the positive shift being the Helmholtz term.  Returns (n, row, col, val) with duplicates-free COO."""
+    rng = np.random.default_rng(seed)
+    n = g * g
+    x, y = np.meshgrid(np.arange(g), np.arange(g), indexing="xy")
+    x, y = x.ravel(), y.ravel()
+    # numbering: tiles in row-major order, random order inside a tile
+    tx, ty = x // tile, y // tile
+    key = (ty * ((g + tile - 1) // tile) + tx).astype(np.int64) * (tile * tile * 4) + rng.permutation(n) % (tile * tile * 4)
+    order = np.argsort(key, kind="stable")
+    number = np.empty(n, np.int64)
+    number[order] = np.arange(n)
+    # forward edges until the drawn row length is reached (half of the off-diagonal count each way)
+    want = rng.choice(np.asarray(row_lengths), size=n, p=np.asarray(weights, float) / np.sum(weights))
+    half = (want - 1 + 1) // 2
+    src, dst = [], []
+    for k, (dx, dy) in enumerate(_HALF_OFFSETS[:int(half.max())]):
+        ok = (half > k) & (x + dx >= 0) & (x + dx < g) & (y + dy < g)
+        src.append(np.flatnonzero(ok))
+        dst.append(src[-1] + dx + dy * g)
+    src, dst = np.concatenate(src), np.concatenate(dst)
+    w = -(0.5 + rng.uniform(0, 1, len(src)))
+    i, j = number[src], number[dst]
+    diag = np.zeros(n)
+    np.add.at(diag, i, -w)
+    np.add.at(diag, j, -w)
+    diag *= 1.0 + shift
+    diag[diag == 0] = 1.0
+    row = np.concatenate((i, j, np.arange(n)))
+    col = np.concatenate((j, i, np.arange(n)))
+    val = np.concatenate((w, w, diag))
+    return n, row, col, val
+
+
+def unstructured2d_rhs(n: int, seed: int = 2024) -> np.ndarray:
+    return np.random.default_rng(seed + 1).uniform(-1, 1, n)

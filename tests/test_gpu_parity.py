@@ -66,6 +66,36 @@ def test_other_matrix_shapes_match_reference_golden(name):
         ctx.close()
 
 
+@pytest.mark.parametrize("g,lengths,weights", [(160, (6, 8, 10), (16, 48, 20)), (72, (24, 32, 40), (64, 192, 80))])
+def test_unstructured_helmholtz_like_shape_matches_oracle(g, lengths, weights):
+    """BASELINE.json configs[4]'s synthetic shape at a size the oracle finishes in seconds: irregular
+    rows, mesh-like numbering; every operator, V-cycle and the PCG history against the CPU oracle"""
+    from saena_b200.sa_setup import build_hierarchy, unstructured2d_coo, unstructured2d_rhs
+    n, row, col, val = unstructured2d_coo(g, row_lengths=lengths, weights=weights)
+    rhs = unstructured2d_rhs(n)
+    h = build_hierarchy(n, row, col, val, device="cpu")
+    o = Oracle(h)
+    ctx = Context()
+    rng = np.random.default_rng(11)
+    try:
+        ctx.upload_hierarchy(h)
+        for l, lv in enumerate(h.levels):
+            v, b = rng.uniform(-1, 1, lv.A.M), rng.uniform(-1, 1, lv.A.M)
+            assert rel(ctx.matvec(l, KIND_A, v), o.matvec(l, KIND_A, v)) <= TOL_OP
+            assert rel(ctx.smooth(l, "chebyshev", 3, v, b), o.smooth(l, "chebyshev", 3, v, b)) <= TOL_OP
+            assert rel(ctx.smooth(l, "jacobi", 2, v, b), o.smooth(l, "jacobi", 2, v, b)) <= TOL_OP
+            if lv.P is not None:
+                vc = rng.uniform(-1, 1, lv.P.n_local_cols)
+                assert rel(ctx.matvec(l, KIND_P, vc), o.matvec(l, KIND_P, vc)) <= TOL_OP
+                assert rel(ctx.matvec(l, KIND_R, v), o.matvec(l, KIND_R, v)) <= TOL_OP
+            assert rel(ctx.vcycle(l, np.zeros(lv.A.M), b), o.vcycle(l, np.zeros(lv.A.M), b)) <= 1e-11
+        u, iters, hist = ctx.solve_pcg(rhs, 50, 1e-8, "chebyshev", 3, 3)
+        u_o, it_o, h_o = o.solve_pcg(rhs, 50, 1e-8, "chebyshev", 3, 3)
+        check_pcg(iters, hist, u, it_o, h_o, u_o)
+    finally:
+        ctx.close()
+
+
 def _band_rows(n, b, v, rows):
     """(A v)_i of the band matrix for a few rows, summed in column order like the kernels' CSR order"""
     out = []

@@ -111,3 +111,17 @@ def test_world_size_2_gloo_host_path():
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "HALO_OK" in out.stdout
+
+
+def test_partitioned_unstructured_shape_equals_one_rank():
+    """configs[4]'s shape over 3 ranks (re-split coarse levels): the multi-rank oracle, halo kept in
+    double, reproduces the one-rank solve; irregular rows give every rank several neighbours"""
+    from saena_b200.sa_setup import build_hierarchy, unstructured2d_coo, unstructured2d_rhs
+    n, row, col, val = unstructured2d_coo(48)
+    rhs = unstructured2d_rhs(n)
+    h = _force_double(build_hierarchy(n, row, col, val, device="cpu"))
+    u1, it1, h1 = Oracle(h).solve_pcg(rhs)
+    hs = partition_hierarchy(h, 3, agglomerate_below=100, rebalance_above=1.05)
+    un, itn, hn = Oracle(hs).solve_pcg(_parts(hs, rhs))
+    assert itn == it1 and np.max(np.abs(hn - h1) / h1) < 1e-9
+    assert rel(np.concatenate(un), u1) < 1e-9

@@ -7,7 +7,7 @@ import pytest
 from oracle.oracle import Oracle
 from saena_b200.hierarchy import partition_hierarchy
 from saena_b200.sa_setup import (SetupOptions, build_device_hierarchy, build_hierarchy, poisson3d_coo,
-                                 poisson3d_rhs)
+                                 poisson3d_rhs, unstructured2d_coo, unstructured2d_rhs)
 from tests.util import GOLDEN, Golden, rel
 
 
@@ -55,6 +55,45 @@ def test_setup_reproduces_the_live_reference_at_32_cubed():
         assert abs(it - it_ref) <= 1 and rel(u, u_ref) < 1e-6
     finally:
         s.close()
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("g,lengths,weights", [(30, (6, 8, 10), (16, 48, 20)), (24, (24, 32, 40), (64, 192, 80))])
+def test_setup_reproduces_the_live_reference_on_the_unstructured_shape(g, lengths, weights):
+    """BASELINE.json configs[4]'s synthetic shape (irregular rows, mesh-like numbering): the reference's
+    own setup (from the same COO) and the restatement give the same hierarchy"""
+    from oracle import ref
+    n, row, col, val = unstructured2d_coo(g, row_lengths=lengths, weights=weights)
+    rhs = unstructured2d_rhs(n)
+    s = ref.RefSolver.from_coo(n, row, col, val, rhs)
+    try:
+        href = s.hierarchy()
+        h = build_hierarchy(n, row, col, val, device="cpu")
+        assert len(h.levels) == len(href.levels)
+        for a, b in zip(h.levels, href.levels):
+            _same_operator(a.A, b.A)
+            if b.P is not None:
+                _same_operator(a.P, b.P)
+                _same_operator(a.R, b.R)
+        u, it, hist = Oracle(h).solve_pcg(rhs)
+        u_ref, it_ref, hist_ref = s.solve_pcg()
+        assert abs(it - it_ref) <= 1 and rel(u, u_ref) < 1e-6
+    finally:
+        s.close()
+
+
+def test_unstructured_shape_has_the_donor_row_lengths():
+    import scipy.sparse as sp
+    n, row, col, val = unstructured2d_coo(64)
+    A = sp.coo_matrix((val, (row, col)), shape=(n, n)).tocsr()
+    assert A.nnz == len(val)                       # duplicate-free COO
+    assert abs(A - A.T).max() == 0                 # symmetric
+    cnt = np.diff(A.indptr)
+    assert 4 <= cnt.min() and cnt.max() <= 12 and 7.5 < cnt.mean() < 9.5   # donor P2: 6 / 8.1 / 10
+    assert np.all(A.diagonal() > np.abs(A - sp.diags(A.diagonal())).sum(axis=1).A1)   # SPD by dominance
+    # mesh-like numbering: neighbours are near in index space for most entries, not all
+    d = np.abs(row - col)
+    assert np.median(d[d > 0]) < 16 * 16 * 2 and d.max() > 64
 
 
 @pytest.mark.parametrize("nprocs,agg,reb", [(1, 0, 0.0), (2, 0, 0.0), (3, 200, 0.0), (4, 10**9, 0.0), (3, 0, 1.01),
