@@ -160,6 +160,17 @@ int saena_b200_p2p_enable(saena_b200_ctx *ctx, int on);
 int saena_b200_autotune_halo(saena_b200_ctx *ctx, int reps);
 int saena_b200_halo_choice(const saena_b200_ctx *ctx, int level, int kind, float *ms_fused, float *ms_unfused);
 
+/* ---- next to the solve path: the Chebyshev bound on the device ---------------
+ * saena_object::find_eig (src/saena_object.cpp:572-590 -> include/lamlan_saena.h:13-79): largest
+ * eigenvalue of D^-1/2 A D^-1/2 by Lanczos (<= max_iter steps, 20 in the reference, full
+ * re-orthogonalisation, stop at a 1e-8 relative change of the Ritz value), times 1.0001.  Runs on
+ * the uploaded operator of `level` with the solve's own SpMV (distributed when nranks > 1; collective).
+ * start: optional host start vector (this rank's rows; the reference draws uniform(-1,1) from
+ * std::random_device), NULL = a seeded generator on the global row index.  store != 0 installs the
+ * result as the level's bound (eig_max_of_invdiagXA). */
+int saena_b200_find_eig(saena_b200_ctx *ctx, int level, int max_iter, const double *start, uint64_t seed, int store,
+                        double *eig_out, int *iters_out);
+
 /* ---- solvers -----------------------------------------------------------------------------
  * rhs / u are this rank's block (grids[0].A->M entries).  u is overwritten (zero initial
  * guess, as the reference does: saena_object_solve.cpp:2482).  `iters` receives the count

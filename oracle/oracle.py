@@ -93,6 +93,36 @@ def _vecs(vs: Sequence[np.ndarray]):
     return arrs, ptrs
 
 
+def _largest_tridiag_eig(alpha, beta, rel_eps):
+    """largest eigenvalue of the symmetric tridiagonal matrix (diagonal alpha, off-diagonal beta) by
+    bisection on the Sturm count -- find_mth_eigenvalue / num_of_eigs_smaller_than,
+    /root/reference/external/lambda_lanczos/include/lambda_lanczos/lambda_lanczos.hpp:303-377"""
+    m = len(alpha)
+
+    def count_below(c):
+        cnt, q = 0, 1.0
+        for i in range(m):
+            q = alpha[i] - c - (beta[i - 1] ** 2 / q if i else 0.0)
+            if q < 0:
+                cnt += 1
+            if q == 0:
+                q = 1e-15
+        return cnt
+
+    r = max(abs(alpha[i]) + (abs(beta[i - 1]) if i else 0.0) + (abs(beta[i]) if i + 1 < m else 0.0) for i in range(m))
+    lo, hi, pmid = -r, r, None
+    while hi - lo > min(abs(lo), abs(hi)) * rel_eps:
+        mid = 0.5 * (lo + hi)
+        if count_below(mid) >= m:
+            hi = mid
+        else:
+            lo = mid
+        if mid == pmid:
+            break
+        pmid = mid
+    return 0.5 * (lo + hi)
+
+
 class Oracle:
     """The hierarchy of every rank, laid out for the C oracle."""
 
@@ -195,6 +225,44 @@ class Oracle:
         fn = lib().so_chebyshev if smoother == "chebyshev" else lib().so_jacobi
         fn(self._lvs(l), self.nranks, int(iters), up, rp)
         return self._unwrap(uin, u)
+
+    def find_eig(self, l, start, max_iter=20, eps=1e-8):
+        """saena_object::find_eig (/root/reference/src/saena_object.cpp:572-590) restated: Lanczos on
+        D^-1/2 A D^-1/2 as LambdaLanczos::run does it (external/lambda_lanczos/.../lambda_lanczos.hpp:170-260:
+        u_0 = 0 dummy, full modified Gram-Schmidt against every earlier vector, largest Ritz value by
+        bisection on the Sturm count :303-377, stop at a relative change below eps), start vector given
+        by the caller (one array per rank, or one array) -> (1.0001 * eigenvalue, steps).  Pinned against
+        the reference's own engine with the same start vector: tests/test_oracle_vs_reference.py."""
+        parts = self._wrap(start)
+        sizes = [len(p) for p in parts]
+        off = np.concatenate(([0], np.cumsum(sizes)))
+        split = lambda v: [v[off[r]:off[r + 1]] for r in range(self.nranks)]  # noqa: E731
+        s = np.sqrt(np.abs(np.concatenate([self.ranks[r].levels[l].inv_diag for r in range(self.nranks)])))
+        mv = lambda v: s * np.concatenate(self._wrap(self.matvec(l, 0, split(s * v) if self.nranks > 1 else s * v)))  # noqa: E731
+        uk = np.concatenate(parts).astype(F64)
+        uk = uk / np.sqrt(uk @ uk)
+        u = [np.zeros_like(uk), uk]
+        alpha, beta = [], []
+        betak, ev, pev, itern = 0.0, 0.0, np.finfo(F64).max, max_iter
+        for k in range(1, max_iter + 1):
+            vk = mv(u[k])
+            alphak = float(u[k] @ vk)
+            alpha.append(alphak)
+            nxt = vk - betak * u[k - 1] - alphak * u[k]
+            for uj in u:
+                nxt = nxt - float(uj @ nxt) * uj
+            betak = float(np.sqrt(nxt @ nxt))
+            beta.append(betak)
+            ev = _largest_tridiag_eig(alpha, beta[:-1], eps * 0.1)
+            if betak < 1e-16:
+                itern = k
+                break
+            u.append(nxt / betak)
+            if abs(ev - pev) < min(abs(ev), abs(pev)) * eps:
+                itern = k
+                break
+            pev = ev
+        return 1.0001 * ev, itern
 
     def dot(self, a, b):
         ain, ap = _vecs(self._wrap(a))

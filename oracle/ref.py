@@ -218,6 +218,16 @@ class RefSolver:
         lib().sref_coarsest_solve(self._h, _p(u), _p(rhs))
         return u
 
+    def find_eig(self, l: int, start) -> tuple:
+        """the reference's find_eig on level l with a caller-given Lanczos start vector -> (eig, steps);
+        perturbs the level's values by the scale / scale-back round trip: use a solver of its own"""
+        start = np.ascontiguousarray(start, F64)
+        it = ctypes.c_int(0)
+        f = lib().sref_find_eig_start
+        f.restype = ctypes.c_double
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+        return float(f(self._h, int(l), _p(start), ctypes.byref(it))), it.value
+
     def set_direct_solver(self, name: str):
         lib().sref_set_direct_solver(self._h, int(name == "CG"))
 

@@ -23,6 +23,7 @@
 #include "saena_matrix.h"
 #include "grid.h"
 #include "aux_functions2.h"
+#include "lambda_lanczos.hpp"   // the reference's own Lanczos engine (external/lambda_lanczos), templates only
 
 #include <cstdio>
 #include <cstring>
@@ -327,6 +328,27 @@ void sref_vcycle(void *hv, int l, int pre, int post, int smoother, double *u, do
     if (!h->vcycle_mem) { o->alloc_vcycle_memory(); h->vcycle_mem = true; }
     o->preSmooth = pre; o->postSmooth = post; o->smoother = smoother ? "chebyshev" : "jacobi";
     o->vcycle(&o->grids[l], u, rhs);
+}
+
+// saena_object::find_eig (saena_object.cpp:572-590) + find_eig_lamlan (lamlan_saena.h:13-79) on level l,
+// with the Lanczos start vector given by the caller instead of std::random_device -- the only
+// change, through the engine's own `init_vector` hook -- so that the result is reproducible.
+// Returns what find_eig stores: 1.0001 * eigenvalue.  scale_matrix / scale_back_matrix round-trip
+// the values in place, as in the reference's setup: use a solver object of its own for this call.
+double sref_find_eig_start(void *hv, int l, const double *start, int *iters) {
+    saena_matrix *A = level_A((Handle *)hv, l);
+    A->scale_matrix(false);
+    auto mv_mul = [&](const std::vector<value_t> &in, std::vector<value_t> &out) { A->matvec(&in[0], &out[0]); };
+    lambda_lanczos::LambdaLanczos<value_t> engine(mv_mul, A->M, true, A->comm);
+    engine.init_vector = [&](std::vector<value_t> &v) {
+        for (size_t i = 0; i < v.size(); ++i) v[i] = start[i];
+    };
+    value_t eigenvalue = 0.0;
+    std::vector<value_t> eigenvector;
+    const int itern = engine.run(eigenvalue, eigenvector);
+    A->scale_back_matrix(false);
+    if (iters) *iters = itern;
+    return 1.0001 * eigenvalue;
 }
 
 // saena_object::direct_solver: "SuperLU" (default, saena_object.h:165) or "CG"

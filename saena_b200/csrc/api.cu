@@ -657,6 +657,28 @@ int saena_b200_halo_choice(const saena_b200_ctx *ctx, int level, int kind, float
     return op.fused && sb_fused_eligible(op) ? 1 : 0;
 }
 
+// saena_object::find_eig on the device (csrc/lanczos.cu).  start: optional host start
+// vector (this rank's rows), else a seeded generator on the global row index.  store != 0 makes the
+// result the level's Chebyshev bound (what find_eig writes into eig_max_of_invdiagXA).
+int saena_b200_find_eig(saena_b200_ctx *ctx, int level, int max_iter, const double *start, uint64_t seed, int store,
+                        double *eig_out, int *iters_out) {
+    SB_ENTER();
+    if (level < 0 || level >= (int)ctx->levels.size() || !eig_out) SB_FAIL("find_eig: no such level");
+    DevLevel &lv = ctx->levels[level];
+    const double *start_dev = nullptr;
+    if (start) {
+        SB_TRY(stage_buf(ctx, 2, lv.M));
+        SB_TRY(h2d(ctx, ctx->stage[2], start, lv.M));
+        start_dev = ctx->stage[2];
+    }
+    SB_TRY(sb_find_eig(ctx, level, max_iter, start_dev, (unsigned long long)seed, eig_out, iters_out));
+    if (store) {
+        lv.eig_max = *eig_out;
+        sb_invalidate_graphs(ctx);  // the captured V-cycle carries the old Chebyshev constants
+    }
+    return 0;
+}
+
 // halo overlap of one operator: full application, local kernels alone, pack + exchange alone
 int saena_b200_time_matvec_parts(saena_b200_ctx *ctx, int level, int kind, int reps, float *full_ms,
                                  float *local_ms, float *halo_ms) {

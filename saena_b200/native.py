@@ -69,6 +69,8 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_finalize.argtypes = [vp]
     L.saena_b200_p2p_export.argtypes = [vp, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
     L.saena_b200_p2p_import.argtypes = [vp, vp, ctypes.c_int64]
+    L.saena_b200_find_eig.argtypes = [vp, i, i, vp, ctypes.c_uint64, i, ctypes.POINTER(ctypes.c_double),
+                                      ctypes.POINTER(ctypes.c_int)]
     L.saena_b200_p2p_enable.argtypes = [vp, i]
     L.saena_b200_autotune_halo.argtypes = [vp, i]
     L.saena_b200_halo_choice.argtypes = [vp, i, i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
@@ -107,7 +109,7 @@ EXPORTED_SYMBOLS = [
     "saena_b200_upload_operator", "saena_b200_upload_band_operator", "saena_b200_upload_level_aux", "saena_b200_upload_level_scale",
     "saena_b200_upload_coarsest",
     "saena_b200_set_coarsest_solver", "saena_b200_set_graphs", "saena_b200_finalize",
-    "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_p2p_enable", "saena_b200_autotune_halo", "saena_b200_halo_choice", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
+    "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_find_eig", "saena_b200_p2p_enable", "saena_b200_autotune_halo", "saena_b200_halo_choice", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
     "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_time_vcycle", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_graph_replays", "saena_b200_set_mapping", "saena_b200_set_mapping_deferred", "saena_b200_get_mapping",
@@ -280,6 +282,14 @@ class Context:
         a, b = ctypes.c_float(0), ctypes.c_float(0)
         c = int(self._L.saena_b200_halo_choice(self._h, level, kind, ctypes.byref(a), ctypes.byref(b)))
         return c, a.value, b.value
+
+    def find_eig(self, level: int, max_iter: int = 20, start=None, seed: int = 0, store: bool = False):
+        """saena_object::find_eig on the device -> (1.0001 * lambda_max(D^-1/2 A D^-1/2), Lanczos steps)"""
+        eig, it = ctypes.c_double(0), ctypes.c_int(0)
+        arr = None if start is None else np.ascontiguousarray(start, F64)   # kept alive across the call
+        self._ck(self._L.saena_b200_find_eig(self._h, level, int(max_iter), _vp(arr), int(seed), int(store),
+                                             ctypes.byref(eig), ctypes.byref(it)))
+        return eig.value, it.value
 
     def set_graphs(self, on: bool):
         self._ck(self._L.saena_b200_set_graphs(self._h, int(on)))

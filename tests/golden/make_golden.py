@@ -94,8 +94,34 @@ def make(name: str, mx, opts: RefOptions, coo=None, rhs=None, with_pcg: bool = T
 DATA = "/root/reference/data"
 
 
+def make_find_eig():
+    """find_eig.npz: the reference's own Lanczos engine (LambdaLanczos via saena_object::find_eig's
+    sequence, oracle/ref_harness.cpp:sref_find_eig_start) on every level of three of the matrices
+    above, with seeded start vectors in place of std::random_device.  The operators of a hierarchy are
+    reproducible run to run (only the eigenvalue estimates are not), so these belong to the
+    hierarchies frozen in the other files."""
+    rng = np.random.default_rng(777)
+    out = {}
+    helm = read_mtx(f"{DATA}/Helmholtz2D_CG_curved_tri/Helmholtz2D_CG_P8_Modes_curved_tri.mtx")
+    for name, build in (("poisson9_cheb", lambda: RefSolver.poisson(9, RefOptions())),
+                        ("poisson12_cheb", lambda: RefSolver.poisson(12, RefOptions())),
+                        ("helmholtz2d_p8", lambda: RefSolver.from_coo(*helm, np.ones(helm[0]), RefOptions()))):
+        s = build()
+        for l, lv in enumerate(s.hierarchy().levels):
+            start = rng.uniform(-1, 1, lv.A.M)
+            eig, iters = s.find_eig(l, start)
+            out[f"{name}.L{l}.start"] = start
+            out[f"{name}.L{l}.eig"] = np.array([eig])
+            out[f"{name}.L{l}.iters"] = np.array([iters])
+            print(name, l, lv.A.M, eig, iters)
+        s.close()
+    np.savez_compressed(os.path.join(HERE, "find_eig.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["poisson12_cheb", "poisson9_cheb", "helmholtz2d_p8", "homg33", "band8_1500"]
+    which = sys.argv[1:] or ["poisson12_cheb", "poisson9_cheb", "helmholtz2d_p8", "homg33", "band8_1500", "find_eig"]
+    if "find_eig" in which:
+        make_find_eig()
     rng = np.random.default_rng(2024)
     if "poisson12_cheb" in which:
         make("poisson12_cheb", 12, RefOptions())

@@ -41,3 +41,27 @@ def test_oracle_stationary_vcycle_converges():
     u, iters, hist = Oracle(g.hier).solve_vcycle(g.rhs, 50, 1e-8)
     assert hist[-1] / hist[0] < 1e-8 and iters < 50
     assert np.all(np.diff(hist) < 0)
+
+
+def _find_eig_cases():
+    import os
+    from tests.util import GOLDEN_DIR
+    d = np.load(os.path.join(GOLDEN_DIR, "find_eig.npz"))
+    names = sorted({k.rsplit(".L", 1)[0] for k in d.files})
+    return d, names
+
+
+@pytest.mark.parametrize("name", _find_eig_cases()[1])
+def test_oracle_find_eig_matches_reference_engine_golden(name):
+    """the Lanczos bound of every level with the start vectors frozen next to the
+    reference engine's answers (tests/golden/make_golden.py:make_find_eig); converged early on some
+    levels (7..17 steps), out of steps (20) on others -- both must agree"""
+    d, _ = _find_eig_cases()
+    g = Golden(name)
+    o = Oracle(g.hier)
+    for l in range(len(g.hier.levels)):
+        eig, iters = o.find_eig(l, d[f"{name}.L{l}.start"])
+        assert abs(eig - float(d[f"{name}.L{l}.eig"][0])) <= 5e-9 * eig, (name, l)
+        assert iters == int(d[f"{name}.L{l}.iters"][0]), (name, l)
+        # and it is the bound the setup stored, up to the reference's random start vector
+        assert abs(eig - g.hier.levels[l].eig_max) <= 2e-2 * eig

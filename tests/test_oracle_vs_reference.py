@@ -70,3 +70,21 @@ def test_pcg_jacobi_smoother_and_max_iter_cap(poisson16):
     u, it, hist = Oracle(h).solve_pcg(s.rhs(), 3, 1e-14, "jacobi", 2, 1)
     assert it == it_ref == 3
     check_pcg(it, hist, u, it_ref, hist_ref, u_ref, TOL_HIST)
+
+
+def test_find_eig_restatement_matches_the_reference_engine():
+    """Oracle.find_eig against saena_object::find_eig's own sequence (scale_matrix,
+    LambdaLanczos::run, scale_back_matrix) with the same start vector, on a solver object of its own
+    (the scale / scale-back round trip perturbs the level's values)"""
+    s = ref.RefSolver.poisson(13)
+    try:
+        h = s.hierarchy()
+        o = Oracle(h)
+        rng = np.random.default_rng(99)
+        for l, lv in enumerate(h.levels):
+            start = rng.uniform(-1, 1, lv.A.M)
+            eig_o, it_o = o.find_eig(l, start)
+            eig_r, it_r = s.find_eig(l, start)
+            assert abs(eig_o - eig_r) <= 5e-9 * eig_r and it_o == it_r, (l, eig_o, eig_r, it_o, it_r)
+    finally:
+        s.close()

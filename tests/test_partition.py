@@ -125,3 +125,15 @@ def test_partitioned_unstructured_shape_equals_one_rank():
     un, itn, hn = Oracle(hs).solve_pcg(_parts(hs, rhs))
     assert itn == it1 and np.max(np.abs(hn - h1) / h1) < 1e-9
     assert rel(np.concatenate(un), u1) < 1e-9
+
+
+def test_partitioned_find_eig_equals_one_rank():
+    g = Golden(GOLDEN[1])
+    h = _force_double(g.hier)
+    hs = partition_hierarchy(h, 3, agglomerate_below=0)
+    rng = np.random.default_rng(8)
+    for l, lv in enumerate(h.levels):
+        start = rng.uniform(-1, 1, lv.A.M)
+        e1, it1 = Oracle(h).find_eig(l, start)
+        en, itn = Oracle(hs).find_eig(l, _parts(hs, start, l))
+        assert abs(e1 - en) <= 1e-9 * e1 and it1 == itn
