@@ -208,7 +208,7 @@ struct VcycleGraph {
     cudaGraphExec_t exec;
     int64_t launches;
     std::vector<int> cur_after;  // each level's ping-pong parity when the V-cycle ends
-    bool exec_pending;           // multi-rank: seen once (ran eagerly), captured at the next use
+    // exec == nullptr: a multi-rank configuration that has run eagerly once and is captured at its next use
 };
 
 struct saena_b200_ctx {

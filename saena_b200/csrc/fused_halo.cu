@@ -233,6 +233,7 @@ static int apply_fused_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x
     // a pack CTA of another rank, never a CTA behind it in this grid)
     a.n_wait = std::min(a.n_wait_blocks, 8 * ctx->sm_count);
     if (mode != 1 && a.n_wait == 0 && !op.recvs.empty()) SB_FAIL("fused apply: receives but no row reads them");
+    if (a.n_segs > 256 || a.n_recv > 256) SB_FAIL("fused apply: more than 256 neighbours (one spinning thread each)");
     const int grid = a.n_pack + a.n_int + a.n_wait;
     if (grid == 0) return 0;
     ++ctx->launches;

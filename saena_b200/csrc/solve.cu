@@ -168,26 +168,21 @@ int sb_vcycle_from_zero(saena_b200_ctx *ctx, int smoother, int pre, int post, co
     for (DevLevel &lv : ctx->levels) lv.cur = 0;
     const bool capturable = ctx->use_graphs && !ctx->coarsest_cg && (ctx->nranks == 1 || ctx->use_graphs_multi);
     if (!capturable) return sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
+    VcycleGraph *known = nullptr;
     for (VcycleGraph &g : ctx->graphs)
-        if (g.rhs == rhs && g.smoother == smoother && g.pre == pre && g.post == post) {
-            // multi-rank: this configuration has run eagerly once (NCCL has opened its
-            // point-to-point channels, every lazy allocation is done) -- capture it now
-            if (!g.exec) break;
-            SB_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
-            ctx->launches += g.launches;
-            ++ctx->graph_replays;
-            for (size_t l = 0; l < ctx->levels.size(); ++l) ctx->levels[l].cur = g.cur_after[l];
-            return 0;
-        }
-    if (ctx->nranks > 1) {
-        bool seen = false;
-        for (VcycleGraph &g : ctx->graphs)
-            seen |= (g.rhs == rhs && g.smoother == smoother && g.pre == pre && g.post == post);
-        if (!seen) {
-            VcycleGraph g{rhs, smoother, pre, post, nullptr, 0, {}, true};
-            ctx->graphs.push_back(g);
-            return sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
-        }
+        if (g.rhs == rhs && g.smoother == smoother && g.pre == pre && g.post == post) known = &g;
+    if (known && known->exec) {
+        SB_CUDA(cudaGraphLaunch(known->exec, ctx->stream));
+        ctx->launches += known->launches;
+        ++ctx->graph_replays;
+        for (size_t l = 0; l < ctx->levels.size(); ++l) ctx->levels[l].cur = known->cur_after[l];
+        return 0;
+    }
+    if (!known && ctx->nranks > 1) {
+        // several ranks: the first V-cycle of a configuration runs eagerly (NCCL opens its
+        // point-to-point channels, every lazy allocation happens), the next one is captured
+        ctx->graphs.push_back(VcycleGraph{rhs, smoother, pre, post, nullptr, 0, {}});
+        return sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
     }
     // first use of this configuration (second on several ranks): capture, instantiate, launch
     const int64_t before = ctx->launches;
@@ -211,7 +206,7 @@ int sb_vcycle_from_zero(saena_b200_ctx *ctx, int smoother, int pre, int post, co
         ctx->error.clear();
         return sb_vcycle(ctx, 0, smoother, pre, post, rhs, true);
     }
-    VcycleGraph g{rhs, smoother, pre, post, nullptr, ctx->launches - before, {}, false};
+    VcycleGraph g{rhs, smoother, pre, post, nullptr, ctx->launches - before, {}};
     const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) {
