@@ -1,0 +1,827 @@
+/*
+ * mpi_multi.c -- multi-process MPI stand-in over Unix-domain sockets (TEST INFRASTRUCTURE).
+ * See mpi.h in this directory.  One process per rank, started by oracle/mprun.py with
+ *   SBMPI_RANK, SBMPI_SIZE, SBMPI_DIR (a private directory for the rendezvous sockets).
+ * Without these variables the world has one rank and no socket is opened.
+ *
+ * Design (small on purpose; N <= 64 ranks on one host):
+ *   - full mesh of stream sockets, all non-blocking;
+ *   - sends are eager and buffered: the payload is copied into the peer's out-queue and the send
+ *     request completes at once (MPI_Issend therefore has MPI_Isend semantics);
+ *   - progress() flushes out-queues and parses whatever has arrived; it runs inside every blocking
+ *     call, so no rank can starve another as long as it eventually enters the library;
+ *   - matching follows MPI: a message is matched against the posted receives in posting order at
+ *     arrival, a receive against the unexpected queue at posting; messages between two ranks on
+ *     one communicator do not overtake (stream order);
+ *   - collectives are linear algorithms on reserved negative tags; reductions combine the
+ *     contributions in rank order (deterministic);
+ *   - a communicator is (context id, list of world ranks); new context ids are agreed by a max
+ *     over the participants.
+ */
+#define _GNU_SOURCE
+#include "mpi.h"
+
+#include <errno.h>
+#include <fcntl.h>
+#include <poll.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/socket.h>
+#include <sys/stat.h>
+#include <sys/un.h>
+#include <time.h>
+#include <unistd.h>
+
+#define MAXP 64
+#define DIE(...) do { fprintf(stderr, "[sbmpi rank %d] ", g_rank); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); \
+                      fflush(stderr); _exit(86); } while (0)
+
+/* ------------------------------------------------------------------ state */
+static int g_rank = 0, g_size = 1, g_inited = 0, g_finalized = 0, g_finalizing = 0;
+static int g_fd[MAXP];
+
+typedef struct Msg { int ctx, tag, src; size_t len; char *data; struct Msg *next; } Msg;
+static Msg *g_unexp_head[MAXP], *g_unexp_tail[MAXP];   /* unexpected messages per world source, FIFO */
+
+typedef struct Out { char *data; size_t len, off; struct Out *next; } Out;
+static Out *g_out_head[MAXP], *g_out_tail[MAXP];
+
+typedef struct { int32_t ctx, tag; int64_t len; } Hdr;
+typedef struct { Hdr h; size_t got_h; char *data; size_t got_d; } InState;
+static InState g_in[MAXP];
+
+typedef struct { int used, ctx, size, rank; int *world; } Comm;
+static Comm *g_comms; static int g_ncomms;
+static int g_next_ctx = 16;
+
+typedef struct { int used, n; int *world; } Group;
+static Group *g_groups; static int g_ngroups;
+
+typedef struct Req {
+    int used, is_recv, done, comm;
+    void *buf; size_t cap; int ctx, src_world /* -1 any */, tag;
+    MPI_Status st;
+    struct Req *next_posted;
+} Req;
+static Req *g_reqs; static int g_nreqs;
+static Req *g_posted_head, *g_posted_tail;   /* posted, unmatched receives in posting order */
+
+static MPI_User_function *g_user_ops[64]; static int g_n_user_ops;
+
+/* ------------------------------------------------------------------ helpers */
+static Comm *C(MPI_Comm c) {
+    if (c <= 0 || c >= g_ncomms || !g_comms[c].used) DIE("invalid communicator %d", c);
+    return &g_comms[c];
+}
+static int new_comm(int ctx, int size, int rank, const int *world) {
+    int id = -1;
+    for (int i = 3; i < g_ncomms; ++i) if (!g_comms[i].used) { id = i; break; }
+    if (id < 0) {
+        int n = g_ncomms ? g_ncomms * 2 : 16;
+        g_comms = (Comm *)realloc(g_comms, sizeof(Comm) * n);
+        memset(g_comms + g_ncomms, 0, sizeof(Comm) * (n - g_ncomms));
+        id = g_ncomms < 3 ? 3 : g_ncomms;
+        g_ncomms = n;
+    }
+    Comm *c = &g_comms[id];
+    c->used = 1; c->ctx = ctx; c->size = size; c->rank = rank;
+    c->world = (int *)malloc(sizeof(int) * (size > 0 ? size : 1));
+    memcpy(c->world, world, sizeof(int) * size);
+    return id;
+}
+static void set_comm(int id, int ctx, int size, int rank, const int *world) {
+    Comm *c = &g_comms[id];
+    c->used = 1; c->ctx = ctx; c->size = size; c->rank = rank;
+    c->world = (int *)malloc(sizeof(int) * size);
+    memcpy(c->world, world, sizeof(int) * size);
+}
+static int new_group(int n, const int *world) {
+    int id = -1;
+    for (int i = 2; i < g_ngroups; ++i) if (!g_groups[i].used) { id = i; break; }
+    if (id < 0) {
+        int m = g_ngroups ? g_ngroups * 2 : 16;
+        g_groups = (Group *)realloc(g_groups, sizeof(Group) * m);
+        memset(g_groups + g_ngroups, 0, sizeof(Group) * (m - g_ngroups));
+        id = g_ngroups < 2 ? 2 : g_ngroups;
+        g_ngroups = m;
+    }
+    g_groups[id].used = 1; g_groups[id].n = n;
+    g_groups[id].world = (int *)malloc(sizeof(int) * (n > 0 ? n : 1));
+    if (n) memcpy(g_groups[id].world, world, sizeof(int) * n);
+    return id;
+}
+static Group *G(MPI_Group g) {
+    static Group empty = {1, 0, NULL};
+    if (g == MPI_GROUP_EMPTY) return &empty;
+    if (g <= 1 || g >= g_ngroups || !g_groups[g].used) DIE("invalid group %d", g);
+    return &g_groups[g];
+}
+static int comm_rank_of_world(const Comm *c, int w) {
+    for (int i = 0; i < c->size; ++i) if (c->world[i] == w) return i;
+    return MPI_UNDEFINED;
+}
+static size_t dt_size(MPI_Datatype dt) { return (size_t)SBMPI_DT_SIZE(dt); }
+static void fill_status(MPI_Status *st, int src, int tag, size_t bytes) {
+    if (!st) return;
+    st->MPI_SOURCE = src; st->MPI_TAG = tag; st->MPI_ERROR = MPI_SUCCESS; st->count_bytes = (int)bytes;
+}
+static int tag_matches(int want, int have) { return want == MPI_ANY_TAG ? have >= 0 : want == have; }
+
+/* ------------------------------------------------------------------ matching */
+static void complete_recv(Req *r, Msg *m) {
+    size_t n = m->len < r->cap ? m->len : r->cap;
+    if (n) memcpy(r->buf, m->data, n);
+    fill_status(&r->st, comm_rank_of_world(C(r->comm), m->src), m->tag, n);
+    r->done = 1;
+    free(m->data);
+    free(m);
+}
+static void deliver(Msg *m) {   /* a complete message from world rank m->src has arrived */
+    Req *prev = NULL;
+    for (Req *r = g_posted_head; r; prev = r, r = r->next_posted) {
+        if (r->ctx == m->ctx && (r->src_world < 0 || r->src_world == m->src) && tag_matches(r->tag, m->tag)) {
+            if (prev) prev->next_posted = r->next_posted; else g_posted_head = r->next_posted;
+            if (g_posted_tail == r) g_posted_tail = prev;
+            r->next_posted = NULL;
+            complete_recv(r, m);
+            return;
+        }
+    }
+    m->next = NULL;
+    if (g_unexp_tail[m->src]) g_unexp_tail[m->src]->next = m; else g_unexp_head[m->src] = m;
+    g_unexp_tail[m->src] = m;
+}
+static Msg *find_unexpected(int ctx, int src_world, int tag, int remove) {
+    int lo = src_world < 0 ? 0 : src_world, hi = src_world < 0 ? g_size - 1 : src_world;
+    for (int s = lo; s <= hi; ++s) {
+        Msg *prev = NULL;
+        for (Msg *m = g_unexp_head[s]; m; prev = m, m = m->next) {
+            if (m->ctx == ctx && tag_matches(tag, m->tag)) {
+                if (remove) {
+                    if (prev) prev->next = m->next; else g_unexp_head[s] = m->next;
+                    if (g_unexp_tail[s] == m) g_unexp_tail[s] = prev;
+                }
+                return m;
+            }
+        }
+    }
+    return NULL;
+}
+
+/* ------------------------------------------------------------------ progress engine */
+static int progress_once(void) {
+    int did = 0;
+    for (int p = 0; p < g_size; ++p) {
+        if (p == g_rank || g_fd[p] < 0) continue;
+        while (g_out_head[p]) {
+            Out *o = g_out_head[p];
+            ssize_t w = send(g_fd[p], o->data + o->off, o->len - o->off, MSG_NOSIGNAL);
+            if (w < 0) {
+                if (errno == EAGAIN || errno == EWOULDBLOCK || errno == EINTR) break;
+                DIE("write to rank %d: %s", p, strerror(errno));
+            }
+            did = 1;
+            o->off += (size_t)w;
+            if (o->off == o->len) {
+                g_out_head[p] = o->next;
+                if (!g_out_head[p]) g_out_tail[p] = NULL;
+                free(o->data); free(o);
+            } else break;
+        }
+        for (;;) {
+            InState *in = &g_in[p];
+            if (in->got_h < sizeof(Hdr)) {
+                ssize_t r = read(g_fd[p], (char *)&in->h + in->got_h, sizeof(Hdr) - in->got_h);
+                if (r < 0) { if (errno == EAGAIN || errno == EWOULDBLOCK || errno == EINTR) break; DIE("read from rank %d: %s", p, strerror(errno)); }
+                if (r == 0) {   /* peer closed: fine once everybody is past the barrier of MPI_Finalize */
+                    if (!g_finalizing) DIE("rank %d closed its connection (it exited or crashed)", p);
+                    close(g_fd[p]); g_fd[p] = -1;
+                    break;
+                }
+                did = 1;
+                in->got_h += (size_t)r;
+                if (in->got_h < sizeof(Hdr)) break;
+                in->data = (char *)malloc(in->h.len > 0 ? (size_t)in->h.len : 1);
+                in->got_d = 0;
+            }
+            if (in->got_d < (size_t)in->h.len) {
+                ssize_t r = read(g_fd[p], in->data + in->got_d, (size_t)in->h.len - in->got_d);
+                if (r < 0) { if (errno == EAGAIN || errno == EWOULDBLOCK || errno == EINTR) break; DIE("read from rank %d: %s", p, strerror(errno)); }
+                if (r == 0) DIE("rank %d closed its connection inside a message", p);
+                did = 1;
+                in->got_d += (size_t)r;
+                if (in->got_d < (size_t)in->h.len) break;
+            }
+            Msg *m = (Msg *)malloc(sizeof(Msg));
+            m->ctx = in->h.ctx; m->tag = in->h.tag; m->src = p; m->len = (size_t)in->h.len; m->data = in->data; m->next = NULL;
+            in->got_h = 0; in->data = NULL; in->got_d = 0;
+            deliver(m);
+        }
+    }
+    return did;
+}
+static void progress_wait(void) {   /* nothing to do right now: sleep until a socket is ready */
+    if (progress_once() || g_size == 1) return;
+    struct pollfd pf[MAXP]; int n = 0;
+    for (int p = 0; p < g_size; ++p) {
+        if (p == g_rank || g_fd[p] < 0) continue;
+        pf[n].fd = g_fd[p]; pf[n].events = POLLIN | (g_out_head[p] ? POLLOUT : 0); pf[n].revents = 0; ++n;
+    }
+    poll(pf, (nfds_t)n, 20);
+}
+
+static void enqueue_send(int ctx, int dest_world, int tag, const void *buf, size_t len) {
+    if (dest_world == g_rank) {
+        Msg *m = (Msg *)malloc(sizeof(Msg));
+        m->ctx = ctx; m->tag = tag; m->src = g_rank; m->len = len; m->next = NULL;
+        m->data = (char *)malloc(len ? len : 1);
+        if (len) memcpy(m->data, buf, len);
+        deliver(m);
+        return;
+    }
+    Out *o = (Out *)malloc(sizeof(Out));
+    o->len = sizeof(Hdr) + len; o->off = 0; o->next = NULL;
+    o->data = (char *)malloc(o->len);
+    Hdr h; h.ctx = ctx; h.tag = tag; h.len = (int64_t)len;
+    memcpy(o->data, &h, sizeof(Hdr));
+    if (len) memcpy(o->data + sizeof(Hdr), buf, len);
+    if (g_out_tail[dest_world]) g_out_tail[dest_world]->next = o; else g_out_head[dest_world] = o;
+    g_out_tail[dest_world] = o;
+    progress_once();
+}
+
+/* ------------------------------------------------------------------ requests */
+static Req *new_req(MPI_Request *h) {
+    for (int i = 1; i < g_nreqs; ++i)
+        if (!g_reqs[i].used) { memset(&g_reqs[i], 0, sizeof(Req)); g_reqs[i].used = 1; *h = i; return &g_reqs[i]; }
+    /* grow: posted receives are linked by pointer, so move the table by hand and re-link */
+    int n = g_nreqs ? g_nreqs * 2 : 256;
+    Req *neu = (Req *)calloc((size_t)n, sizeof(Req));
+    if (g_reqs) {
+        memcpy(neu, g_reqs, sizeof(Req) * g_nreqs);
+#define RELINK(p) ((p) ? neu + ((p) - g_reqs) : NULL)
+        g_posted_head = RELINK(g_posted_head);
+        g_posted_tail = RELINK(g_posted_tail);
+        for (int i = 1; i < g_nreqs; ++i) neu[i].next_posted = RELINK(neu[i].next_posted);
+#undef RELINK
+        free(g_reqs);
+    }
+    g_reqs = neu;
+    int id = g_nreqs ? g_nreqs : 1;
+    g_nreqs = n;
+    g_reqs[id].used = 1; *h = id;
+    return &g_reqs[id];
+}
+static void post_recv(Req *r) {
+    Msg *m = find_unexpected(r->ctx, r->src_world, r->tag, 1);
+    if (m) { complete_recv(r, m); return; }
+    r->next_posted = NULL;
+    if (g_posted_tail) g_posted_tail->next_posted = r; else g_posted_head = r;
+    g_posted_tail = r;
+}
+static void unpost(Req *r) {
+    Req *prev = NULL;
+    for (Req *q = g_posted_head; q; prev = q, q = q->next_posted)
+        if (q == r) {
+            if (prev) prev->next_posted = q->next_posted; else g_posted_head = q->next_posted;
+            if (g_posted_tail == q) g_posted_tail = prev;
+            return;
+        }
+}
+
+/* blocking internal point-to-point on a communicator's context (collectives) */
+static void csend(const Comm *c, int dest, int tag, const void *buf, size_t len) { enqueue_send(c->ctx, c->world[dest], tag, buf, len); }
+static void crecv(MPI_Comm comm, int src, int tag, void *buf, size_t len) {
+    MPI_Request h; Req *r = new_req(&h);
+    Comm *c = C(comm);
+    r->is_recv = 1; r->comm = comm; r->buf = buf; r->cap = len; r->ctx = c->ctx; r->src_world = c->world[src]; r->tag = tag;
+    post_recv(r);
+    while (!g_reqs[h].done) progress_wait();
+    g_reqs[h].used = 0;
+}
+
+/* ------------------------------------------------------------------ init / finalize */
+static void set_nonblock(int fd) { fcntl(fd, F_SETFL, fcntl(fd, F_GETFL, 0) | O_NONBLOCK); }
+static void full_write(int fd, const void *b, size_t n) { const char *p = (const char *)b; while (n) { ssize_t w = write(fd, p, n); if (w <= 0) { if (errno == EINTR) continue; DIE("rendezvous write: %s", strerror(errno)); } p += w; n -= (size_t)w; } }
+static void full_read(int fd, void *b, size_t n) { char *p = (char *)b; while (n) { ssize_t r = read(fd, p, n); if (r <= 0) { if (r < 0 && errno == EINTR) continue; DIE("rendezvous read: %s", r ? strerror(errno) : "closed"); } p += r; n -= (size_t)r; } }
+
+int MPI_Init(int *argc, char ***argv) {
+    (void)argc; (void)argv;
+    if (g_inited) return MPI_SUCCESS;
+    g_inited = 1;
+    const char *er = getenv("SBMPI_RANK"), *es = getenv("SBMPI_SIZE"), *ed = getenv("SBMPI_DIR");
+    if (er && es && ed) { g_rank = atoi(er); g_size = atoi(es); }
+    if (g_size < 1 || g_size > MAXP || g_rank < 0 || g_rank >= g_size) DIE("bad SBMPI_RANK / SBMPI_SIZE");
+    for (int p = 0; p < MAXP; ++p) g_fd[p] = -1;
+    g_comms = (Comm *)calloc(16, sizeof(Comm)); g_ncomms = 16;
+    int world[MAXP]; for (int i = 0; i < g_size; ++i) world[i] = i;
+    set_comm(MPI_COMM_WORLD, 1, g_size, g_rank, world);
+    set_comm(MPI_COMM_SELF, 2, 1, 0, &g_rank);
+    g_groups = (Group *)calloc(16, sizeof(Group)); g_ngroups = 16;
+    g_reqs = NULL; g_nreqs = 0;
+    if (g_size == 1) return MPI_SUCCESS;
+    /* rendezvous: listen on <dir>/<rank>.sock, connect to every lower rank, accept every higher one */
+    struct sockaddr_un a; memset(&a, 0, sizeof(a)); a.sun_family = AF_UNIX;
+    snprintf(a.sun_path, sizeof(a.sun_path), "%s/%d.sock", ed, g_rank);
+    int ls = socket(AF_UNIX, SOCK_STREAM, 0);
+    unlink(a.sun_path);
+    if (bind(ls, (struct sockaddr *)&a, sizeof(a)) || listen(ls, MAXP)) DIE("listen on %s: %s", a.sun_path, strerror(errno));
+    for (int p = 0; p < g_rank; ++p) {
+        struct sockaddr_un b; memset(&b, 0, sizeof(b)); b.sun_family = AF_UNIX;
+        snprintf(b.sun_path, sizeof(b.sun_path), "%s/%d.sock", ed, p);
+        int fd = -1;
+        for (int tries = 0; tries < 6000; ++tries) {   /* up to ~60 s for the peer to start listening */
+            fd = socket(AF_UNIX, SOCK_STREAM, 0);
+            if (connect(fd, (struct sockaddr *)&b, sizeof(b)) == 0) break;
+            close(fd); fd = -1;
+            usleep(10000);
+        }
+        if (fd < 0) DIE("cannot connect to rank %d", p);
+        int32_t me = g_rank; full_write(fd, &me, sizeof(me));
+        g_fd[p] = fd;
+    }
+    for (int k = g_rank + 1; k < g_size; ++k) {
+        int fd = accept(ls, NULL, NULL);
+        if (fd < 0) DIE("accept: %s", strerror(errno));
+        int32_t who = -1; full_read(fd, &who, sizeof(who));
+        if (who <= g_rank || who >= g_size || g_fd[who] >= 0) DIE("unexpected peer %d", who);
+        g_fd[who] = fd;
+    }
+    close(ls);
+    for (int p = 0; p < g_size; ++p) if (g_fd[p] >= 0) {
+        set_nonblock(g_fd[p]);
+        int sz = 4 << 20; setsockopt(g_fd[p], SOL_SOCKET, SO_SNDBUF, &sz, sizeof(sz)); setsockopt(g_fd[p], SOL_SOCKET, SO_RCVBUF, &sz, sizeof(sz));
+    }
+    return MPI_SUCCESS;
+}
+int MPI_Init_thread(int *argc, char ***argv, int required, int *provided) { if (provided) *provided = required; return MPI_Init(argc, argv); }
+int MPI_Initialized(int *flag) { *flag = g_inited; return MPI_SUCCESS; }
+int MPI_Finalized(int *flag) { *flag = g_finalized; return MPI_SUCCESS; }
+int MPI_Finalize(void) {
+    if (!g_inited || g_finalized) return MPI_SUCCESS;
+    g_finalizing = 1;
+    MPI_Barrier(MPI_COMM_WORLD);
+    for (;;) {   /* drain */
+        int pending = 0;
+        for (int p = 0; p < g_size; ++p) if (g_out_head[p] && g_fd[p] >= 0) pending = 1;
+        if (!pending) break;
+        progress_wait();
+    }
+    g_finalized = 1;
+    for (int p = 0; p < g_size; ++p) if (g_fd[p] >= 0) { shutdown(g_fd[p], SHUT_WR); }
+    return MPI_SUCCESS;
+}
+int MPI_Abort(MPI_Comm comm, int code) { (void)comm; fprintf(stderr, "[sbmpi rank %d] MPI_Abort(%d)\n", g_rank, code); fflush(NULL); _exit(code ? code : 1); }
+double MPI_Wtime(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+int MPI_Pcontrol(const int level, ...) { (void)level; return MPI_SUCCESS; }
+int MPI_Get_processor_name(char *name, int *len) { snprintf(name, MPI_MAX_PROCESSOR_NAME, "sbmpi-%d", g_rank); *len = (int)strlen(name); return MPI_SUCCESS; }
+
+/* ------------------------------------------------------------------ communicators and groups */
+int MPI_Comm_size(MPI_Comm comm, int *size) { *size = C(comm)->size; return MPI_SUCCESS; }
+int MPI_Comm_rank(MPI_Comm comm, int *rank) { *rank = C(comm)->rank; return MPI_SUCCESS; }
+static int agree_ctx(MPI_Comm comm) {
+    int mine = g_next_ctx, mx = 0;
+    MPI_Allreduce(&mine, &mx, 1, MPI_INT, MPI_MAX, comm);
+    g_next_ctx = mx + 1;
+    return mx;
+}
+int MPI_Comm_dup(MPI_Comm comm, MPI_Comm *out) {
+    Comm *c = C(comm);
+    int ctx = agree_ctx(comm);
+    c = C(comm);
+    *out = new_comm(ctx, c->size, c->rank, c->world);
+    return MPI_SUCCESS;
+}
+int MPI_Comm_split(MPI_Comm comm, int color, int key, MPI_Comm *out) {
+    Comm *c = C(comm);
+    const int n = c->size;
+    int mine[3] = {color, key, g_rank};
+    int *all = (int *)malloc(sizeof(int) * 3 * n);
+    MPI_Allgather(mine, 3, MPI_INT, all, 3, MPI_INT, comm);
+    int ctx = agree_ctx(comm);
+    c = C(comm);
+    if (color == MPI_UNDEFINED) { *out = MPI_COMM_NULL; free(all); return MPI_SUCCESS; }
+    /* members of my colour ordered by (key, rank in the parent) */
+    int *idx = (int *)malloc(sizeof(int) * n); int m = 0;
+    for (int i = 0; i < n; ++i) if (all[3 * i] == color) idx[m++] = i;
+    for (int i = 1; i < m; ++i) {   /* stable insertion sort by key */
+        int v = idx[i], j = i - 1;
+        while (j >= 0 && all[3 * idx[j] + 1] > all[3 * v + 1]) { idx[j + 1] = idx[j]; --j; }
+        idx[j + 1] = v;
+    }
+    int *world = (int *)malloc(sizeof(int) * m); int me = -1;
+    for (int i = 0; i < m; ++i) { world[i] = all[3 * idx[i] + 2]; if (world[i] == g_rank) me = i; }
+    *out = new_comm(ctx, m, me, world);
+    free(world); free(idx); free(all);
+    return MPI_SUCCESS;
+}
+int MPI_Comm_free(MPI_Comm *comm) {
+    if (*comm > 2 && *comm < g_ncomms && g_comms[*comm].used) { free(g_comms[*comm].world); g_comms[*comm].used = 0; }
+    *comm = MPI_COMM_NULL;
+    return MPI_SUCCESS;
+}
+int MPI_Comm_group(MPI_Comm comm, MPI_Group *group) { Comm *c = C(comm); *group = new_group(c->size, c->world); return MPI_SUCCESS; }
+int MPI_Group_incl(MPI_Group group, int n, const int ranks[], MPI_Group *out) {
+    Group *g = G(group);
+    if (n == 0) { *out = MPI_GROUP_EMPTY; return MPI_SUCCESS; }
+    int *w = (int *)malloc(sizeof(int) * n);
+    for (int i = 0; i < n; ++i) { if (ranks[i] < 0 || ranks[i] >= g->n) DIE("MPI_Group_incl: rank out of range"); w[i] = g->world[ranks[i]]; }
+    *out = new_group(n, w);
+    free(w);
+    return MPI_SUCCESS;
+}
+int MPI_Group_free(MPI_Group *group) {
+    if (*group > 1 && *group < g_ngroups && g_groups[*group].used) { free(g_groups[*group].world); g_groups[*group].used = 0; }
+    *group = MPI_GROUP_NULL;
+    return MPI_SUCCESS;
+}
+static int group_rank_of_me(const Group *g) { for (int i = 0; i < g->n; ++i) if (g->world[i] == g_rank) return i; return -1; }
+int MPI_Comm_create(MPI_Comm comm, MPI_Group group, MPI_Comm *out) {
+    int ctx = agree_ctx(comm);   /* collective over the parent */
+    Group *g = G(group);
+    int me = group_rank_of_me(g);
+    *out = me < 0 ? MPI_COMM_NULL : new_comm(ctx, g->n, me, g->world);
+    return MPI_SUCCESS;
+}
+int MPI_Comm_create_group(MPI_Comm comm, MPI_Group group, int tag, MPI_Comm *out) {
+    /* collective over the group only: its first member collects the proposals and answers */
+    Comm *c = C(comm);
+    Group *g = G(group);
+    int me = group_rank_of_me(g);
+    if (me < 0) { *out = MPI_COMM_NULL; return MPI_SUCCESS; }
+    const int t = -1000 - (tag & 0xFFFF);
+    int ctx = g_next_ctx;
+    if (me == 0) {
+        for (int i = 1; i < g->n; ++i) {
+            int v = 0; crecv(comm, comm_rank_of_world(c, g->world[i]), t, &v, sizeof(v));
+            c = C(comm);
+            if (v > ctx) ctx = v;
+        }
+        for (int i = 1; i < g->n; ++i) enqueue_send(c->ctx, g->world[i], t, &ctx, sizeof(ctx));
+    } else {
+        enqueue_send(c->ctx, g->world[0], t, &ctx, sizeof(ctx));
+        crecv(comm, comm_rank_of_world(c, g->world[0]), t, &ctx, sizeof(ctx));
+    }
+    g_next_ctx = ctx + 1;
+    *out = new_comm(ctx, g->n, me, g->world);
+    return MPI_SUCCESS;
+}
+int MPI_Comm_set_errhandler(MPI_Comm comm, MPI_Errhandler eh) { (void)comm; (void)eh; return MPI_SUCCESS; }
+int MPI_Attr_get(MPI_Comm comm, int keyval, void *attr, int *flag) {
+    static int tag_ub = 1 << 30;
+    (void)comm;
+    if (keyval == MPI_TAG_UB) { *(int **)attr = &tag_ub; *flag = 1; } else *flag = 0;
+    return MPI_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ point to point */
+int MPI_Isend(const void *buf, int count, MPI_Datatype dt, int dest, int tag, MPI_Comm comm, MPI_Request *req) {
+    Req *r = new_req(req);
+    r->done = 1; r->comm = comm;
+    if (dest == MPI_PROC_NULL) return MPI_SUCCESS;
+    Comm *c = C(comm);
+    if (dest < 0 || dest >= c->size) DIE("MPI_Isend: destination %d outside a communicator of %d", dest, c->size);
+    if (tag < 0) DIE("MPI_Isend: negative tag");
+    enqueue_send(c->ctx, c->world[dest], tag, buf, (size_t)count * dt_size(dt));
+    return MPI_SUCCESS;
+}
+int MPI_Issend(const void *buf, int count, MPI_Datatype dt, int dest, int tag, MPI_Comm comm, MPI_Request *req) { return MPI_Isend(buf, count, dt, dest, tag, comm, req); }
+int MPI_Send(const void *buf, int count, MPI_Datatype dt, int dest, int tag, MPI_Comm comm) {
+    MPI_Request r; MPI_Isend(buf, count, dt, dest, tag, comm, &r); g_reqs[r].used = 0; return MPI_SUCCESS;
+}
+int MPI_Bsend(const void *buf, int count, MPI_Datatype dt, int dest, int tag, MPI_Comm comm) { return MPI_Send(buf, count, dt, dest, tag, comm); }
+int MPI_Irecv(void *buf, int count, MPI_Datatype dt, int src, int tag, MPI_Comm comm, MPI_Request *req) {
+    Req *r = new_req(req);
+    r->is_recv = 1; r->comm = comm; r->buf = buf; r->cap = (size_t)count * dt_size(dt);
+    if (src == MPI_PROC_NULL) { r->done = 1; fill_status(&r->st, MPI_PROC_NULL, MPI_ANY_TAG, 0); return MPI_SUCCESS; }
+    Comm *c = C(comm);
+    if (src != MPI_ANY_SOURCE && (src < 0 || src >= c->size)) DIE("MPI_Irecv: source %d outside a communicator of %d", src, c->size);
+    r->ctx = c->ctx; r->src_world = src == MPI_ANY_SOURCE ? -1 : c->world[src]; r->tag = tag;
+    progress_once();
+    post_recv(&g_reqs[*req]);
+    return MPI_SUCCESS;
+}
+int MPI_Wait(MPI_Request *req, MPI_Status *st) {
+    if (*req == MPI_REQUEST_NULL) { fill_status(st, MPI_ANY_SOURCE, MPI_ANY_TAG, 0); return MPI_SUCCESS; }
+    const int h = *req;
+    while (!g_reqs[h].done) progress_wait();
+    if (st) { if (g_reqs[h].is_recv) *st = g_reqs[h].st; else fill_status(st, MPI_ANY_SOURCE, MPI_ANY_TAG, 0); }
+    g_reqs[h].used = 0;
+    *req = MPI_REQUEST_NULL;
+    return MPI_SUCCESS;
+}
+int MPI_Recv(void *buf, int count, MPI_Datatype dt, int src, int tag, MPI_Comm comm, MPI_Status *st) {
+    MPI_Request r; MPI_Irecv(buf, count, dt, src, tag, comm, &r); return MPI_Wait(&r, st);
+}
+int MPI_Sendrecv(const void *s, int sc, MPI_Datatype sdt, int dest, int stag, void *r, int rc, MPI_Datatype rdt,
+                 int src, int rtag, MPI_Comm comm, MPI_Status *status) {
+    MPI_Request rq; MPI_Irecv(r, rc, rdt, src, rtag, comm, &rq);
+    MPI_Send(s, sc, sdt, dest, stag, comm);
+    return MPI_Wait(&rq, status);
+}
+int MPI_Waitall(int n, MPI_Request reqs[], MPI_Status sts[]) {
+    for (int i = 0; i < n; ++i) MPI_Wait(&reqs[i], sts ? &sts[i] : MPI_STATUS_IGNORE);
+    return MPI_SUCCESS;
+}
+int MPI_Waitany(int n, MPI_Request reqs[], int *index, MPI_Status *st) {
+    int active = 0;
+    for (int i = 0; i < n; ++i) if (reqs[i] != MPI_REQUEST_NULL) active = 1;
+    if (!active) { *index = MPI_UNDEFINED; return MPI_SUCCESS; }
+    for (;;) {
+        for (int i = 0; i < n; ++i)
+            if (reqs[i] != MPI_REQUEST_NULL && g_reqs[reqs[i]].done) { *index = i; return MPI_Wait(&reqs[i], st); }
+        progress_wait();
+    }
+}
+int MPI_Test(MPI_Request *req, int *flag, MPI_Status *st) {
+    if (*req == MPI_REQUEST_NULL) { *flag = 1; fill_status(st, MPI_ANY_SOURCE, MPI_ANY_TAG, 0); return MPI_SUCCESS; }
+    /* Deviation kept on purpose: a successful test does NOT release the request.  The reference
+     * calls MPI_Test right after MPI_Irecv only to kick progress and later hands the same request
+     * array to MPI_Waitany / MPI_Waitall expecting every receive to be reported there
+     * (/root/reference/src/saena_matrix_matvec.cpp:33-35, :88); with eager delivery the message
+     * is often already here. */
+    if (!g_reqs[*req].done) progress_once();
+    *flag = g_reqs[*req].done;
+    if (*flag && st) { if (g_reqs[*req].is_recv) *st = g_reqs[*req].st; else fill_status(st, MPI_ANY_SOURCE, MPI_ANY_TAG, 0); }
+    return MPI_SUCCESS;
+}
+int MPI_Testall(int n, MPI_Request reqs[], int *flag, MPI_Status sts[]) {
+    progress_once();
+    for (int i = 0; i < n; ++i) if (reqs[i] != MPI_REQUEST_NULL && !g_reqs[reqs[i]].done) { *flag = 0; return MPI_SUCCESS; }
+    *flag = 1;
+    return MPI_Waitall(n, reqs, sts);
+}
+int MPI_Iprobe(int src, int tag, MPI_Comm comm, int *flag, MPI_Status *st) {
+    Comm *c = C(comm);
+    progress_once();
+    Msg *m = find_unexpected(c->ctx, src == MPI_ANY_SOURCE ? -1 : c->world[src], tag, 0);
+    *flag = m != NULL;
+    if (m) fill_status(st, comm_rank_of_world(c, m->src), m->tag, m->len);
+    return MPI_SUCCESS;
+}
+int MPI_Probe(int src, int tag, MPI_Comm comm, MPI_Status *st) {
+    for (;;) { int f = 0; MPI_Iprobe(src, tag, comm, &f, st); if (f) return MPI_SUCCESS; progress_wait(); }
+}
+int MPI_Request_free(MPI_Request *req) {
+    if (*req != MPI_REQUEST_NULL) {
+        Req *r = &g_reqs[*req];
+        if (r->is_recv && !r->done) DIE("MPI_Request_free on a pending receive is not supported");
+        r->used = 0;
+    }
+    *req = MPI_REQUEST_NULL;
+    return MPI_SUCCESS;
+}
+int MPI_Cancel(MPI_Request *req) {
+    if (*req != MPI_REQUEST_NULL) {
+        Req *r = &g_reqs[*req];
+        if (r->is_recv && !r->done) { unpost(r); r->done = 1; fill_status(&r->st, MPI_ANY_SOURCE, MPI_ANY_TAG, 0); }
+    }
+    return MPI_SUCCESS;
+}
+int MPI_Get_count(const MPI_Status *st, MPI_Datatype dt, int *count) { *count = (int)((size_t)st->count_bytes / dt_size(dt)); return MPI_SUCCESS; }
+
+/* ------------------------------------------------------------------ reductions */
+#define RED_LOOP(T, EXPR) do { const T *a = (const T *)in; T *b = (T *)inout; for (int i = 0; i < count; ++i) { T x = a[i], y = b[i]; b[i] = (EXPR); } } while (0)
+#define RED_ARITH(T) do { switch (op) { \
+    case MPI_SUM: RED_LOOP(T, x + y); break; case MPI_PROD: RED_LOOP(T, x * y); break; \
+    case MPI_MAX: RED_LOOP(T, x > y ? x : y); break; case MPI_MIN: RED_LOOP(T, x < y ? x : y); break; \
+    case MPI_LOR: RED_LOOP(T, (T)((x != 0) || (y != 0))); break; case MPI_LAND: RED_LOOP(T, (T)((x != 0) && (y != 0))); break; \
+    default: DIE("reduction op %d not defined for this type", op); } } while (0)
+#define RED_INT(T) do { switch (op) { \
+    case MPI_BOR: RED_LOOP(T, (T)(x | y)); break; case MPI_BAND: RED_LOOP(T, (T)(x & y)); break; default: RED_ARITH(T); } } while (0)
+#define RED_PAIR(VT) do { typedef struct { VT v; int i; } P; const P *a = (const P *)in; P *b = (P *)inout; \
+    for (int k = 0; k < count; ++k) { \
+        if (op == MPI_MAXLOC) { if (a[k].v > b[k].v || (a[k].v == b[k].v && a[k].i < b[k].i)) b[k] = a[k]; } \
+        else if (op == MPI_MINLOC) { if (a[k].v < b[k].v || (a[k].v == b[k].v && a[k].i < b[k].i)) b[k] = a[k]; } \
+        else DIE("only MAXLOC / MINLOC on pair types"); } } while (0)
+/* inout = in (op) inout, `in` being the contribution of the lower rank */
+static void reduce_local(const void *in, void *inout, int count, MPI_Datatype dt, MPI_Op op) {
+    if (op >= 100) { int c = count; MPI_Datatype d = dt; g_user_ops[op - 100]((void *)in, inout, &c, &d); return; }
+    switch (SBMPI_DT_KIND(dt)) {
+        case SBMPI_K_I8: RED_INT(signed char); break;
+        case SBMPI_K_U8: RED_INT(unsigned char); break;
+        case SBMPI_K_I16: RED_INT(short); break;
+        case SBMPI_K_U16: RED_INT(unsigned short); break;
+        case SBMPI_K_I32: RED_INT(int); break;
+        case SBMPI_K_U32: RED_INT(unsigned int); break;
+        case SBMPI_K_I64: RED_INT(long long); break;
+        case SBMPI_K_U64: RED_INT(unsigned long long); break;
+        case SBMPI_K_F32: RED_ARITH(float); break;
+        case SBMPI_K_F64: RED_ARITH(double); break;
+        case SBMPI_K_F128: RED_ARITH(long double); break;
+        case SBMPI_K_P_FLOAT_INT: RED_PAIR(float); break;
+        case SBMPI_K_P_DOUBLE_INT: RED_PAIR(double); break;
+        case SBMPI_K_P_LONG_INT: RED_PAIR(long); break;
+        case SBMPI_K_P_SHORT_INT: RED_PAIR(short); break;
+        case SBMPI_K_P_2INT: RED_PAIR(int); break;
+        default: DIE("reduction on datatype kind %d", SBMPI_DT_KIND(dt));
+    }
+}
+int MPI_Op_create(MPI_User_function *fn, int commute, MPI_Op *op) {
+    (void)commute;
+    if (g_n_user_ops >= 64) DIE("too many user ops");
+    g_user_ops[g_n_user_ops] = fn; *op = 100 + g_n_user_ops++;
+    return MPI_SUCCESS;
+}
+int MPI_Op_free(MPI_Op *op) { *op = MPI_OP_NULL; return MPI_SUCCESS; }
+
+/* ------------------------------------------------------------------ collectives */
+enum { T_BARRIER = -10, T_BCAST = -11, T_REDUCE = -12, T_GATHER = -13, T_SCATTER = -14, T_ALLTOALL = -15, T_SCAN = -16 };
+
+int MPI_Barrier(MPI_Comm comm) {
+    Comm *c = C(comm);
+    char z = 0;
+    if (c->size == 1) return MPI_SUCCESS;
+    if (c->rank == 0) {
+        for (int i = 1; i < c->size; ++i) { crecv(comm, i, T_BARRIER, &z, 1); c = C(comm); }
+        for (int i = 1; i < c->size; ++i) csend(c, i, T_BARRIER, &z, 1);
+    } else {
+        csend(c, 0, T_BARRIER, &z, 1);
+        crecv(comm, 0, T_BARRIER, &z, 1);
+    }
+    return MPI_SUCCESS;
+}
+int MPI_Bcast(void *buf, int count, MPI_Datatype dt, int root, MPI_Comm comm) {
+    Comm *c = C(comm);
+    const size_t n = (size_t)count * dt_size(dt);
+    if (c->size == 1) return MPI_SUCCESS;
+    if (c->rank == root) { for (int i = 0; i < c->size; ++i) if (i != root) csend(c, i, T_BCAST, buf, n); }
+    else crecv(comm, root, T_BCAST, buf, n);
+    return MPI_SUCCESS;
+}
+int MPI_Reduce(const void *s, void *r, int count, MPI_Datatype dt, MPI_Op op, int root, MPI_Comm comm) {
+    Comm *c = C(comm);
+    const size_t n = (size_t)count * dt_size(dt);
+    const void *mine = s == MPI_IN_PLACE ? r : s;
+    if (c->rank != root) { csend(c, root, T_REDUCE, mine, n); return MPI_SUCCESS; }
+    /* combine in rank order: acc = c_0 op c_1 op ... (deterministic; `in` = lower ranks' partial) */
+    char *acc = (char *)malloc(n ? n : 1), *tmp = (char *)malloc(n ? n : 1);
+    for (int i = 0; i < c->size; ++i) {
+        if (i == root) memcpy(tmp, mine, n); else { crecv(comm, i, T_REDUCE, tmp, n); c = C(comm); }
+        if (i == 0) memcpy(acc, tmp, n);
+        else { reduce_local(acc, tmp, count, dt, op); memcpy(acc, tmp, n); }
+    }
+    memcpy(r, acc, n);
+    free(acc); free(tmp);
+    return MPI_SUCCESS;
+}
+int MPI_Allreduce(const void *s, void *r, int count, MPI_Datatype dt, MPI_Op op, MPI_Comm comm) {
+    MPI_Reduce(s, r, count, dt, op, 0, comm);
+    return MPI_Bcast(r, count, dt, 0, comm);
+}
+static int scan_impl(const void *s, void *r, int count, MPI_Datatype dt, MPI_Op op, MPI_Comm comm, int exclusive) {
+    Comm *c = C(comm);
+    const size_t n = (size_t)count * dt_size(dt);
+    char *incl = (char *)malloc(n ? n : 1);   /* inclusive prefix of this rank */
+    memcpy(incl, s == MPI_IN_PLACE ? r : s, n);
+    if (c->rank > 0) {
+        char *prev = (char *)malloc(n ? n : 1);
+        crecv(comm, c->rank - 1, T_SCAN, prev, n); c = C(comm);
+        if (exclusive) memcpy(r, prev, n);
+        reduce_local(prev, incl, count, dt, op);
+        free(prev);
+    }
+    if (c->rank + 1 < c->size) csend(c, c->rank + 1, T_SCAN, incl, n);
+    if (!exclusive) memcpy(r, incl, n);
+    free(incl);
+    return MPI_SUCCESS;
+}
+int MPI_Scan(const void *s, void *r, int count, MPI_Datatype dt, MPI_Op op, MPI_Comm comm) { return scan_impl(s, r, count, dt, op, comm, 0); }
+int MPI_Exscan(const void *s, void *r, int count, MPI_Datatype dt, MPI_Op op, MPI_Comm comm) { return scan_impl(s, r, count, dt, op, comm, 1); }
+
+int MPI_Gatherv(const void *s, int sc, MPI_Datatype st, void *r, const int *rc, const int *displs, MPI_Datatype rt,
+                int root, MPI_Comm comm) {
+    Comm *c = C(comm);
+    if (c->rank != root) { csend(c, root, T_GATHER, s, (size_t)sc * dt_size(st)); return MPI_SUCCESS; }
+    const size_t es = dt_size(rt);
+    for (int i = 0; i < c->size; ++i) {
+        char *dst = (char *)r + (size_t)displs[i] * es;
+        if (i == root) { if (s != MPI_IN_PLACE) memmove(dst, s, (size_t)sc * dt_size(st)); }
+        else { crecv(comm, i, T_GATHER, dst, (size_t)rc[i] * es); c = C(comm); }
+    }
+    return MPI_SUCCESS;
+}
+int MPI_Gather(const void *s, int sc, MPI_Datatype st, void *r, int rc, MPI_Datatype rt, int root, MPI_Comm comm) {
+    Comm *c = C(comm);
+    if (c->rank != root) { csend(c, root, T_GATHER, s, (size_t)sc * dt_size(st)); return MPI_SUCCESS; }
+    const size_t blk = (size_t)rc * dt_size(rt);
+    for (int i = 0; i < c->size; ++i) {
+        char *dst = (char *)r + (size_t)i * blk;
+        if (i == root) { if (s != MPI_IN_PLACE) memmove(dst, s, (size_t)sc * dt_size(st)); }
+        else { crecv(comm, i, T_GATHER, dst, blk); c = C(comm); }
+    }
+    return MPI_SUCCESS;
+}
+int MPI_Allgather(const void *s, int sc, MPI_Datatype st, void *r, int rc, MPI_Datatype rt, MPI_Comm comm) {
+    Comm *c = C(comm);
+    const size_t blk = (size_t)rc * dt_size(rt);
+    if (s == MPI_IN_PLACE) { s = (char *)r + (size_t)c->rank * blk; sc = rc; st = rt; }
+    MPI_Gather(s, sc, st, r, rc, rt, 0, comm);
+    c = C(comm);
+    return MPI_Bcast(r, (int)(blk * (size_t)c->size), MPI_BYTE, 0, comm);
+}
+int MPI_Allgatherv(const void *s, int sc, MPI_Datatype st, void *r, const int *rc, const int *displs, MPI_Datatype rt,
+                   MPI_Comm comm) {
+    Comm *c = C(comm);
+    const size_t es = dt_size(rt);
+    if (s == MPI_IN_PLACE) { s = (char *)r + (size_t)displs[c->rank] * es; sc = rc[c->rank]; st = rt; }
+    MPI_Gatherv(s, sc, st, r, rc, displs, rt, 0, comm);
+    c = C(comm);
+    /* the blocks may leave gaps: broadcast block by block */
+    for (int i = 0; i < c->size; ++i) { MPI_Bcast((char *)r + (size_t)displs[i] * es, (int)((size_t)rc[i] * es), MPI_BYTE, 0, comm); c = C(comm); }
+    return MPI_SUCCESS;
+}
+int MPI_Scatterv(const void *s, const int *sc, const int *displs, MPI_Datatype st, void *r, int rc, MPI_Datatype rt,
+                 int root, MPI_Comm comm) {
+    Comm *c = C(comm);
+    if (c->rank == root) {
+        const size_t es = dt_size(st);
+        for (int i = 0; i < c->size; ++i) {
+            const char *src = (const char *)s + (size_t)displs[i] * es;
+            if (i == root) { if (r != MPI_IN_PLACE) memmove(r, src, (size_t)sc[i] * es); }
+            else csend(c, i, T_SCATTER, src, (size_t)sc[i] * es);
+        }
+    } else crecv(comm, root, T_SCATTER, r, (size_t)rc * dt_size(rt));
+    return MPI_SUCCESS;
+}
+int MPI_Alltoallv(const void *s, const int *sc, const int *sd, MPI_Datatype st, void *r, const int *rc, const int *rd,
+                  MPI_Datatype rt, MPI_Comm comm) {
+    Comm *c = C(comm);
+    const size_t ss = dt_size(st), rs = dt_size(rt);
+    const int n = c->size;
+    for (int i = 0; i < n; ++i) csend(c, i, T_ALLTOALL, (const char *)s + (size_t)sd[i] * ss, (size_t)sc[i] * ss);
+    for (int i = 0; i < n; ++i) { crecv(comm, i, T_ALLTOALL, (char *)r + (size_t)rd[i] * rs, (size_t)rc[i] * rs); }
+    return MPI_SUCCESS;
+}
+int MPI_Alltoall(const void *s, int sc, MPI_Datatype st, void *r, int rc, MPI_Datatype rt, MPI_Comm comm) {
+    Comm *c = C(comm);
+    const size_t sb = (size_t)sc * dt_size(st), rb = (size_t)rc * dt_size(rt);
+    const int n = c->size;
+    for (int i = 0; i < n; ++i) csend(c, i, T_ALLTOALL, (const char *)s + (size_t)i * sb, sb);
+    for (int i = 0; i < n; ++i) crecv(comm, i, T_ALLTOALL, (char *)r + (size_t)i * rb, rb);
+    return MPI_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ datatypes */
+int MPI_Type_contiguous(int count, MPI_Datatype old, MPI_Datatype *newt) {
+    const size_t n = (size_t)count * dt_size(old);
+    if (n > 0xFFFFFF) DIE("derived datatype larger than 16 MB");
+    *newt = SBMPI_DT(SBMPI_K_DERIVED, (int)n);
+    return MPI_SUCCESS;
+}
+int MPI_Type_create_struct(int n, const int bl[], const MPI_Aint disp[], const MPI_Datatype types[], MPI_Datatype *newt) {
+    long end = 0, align = 1;
+    for (int i = 0; i < n; ++i) {
+        const long sz = (long)dt_size(types[i]);
+        const long e = (long)disp[i] + (long)bl[i] * sz;
+        if (e > end) end = e;
+        const long a = sz > 8 ? 8 : sz;
+        if (a > align) align = a;
+    }
+    *newt = SBMPI_DT(SBMPI_K_DERIVED, (int)((end + align - 1) / align * align));
+    return MPI_SUCCESS;
+}
+int MPI_Type_commit(MPI_Datatype *dt) { (void)dt; return MPI_SUCCESS; }
+int MPI_Type_free(MPI_Datatype *dt) { *dt = MPI_DATATYPE_NULL; return MPI_SUCCESS; }
+int MPI_Type_size(MPI_Datatype dt, int *size) { *size = (int)dt_size(dt); return MPI_SUCCESS; }
+
+/* ------------------------------------------------------------------ memory, windows (unused by the solve path), files */
+int MPI_Alloc_mem(MPI_Aint size, MPI_Info info, void *baseptr) { (void)info; *(void **)baseptr = malloc((size_t)size); return MPI_SUCCESS; }
+int MPI_Free_mem(void *base) { free(base); return MPI_SUCCESS; }
+struct mpi_serial_win { int unused; };
+int MPI_Win_create(void *base, MPI_Aint size, int disp_unit, MPI_Info info, MPI_Comm comm, MPI_Win *win) {
+    (void)base; (void)size; (void)disp_unit; (void)info; (void)comm; (void)win;
+    DIE("MPI one-sided communication is not provided by this stand-in");
+    return MPI_ERR_OTHER;
+}
+int MPI_Win_fence(int assert_, MPI_Win win) { (void)assert_; (void)win; DIE("MPI_Win_fence"); return MPI_ERR_OTHER; }
+int MPI_Win_free(MPI_Win *win) { (void)win; return MPI_SUCCESS; }
+int MPI_Put(const void *origin, int ocount, MPI_Datatype odt, int target, MPI_Aint tdisp, int tcount, MPI_Datatype tdt, MPI_Win win) {
+    (void)origin; (void)ocount; (void)odt; (void)target; (void)tdisp; (void)tcount; (void)tdt; (void)win;
+    DIE("MPI_Put"); return MPI_ERR_OTHER;
+}
+struct mpi_serial_file { FILE *f; };
+int MPI_File_open(MPI_Comm comm, const char *name, int amode, MPI_Info info, MPI_File *fh) {
+    (void)comm; (void)info;
+    FILE *f = fopen(name, (amode & MPI_MODE_RDONLY) ? "rb" : ((amode & MPI_MODE_CREATE) ? "wb+" : "rb+"));
+    if (!f) { *fh = NULL; return MPI_ERR_OTHER; }
+    *fh = (MPI_File)malloc(sizeof(struct mpi_serial_file));
+    (*fh)->f = f;
+    return MPI_SUCCESS;
+}
+int MPI_File_read_at(MPI_File fh, MPI_Offset off, void *buf, int count, MPI_Datatype dt, MPI_Status *st) {
+    fseeko(fh->f, (off_t)off, SEEK_SET);
+    size_t n = fread(buf, dt_size(dt), (size_t)count, fh->f);
+    fill_status(st, 0, 0, n * dt_size(dt));
+    return MPI_SUCCESS;
+}
+int MPI_File_write_at(MPI_File fh, MPI_Offset off, const void *buf, int count, MPI_Datatype dt, MPI_Status *st) {
+    fseeko(fh->f, (off_t)off, SEEK_SET);
+    size_t n = fwrite(buf, dt_size(dt), (size_t)count, fh->f);
+    fill_status(st, 0, 0, n * dt_size(dt));
+    return MPI_SUCCESS;
+}
+int MPI_File_close(MPI_File *fh) { if (*fh) { fclose((*fh)->f); free(*fh); *fh = NULL; } return MPI_SUCCESS; }
