@@ -1,0 +1,38 @@
+"""One rank of a multi-rank run of the compiled reference (TEST INFRASTRUCTURE):
+
+    python -m oracle.mprun -n 4 python -m oracle.mp_worker poisson 14 /tmp/out [reps]
+
+Every rank runs experiments/Poisson.cpp's sequence through oracle/ref_harness.cpp on
+MPI_COMM_WORLD (the multi-process stand-in of ref_shim_mp/), solves with solve_pCG, and writes
+<out>/rank<r>.npz: its rows of the solution, the residual history, the iteration count, its share of
+the hierarchy (the reference's own per-rank arrays) and the wall time of `reps` timed solves."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import ref  # noqa: E402
+
+
+def main():
+    what, mx, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+    reps = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    L = ref.lib()
+    rank, size = L.sref_rank(), L.sref_size()
+    assert what == "poisson"
+    s = ref.RefSolver.poisson(mx)
+    u, iters, hist = s.solve_pcg()
+    res = dict(u=u, iters=np.array([iters]), hist=hist, rank=np.array([rank]), size=np.array([size]))
+    if reps:
+        res["sec_per_solve"] = np.array([s.time_solve_pcg(reps) / reps])
+    os.makedirs(out, exist_ok=True)
+    np.savez(os.path.join(out, f"rank{rank}.npz"), **res)
+    s.close()
+    L.sref_barrier()
+    L.sref_finalize()
+
+
+if __name__ == "__main__":
+    main()

@@ -17,7 +17,14 @@ import numpy as np
 from saena_b200.hierarchy import (F64, I32, KIND_A, KIND_P, KIND_R, Hierarchy, Level, Operator)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libsaena_ref.so")
+# the ranks of `python -m oracle.mprun` (SBMPI_SIZE set) load the build against the multi-process MPI
+# stand-in (make -C oracle ref_mp); everything else the one-rank build
+MP_LIB_PATH = os.path.join(_HERE, "_ref", "libsaena_ref_mp.so")
+LIB_PATH = MP_LIB_PATH if os.environ.get("SBMPI_SIZE") else os.path.join(_HERE, "_ref", "libsaena_ref.so")
+
+
+def mp_available() -> bool:
+    return os.path.exists(MP_LIB_PATH)
 
 # field ids of sref_array (ref_harness.cpp)
 F_NNZ_PER_ROW_LOCAL, F_COL_LOCAL, F_VAL_LOCAL, F_INV_DIAG, F_SPLIT, F_SPLIT_NEW = range(6)
@@ -84,6 +91,8 @@ def lib():
         L.sref_array.restype = ctypes.c_long
         L.sref_dot.restype = ctypes.c_double
         L.sref_time_solve_pcg.restype = ctypes.c_double
+        if hasattr(L, "sref_wtime"):
+            L.sref_wtime.restype = ctypes.c_double
         _lib = L
     return _lib
 

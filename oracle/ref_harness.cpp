@@ -154,6 +154,13 @@ void *sref_coo_new(int n, long nnz, const int *row, const int *col, const double
     return h;
 }
 
+// multi-rank runs (oracle/mprun.py): who am I, and a clean shutdown of the MPI stand-in
+int sref_rank() { ensure_mpi(); int r = 0; MPI_Comm_rank(MPI_COMM_WORLD, &r); return r; }
+int sref_size() { ensure_mpi(); int s = 1; MPI_Comm_size(MPI_COMM_WORLD, &s); return s; }
+void sref_barrier() { ensure_mpi(); MPI_Barrier(MPI_COMM_WORLD); }
+double sref_wtime() { return MPI_Wtime(); }
+void sref_finalize() { int inited = 0; MPI_Initialized(&inited); if (inited) MPI_Finalize(); }
+
 void sref_free(void *hv) {
     Handle *h = (Handle *)hv;
     if (!h) return;
