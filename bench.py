@@ -104,9 +104,51 @@ class ClockSampler:
 # oracle/_ref by oracle/Makefile), one MPI rank = one core (no MPI in this image; the reference's
 # OpenMP is off by default, CMakeLists.txt:27).  Falls back to the C oracle port.
 # ------------------------------------------------------------------------------------------------
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_solve_multirank(reps: int, warmup: int, ranks: int, mx: int):
+    """The reference's own MPI solve on `ranks` host cores: the UNMODIFIED sources built against the
+    multi-process MPI stand-in (oracle/ref_shim_mp, make -C oracle ref_mp), one process per rank started
+    by oracle/mprun.py -- row partitioning, float halo, repartition / shrink, distributed setup and all."""
+    import shutil
+    import tempfile
+    from oracle import mprun
+    out = tempfile.mkdtemp(prefix="saena_ref_mp_")
+    try:
+        t = time.perf_counter()
+        rc = mprun.run(ranks, [sys.executable, "-m", "oracle.mp_worker", "poisson", str(mx), out, str(max(reps, 1)),
+                               str(warmup)], timeout=600, env=dict(os.environ, PYTHONPATH=ROOT))
+        wall = time.perf_counter() - t
+        if rc:
+            raise RuntimeError(f"multi-rank reference run exited with {rc}")
+        parts = [np.load(os.path.join(out, f"rank{r}.npz")) for r in range(ranks)]
+    finally:
+        shutil.rmtree(out, ignore_errors=True)
+    sec = max(float(p["sec_per_solve"][0]) for p in parts)   # max over ranks, as Poisson.cpp:216-246 reports
+    iters = int(parts[0]["iters"][0])
+    n = (mx - 2) ** 3
+    what = (f"the reference's own solve_pCG (oracle/_ref/libsaena_ref_mp.so = unmodified paralab/Saena sources, -Ofast) "
+            f"on {ranks} MPI ranks = {ranks} host cores (multi-process MPI stand-in over Unix sockets, oracle/ref_shim_mp), "
+            f"3D Poisson {mx - 2}^3 = {n} unknowns (laplacian3D mx={mx}), same options; {reps} solves, {iters} "
+            f"iterations each, max over ranks; setup + warm-up not timed (whole run {wall:.0f} s)")
+    return dict(value=n / sec / 1e6, unit=UNIT, cores=ranks, kind="reference", sample=what), sec, iters, n
+
+
 def cpu_reference_solve(reps: int, warmup: int = 0, mx: int = CPU_SAMPLE_MX):
     from oracle import ref
     n = (mx - 2) ** 3
+    ranks = min(host_cores(), int(os.environ.get("SAENA_BENCH_CPU_RANKS", 16)))
+    if ref.mp_available() and ranks > 1:
+        try:
+            # a larger sample than the one-rank arm: 64^3 unknowns keep >= 16 k rows per rank at 16 ranks
+            return cpu_reference_solve_multirank(reps, warmup, ranks, int(os.environ.get("SAENA_BENCH_CPU_MX_MP", 66)))
+        except Exception as e:   # fall back to the one-rank build below
+            log(f"[reference arm] multi-rank run failed ({e!r}); falling back to one rank")
     if ref.available():
         t = time.perf_counter()
         s = ref.RefSolver.poisson(mx)
@@ -143,8 +185,9 @@ def run_reference_arm(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D 7-point Poisson AMG-PCG, bounded sample {CPU_SAMPLE_MX - 2}^3 unknowns of the "
-                                   f"256^3 workload", "options": "data/options006_poisson.xml values"},
+            "config": {"workload": f"3D 7-point Poisson AMG-PCG, bounded sample {round(n ** (1 / 3))}^3 unknowns of the "
+                                   f"256^3 workload, {base['cores']} host core(s)",
+                       "options": "data/options006_poisson.xml values"},
             "iterations": iters, "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

@@ -19,6 +19,7 @@ from oracle import ref  # noqa: E402
 def main():
     what, mx, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
     reps = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    warmup = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     L = ref.lib()
     rank, size = L.sref_rank(), L.sref_size()
     assert what == "poisson"
@@ -26,6 +27,9 @@ def main():
     u, iters, hist = s.solve_pcg()
     res = dict(u=u, iters=np.array([iters]), hist=hist, rank=np.array([rank]), size=np.array([size]))
     if reps:
+        for _ in range(warmup):
+            s.time_solve_pcg(1)
+        L.sref_barrier()   # MPI_Barrier before the timed region, as experiments/Poisson.cpp:216-246
         res["sec_per_solve"] = np.array([s.time_solve_pcg(reps) / reps])
     os.makedirs(out, exist_ok=True)
     np.savez(os.path.join(out, f"rank{rank}.npz"), **res)

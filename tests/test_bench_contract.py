@@ -7,8 +7,18 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_arm_prints_one_contract_line():
-    env = dict(os.environ, SAENA_BENCH_CPU_MX="12")   # 10^3 unknowns: a second instead of half a minute
+import pytest
+
+
+@pytest.mark.parametrize("ranks", [1, 3])
+def test_reference_arm_prints_one_contract_line(ranks):
+    # 10^3 / 16^3 unknowns: seconds instead of half a minute; ranks > 1 = the reference on several MPI ranks
+    # (multi-process MPI stand-in), what the arm uses on a multi-core host
+    env = dict(os.environ, SAENA_BENCH_CPU_MX="12", SAENA_BENCH_CPU_MX_MP="18", SAENA_BENCH_CPU_RANKS=str(ranks))
+    if ranks > 1:
+        from oracle import ref
+        if not ref.mp_available():
+            pytest.skip("oracle/_ref/libsaena_ref_mp.so not built (make -C oracle ref_mp)")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
                           "--warmup", "1"], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -19,7 +29,8 @@ def test_reference_arm_prints_one_contract_line():
     for k in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config",
               "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["cpu_baseline"]["cores"] == (ranks if d["cpu_baseline"]["kind"] == "reference" else 1)
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
     assert "workload" in d["config"]
 
