@@ -26,6 +26,28 @@ def main():
     s = ref.RefSolver.poisson(mx)
     u, iters, hist = s.solve_pcg()
     res = dict(u=u, iters=np.array([iters]), hist=hist, rank=np.array([rank]), size=np.array([size]))
+    if os.environ.get("SAENA_MP_DUMP"):
+        # this rank's share of the hierarchy (the reference's own arrays, ranks translated to world ranks)
+        # and the reference's own operators applied to slices of seeded global vectors
+        from saena_b200.hierarchy import hierarchy_to_arrays
+        h = s.hierarchy()
+        res.update({"hier." + k: v for k, v in hierarchy_to_arrays(h).items()})
+        res["rhs"] = s.rhs()
+        for l, lv in enumerate(h.levels):
+            if lv.A.M == 0 and not lv.active:
+                continue
+            g = np.random.default_rng(1000 + l)
+            v_all, b_all = g.uniform(-1, 1, lv.A.Mbig), g.uniform(-1, 1, lv.A.Mbig)
+            r0 = lv.A.row_offset
+            v, b = v_all[r0:r0 + lv.A.M], b_all[r0:r0 + lv.A.M]
+            res[f"out.L{l}.A_matvec"] = s.matvec(l, 0, v)
+            res[f"out.L{l}.chebyshev3"] = s.smooth(l, "chebyshev", 3, v, b)
+            res[f"out.L{l}.jacobi2"] = s.smooth(l, "jacobi", 2, v, b)
+            if lv.P is not None:
+                vc_all = g.uniform(-1, 1, lv.P.Nbig)
+                vc = vc_all[lv.P.col_offset:lv.P.col_offset + lv.P.n_local_cols]
+                res[f"out.L{l}.P_matvec"] = s.matvec(l, 1, vc)
+                res[f"out.L{l}.R_matvec"] = s.matvec(l, 2, v)
     if reps:
         for _ in range(warmup):
             s.time_solve_pcg(1)

@@ -30,6 +30,7 @@ def mp_available() -> bool:
 F_NNZ_PER_ROW_LOCAL, F_COL_LOCAL, F_VAL_LOCAL, F_INV_DIAG, F_SPLIT, F_SPLIT_NEW = range(6)
 F_ROW_REMOTE, F_VAL_REMOTE, F_NNZ_PER_COL_REMOTE, F_ENTRY_ROW, F_ENTRY_COL, F_ENTRY_VAL = range(6, 12)
 F_INV_SQ_DIAG_ORIG = 12
+F_VINDEX, F_SEND_PROC_RANK, F_SEND_PROC_COUNT, F_VDISPLS, F_RECV_PROC_RANK, F_RECV_PROC_COUNT, F_RDISPLS = range(13, 20)
 
 
 class _Opts(ctypes.Structure):
@@ -155,19 +156,91 @@ class RefSolver:
             lib().sref_array(self._h, l, kind, field, _p(out))
         return out
 
+    # ---- several ranks (python -m oracle.mprun): ranks of a level's plans are ranks of that level's
+    #      communicator, which shrinks as the levels get small; everything is translated to WORLD ranks
+    @property
+    def world_size(self) -> int:
+        return int(lib().sref_size())
+
+    @property
+    def world_rank(self) -> int:
+        return int(lib().sref_rank())
+
+    def level_comm(self, l) -> np.ndarray:
+        """world ranks of the members of level l's communicator, in its rank order ([] if not a member)"""
+        out = np.zeros(self.world_size, I32)
+        n = lib().sref_level_comm(self._h, int(l), _p(out))
+        return out[:n].copy()
+
     def _operator(self, l, kind) -> Operator:
         info = self._info(l, kind)
-        assert info.nnz_remote == 0, "one-rank reference: no remote part expected"
-        return Operator(kind=kind, level=l, M=info.M, Mbig=info.Mbig, Nbig=info.Nbig, row_offset=0, col_offset=0,
-                        n_local_cols=info.Nbig,
+        W, me = self.world_size, self.world_rank
+        if W == 1:
+            assert info.nnz_remote == 0, "one-rank reference: no remote part expected"
+            return Operator(kind=kind, level=l, M=info.M, Mbig=info.Mbig, Nbig=info.Nbig, row_offset=0, col_offset=0,
+                            n_local_cols=info.Nbig,
+                            nnzPerRow_local=self._arr(l, kind, F_NNZ_PER_ROW_LOCAL, I32),
+                            col_local=self._arr(l, kind, F_COL_LOCAL, I32),
+                            val_local=self._arr(l, kind, F_VAL_LOCAL, F64),
+                            use_double=bool(info.use_double))
+        comm = self.level_comm(l)
+        if len(comm) == 0:   # not a member of this level's communicator: an empty operator
+            return Operator(kind=kind, level=l, M=0, Mbig=0, Nbig=0, row_offset=0, col_offset=0, n_local_cols=0,
+                            nnzPerRow_local=np.zeros(0, I32), col_local=np.zeros(0, I32), val_local=np.zeros(0, F64),
+                            nnzPerProcScan=np.zeros(W + 1, np.int64), vdispls=np.zeros(W, I32), rdispls=np.zeros(W, I32),
+                            use_double=bool(info.use_double), nprocs=W, rank=me)
+        rl = int(np.flatnonzero(comm == me)[0])
+        # row / column partitions: the fine side is A's split, the coarse side splitNew (the partition R
+        # writes into, before Grid::repart_u); P and R do not each fill both of their own copies
+        fine = self._arr(l, KIND_A, F_SPLIT, I32)
+        if kind == KIND_A:
+            rsp = csp = fine
+        else:
+            coarse = self._arr(l, KIND_P, F_SPLIT_NEW, I32)
+            if len(coarse) == 0:
+                coarse = self._arr(l, KIND_R, F_SPLIT_NEW, I32)
+            rsp, csp = (fine, coarse) if kind == KIND_P else (coarse, fine)
+
+        def to_world(per_comm_rank):
+            out = np.zeros(W, I32)
+            if len(per_comm_rank) >= len(comm):   # (a one-rank communicator builds no plan at all)
+                out[comm] = per_comm_rank[:len(comm)]
+            return out
+
+        npc = self._arr(l, kind, F_NNZ_PER_COL_REMOTE, I32)
+        rpr, rpc = self._arr(l, kind, F_RECV_PROC_RANK, I32), self._arr(l, kind, F_RECV_PROC_COUNT, I32)
+        rdis = self._arr(l, kind, F_RDISPLS, I32)
+        # entries of the remote block per sender (world order == communicator order for contiguous blocks)
+        scan = np.zeros(W + 1, np.int64)
+        csum = np.concatenate(([0], np.cumsum(npc))).astype(np.int64)
+        for p, c in zip(rpr, rpc):
+            scan[comm[p] + 1] = csum[rdis[p] + c] - csum[rdis[p]]
+        scan = np.cumsum(scan)
+        return Operator(kind=kind, level=l, M=info.M, Mbig=info.Mbig, Nbig=info.Nbig,
+                        row_offset=int(rsp[rl]), col_offset=int(csp[rl]), n_local_cols=int(csp[rl + 1] - csp[rl]),
                         nnzPerRow_local=self._arr(l, kind, F_NNZ_PER_ROW_LOCAL, I32),
-                        col_local=self._arr(l, kind, F_COL_LOCAL, I32),
-                        val_local=self._arr(l, kind, F_VAL_LOCAL, F64),
-                        use_double=bool(info.use_double))
+                        col_local=self._arr(l, kind, F_COL_LOCAL, I32), val_local=self._arr(l, kind, F_VAL_LOCAL, F64),
+                        row_remote=self._arr(l, kind, F_ROW_REMOTE, I32), val_remote=self._arr(l, kind, F_VAL_REMOTE, F64),
+                        nnzPerCol_remote=npc, nnzPerProcScan=scan,
+                        vIndex=self._arr(l, kind, F_VINDEX, I32),
+                        vdispls=to_world(self._arr(l, kind, F_VDISPLS, I32)), rdispls=to_world(rdis),
+                        sendProcRank=comm[self._arr(l, kind, F_SEND_PROC_RANK, I32)].astype(I32),
+                        sendProcCount=self._arr(l, kind, F_SEND_PROC_COUNT, I32),
+                        recvProcRank=comm[rpr].astype(I32), recvProcCount=rpc,
+                        use_double=bool(info.use_double), nprocs=W, rank=me)
+
+    def _repart(self, l, which, comm):
+        n = lib().sref_repart_plan(self._h, int(l), which, None, None, None)
+        peer, off, cnt = np.zeros(n, I32), np.zeros(n, I32), np.zeros(n, I32)
+        if n:
+            lib().sref_repart_plan(self._h, int(l), which, _p(peer), _p(off), _p(cnt))
+        return [(int(comm[p]), int(o), int(c)) for p, o, c in zip(peer, off, cnt)]
 
     def hierarchy(self) -> Hierarchy:
+        """This rank's share of the hierarchy, in the layout the C ABI takes (world ranks everywhere)."""
         ml = self.max_level
         scale = bool(lib().sref_scale(self._h))
+        W = self.world_size
         levels = []
         for l in range(ml + 1):
             info = self._info(l, KIND_A)
@@ -178,13 +251,23 @@ class RefSolver:
                 lv.R = self._operator(l, KIND_R)
                 lv.M_coarse_old = lv.R.M
                 lv.M_coarse = lv.R.M
+                if W > 1:
+                    mo, mn = ctypes.c_int(0), ctypes.c_int(0)
+                    lib().sref_coarse_sizes(self._h, l, ctypes.byref(mo), ctypes.byref(mn))
+                    lv.M_coarse_old, lv.M_coarse = mo.value, mn.value
+                    comm = self.level_comm(l)
+                    if len(comm):
+                        lv.repart_send = self._repart(l, 0, comm)
+                        lv.repart_recv = self._repart(l, 1, comm)
             if scale:
                 lv.inv_sq_diag = self._arr(l, KIND_A, F_INV_SQ_DIAG_ORIG, F64)
             levels.append(lv)
-        h = Hierarchy(levels=levels, scale=scale, coarse_n=levels[-1].A.Mbig,
-                      coarse_row=self._arr(ml, KIND_A, F_ENTRY_ROW, I32),
-                      coarse_col=self._arr(ml, KIND_A, F_ENTRY_COL, I32),
-                      coarse_val=self._arr(ml, KIND_A, F_ENTRY_VAL, F64))
+        coarse_n = int(self._info(ml, KIND_A).Mbig)
+        h = Hierarchy(levels=levels, scale=scale, coarse_n=coarse_n,
+                      coarse_row=self._arr(ml, KIND_A, F_ENTRY_ROW, I32) if coarse_n else np.zeros(0, I32),
+                      coarse_col=self._arr(ml, KIND_A, F_ENTRY_COL, I32) if coarse_n else np.zeros(0, I32),
+                      coarse_val=self._arr(ml, KIND_A, F_ENTRY_VAL, F64) if coarse_n else np.zeros(0, F64))
+        h.nprocs, h.rank = W, self.world_rank
         return h
 
     def rhs(self) -> np.ndarray:

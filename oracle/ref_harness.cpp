@@ -194,6 +194,8 @@ int sref_level_info_get(void *hv, int l, int kind, sref_level_info *out) {
     memset(out, 0, sizeof(*out));
     if (l < 0 || l > obj(h)->max_level) return 1;
     Grid &g = obj(h)->grids[l];
+    // a rank that a shrink left out of this level's communicator owns nothing of it
+    if (!g.A || !g.A->active || (kind != 0 && !g.active)) { out->use_double = 1; return 0; }
     if (kind == 0) {
         saena_matrix *A = g.A;
         out->M = A->M; out->Mbig = A->Mbig; out->Nbig = A->Mbig;
@@ -224,12 +226,16 @@ int sref_level_info_get(void *hv, int l, int kind, sref_level_info *out) {
 // field ids for sref_array
 enum { F_NNZ_PER_ROW_LOCAL = 0, F_COL_LOCAL = 1, F_VAL_LOCAL = 2, F_INV_DIAG = 3, F_SPLIT = 4, F_SPLIT_NEW = 5,
        F_ROW_REMOTE = 6, F_VAL_REMOTE = 7, F_NNZ_PER_COL_REMOTE = 8, F_ENTRY_ROW = 9, F_ENTRY_COL = 10,
-       F_ENTRY_VAL = 11, F_INV_SQ_DIAG_ORIG = 12 };
+       F_ENTRY_VAL = 11, F_INV_SQ_DIAG_ORIG = 12,
+       // the halo plan (ranks are ranks of the LEVEL's communicator: see sref_level_comm)
+       F_VINDEX = 13, F_SEND_PROC_RANK = 14, F_SEND_PROC_COUNT = 15, F_VDISPLS = 16, F_RECV_PROC_RANK = 17,
+       F_RECV_PROC_COUNT = 18, F_RDISPLS = 19 };
 
 // Copies one layout array of an operator into `dst` (if non-null) and returns its element count.
 long sref_array(void *hv, int l, int kind, int field, void *dst) {
     Handle *h = (Handle *)hv;
     Grid &g = obj(h)->grids[l];
+    if (!g.A || !g.A->active || (kind != 0 && !g.active)) return 0;
 #define COPY_VEC(v) do { if (dst && !(v).empty()) memcpy(dst, (v).data(), (v).size() * sizeof((v)[0])); \
                          return (long)(v).size(); } while (0)
 #define COPY_PTR(p, n) do { if (dst && (n) > 0) memcpy(dst, (p), (size_t)(n) * sizeof((p)[0])); return (long)(n); } while (0)
@@ -247,6 +253,13 @@ long sref_array(void *hv, int l, int kind, int field, void *dst) {
             case F_ROW_REMOTE: COPY_PTR(A->row_remote, A->nnz_l_remote);
             case F_VAL_REMOTE: COPY_PTR(A->val_remote, A->nnz_l_remote);
             case F_NNZ_PER_COL_REMOTE: COPY_VEC(A->nnzPerCol_remote);
+            case F_VINDEX: COPY_VEC(A->vIndex);
+            case F_SEND_PROC_RANK: COPY_VEC(A->sendProcRank);
+            case F_SEND_PROC_COUNT: COPY_VEC(A->sendProcCount);
+            case F_VDISPLS: COPY_VEC(A->vdispls);
+            case F_RECV_PROC_RANK: COPY_VEC(A->recvProcRank);
+            case F_RECV_PROC_COUNT: COPY_VEC(A->recvProcCount);
+            case F_RDISPLS: COPY_VEC(A->rdispls);
             case F_ENTRY_ROW: COPY_ENTRY(A->entry, row, int);
             case F_ENTRY_COL: COPY_ENTRY(A->entry, col, int);
             case F_ENTRY_VAL: COPY_ENTRY(A->entry, val, double);
@@ -263,6 +276,13 @@ long sref_array(void *hv, int l, int kind, int field, void *dst) {
             case F_ROW_REMOTE: COPY_VEC(P.row_remote);
             case F_VAL_REMOTE: COPY_VEC(P.val_remote);
             case F_NNZ_PER_COL_REMOTE: COPY_VEC(P.nnzPerCol_remote);
+            case F_VINDEX: COPY_VEC(P.vIndex);
+            case F_SEND_PROC_RANK: COPY_VEC(P.sendProcRank);
+            case F_SEND_PROC_COUNT: COPY_VEC(P.sendProcCount);
+            case F_VDISPLS: COPY_VEC(P.vdispls);
+            case F_RECV_PROC_RANK: COPY_VEC(P.recvProcRank);
+            case F_RECV_PROC_COUNT: COPY_VEC(P.recvProcCount);
+            case F_RDISPLS: COPY_VEC(P.rdispls);
             case F_ENTRY_ROW: COPY_ENTRY(P.entry, row, int);
             case F_ENTRY_COL: COPY_ENTRY(P.entry, col, int);
             case F_ENTRY_VAL: COPY_ENTRY(P.entry, val, double);
@@ -279,6 +299,13 @@ long sref_array(void *hv, int l, int kind, int field, void *dst) {
             case F_ROW_REMOTE: COPY_VEC(R.row_remote);
             case F_VAL_REMOTE: COPY_VEC(R.val_remote);
             case F_NNZ_PER_COL_REMOTE: COPY_VEC(R.nnzPerCol_remote);
+            case F_VINDEX: COPY_VEC(R.vIndex);
+            case F_SEND_PROC_RANK: COPY_VEC(R.sendProcRank);
+            case F_SEND_PROC_COUNT: COPY_VEC(R.sendProcCount);
+            case F_VDISPLS: COPY_VEC(R.vdispls);
+            case F_RECV_PROC_RANK: COPY_VEC(R.recvProcRank);
+            case F_RECV_PROC_COUNT: COPY_VEC(R.recvProcCount);
+            case F_RDISPLS: COPY_VEC(R.rdispls);
             case F_ENTRY_ROW: COPY_ENTRY(R.entry, row, int);
             case F_ENTRY_COL: COPY_ENTRY(R.entry, col, int);
             case F_ENTRY_VAL: COPY_ENTRY(R.entry, val, double);
@@ -288,6 +315,42 @@ long sref_array(void *hv, int l, int kind, int field, void *dst) {
 #undef COPY_VEC
 #undef COPY_PTR
 #undef COPY_ENTRY
+}
+
+// The communicator of level l (it shrinks as the levels get small, saena_matrix_shrink.cpp): the WORLD
+// ranks of its members in its own rank order; every rank number in that level's halo plans and
+// splits refers to this order.  Returns the size (0 on a rank that is not a member).  Collective
+// over the level's communicator.
+int sref_level_comm(void *hv, int l, int *world_ranks) {
+    Handle *h = (Handle *)hv;
+    Grid &g = obj(h)->grids[l];
+    if (!g.A || !g.A->active) return 0;
+    int n = 0, me = 0;
+    MPI_Comm_size(g.A->comm, &n);
+    MPI_Comm_rank(MPI_COMM_WORLD, &me);
+    MPI_Allgather(&me, 1, MPI_INT, world_ranks, 1, MPI_INT, g.A->comm);
+    return n;
+}
+
+// Grid::repart_u's plan of level l (grid.cpp:3-97; ranks of the level's communicator): which = 0 the
+// sends (scount3 / sproc_id / sdispls2), 1 the receives; and the coarse sizes around it
+int sref_repart_plan(void *hv, int l, int which, int *peer, int *offset, int *count) {
+    Handle *h = (Handle *)hv;
+    Grid &g = obj(h)->grids[l];
+    if (!g.A || !g.A->active || !g.active) return 0;
+    const std::vector<int> &cnt = which ? g.rcount3 : g.scount3, &id = which ? g.rproc_id : g.sproc_id,
+                           &dsp = which ? g.rdispls2 : g.sdispls2;
+    if (peer)
+        for (size_t i = 0; i < cnt.size(); ++i) { peer[i] = id[i]; offset[i] = dsp[id[i]]; count[i] = cnt[i]; }
+    return (int)cnt.size();
+}
+void sref_coarse_sizes(void *hv, int l, int *M_old, int *M_new) {
+    Handle *h = (Handle *)hv;
+    Grid &g = obj(h)->grids[l];
+    *M_old = *M_new = 0;
+    if (!g.A || !g.A->active || !g.active) return;
+    *M_old = (int)g.Ac.M_old;
+    *M_new = g.Ac.active ? (int)g.Ac.M : 0;
 }
 
 // solver parameters the reference ended up with

@@ -1,0 +1,75 @@
+"""The multi-rank oracle against the reference ITSELF on several MPI ranks.
+
+The reference is compiled unmodified against a multi-process MPI stand-in (oracle/ref_shim_mp, N
+processes over Unix sockets, oracle/mprun.py) and runs its real multi-rank paths: nnz-balanced row
+partition, local / remote split, float halo, Grid::repart_u, coarse levels shrunk onto fewer ranks,
+the coarsest level on one.  Each rank's share of the hierarchy is taken exactly as the reference laid
+it out (ranks translated to world ranks) and handed to the multi-rank oracle -- the same arrays the
+drop-in adaptor uploads per rank -- so this pins the multi-rank restatement, float halo included,
+against the reference's own numbers: frozen in tests/golden/*_np{2,4}.npz (runs everywhere), and
+live at other rank counts where oracle/_ref/libsaena_ref_mp.so exists."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from tests.util import (GOLDEN_MULTIRANK, TOL_HIST_F32_HALO, MultiRankGolden, check_multirank_against_golden, rel)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_apply(o):
+    def apply(name, l, *a):
+        if name == "A":
+            return o.matvec(l, 0, a[0])
+        if name == "P":
+            return o.matvec(l, 1, a[0])
+        if name == "R":
+            return o.matvec(l, 2, a[0])
+        return o.smooth(l, "chebyshev" if name == "cheb3" else "jacobi", 3 if name == "cheb3" else 2, a[0], a[1])
+    return apply
+
+
+def _check(g):
+    o = Oracle(g.hiers)
+    worst = check_multirank_against_golden(_oracle_apply(o), g)
+    u, iters, hist = o.solve_pcg(g.rhs)
+    assert iters == g.iters
+    n = min(len(hist), len(g.hist))
+    assert np.max(np.abs(hist[:n] - g.hist[:n]) / g.hist[:n]) <= TOL_HIST_F32_HALO
+    assert rel(np.concatenate(u), np.concatenate(g.u)) <= 1e-8
+    return worst
+
+
+@pytest.mark.parametrize("name", GOLDEN_MULTIRANK)
+def test_multirank_oracle_matches_the_multirank_reference_golden(name):
+    g = MultiRankGolden(name)
+    _check(g)
+    hs = g.hiers
+    # the fixture really holds the reference's multi-rank structure: remote blocks, a halo plan, and
+    # (4 ranks) a coarse level that left some ranks
+    assert any(h.levels[0].A.nnz_remote > 0 and len(h.levels[0].A.sendProcRank) for h in hs)
+    assert not any(h.levels[0].A.use_double for h in hs)          # float_level 0: ghost values travel as float
+    if g.nranks == 4:
+        assert any(h.levels[l].A.M == 0 for h in hs for l in range(1, len(h.levels) - 1))
+        assert any(lv.repart_send or lv.repart_recv for h in hs for lv in h.levels)
+    assert sum(h.levels[-1].A.M > 0 for h in hs) == 1             # the coarsest level lives on one rank
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("ranks,mx", [(2, 14), (3, 12), (5, 18), (8, 22)])
+def test_multirank_oracle_matches_the_live_multirank_reference(ranks, mx, tmp_path):
+    from oracle import mprun, ref
+    if not ref.mp_available():
+        pytest.skip("oracle/_ref/libsaena_ref_mp.so not built (make -C oracle ref_mp)")
+    out = str(tmp_path / "mp")
+    rc = mprun.run(ranks, [sys.executable, "-m", "oracle.mp_worker", "poisson", str(mx), out], timeout=600,
+                   env=dict(os.environ, SAENA_MP_DUMP="1", PYTHONPATH=ROOT))
+    assert rc == 0
+    parts = []
+    for r in range(ranks):
+        d = np.load(os.path.join(out, f"rank{r}.npz"))
+        parts.append({k: d[k] for k in d.files})
+    _check(MultiRankGolden(f"live np{ranks} mx{mx}", parts))

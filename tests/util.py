@@ -95,3 +95,58 @@ def check_pcg(iters, hist, u, ref_iters, ref_hist, ref_u, tol_hist=TOL_HIST):
     if iters == ref_iters:
         assert rel(u, ref_u) <= 1e-8
     return float(err.max())
+
+
+# ---- multi-rank goldens: the reference itself on N MPI ranks (tests/golden/make_golden_multirank.py) ----
+GOLDEN_MULTIRANK = ["poisson10_np2", "poisson14_np4"]
+TOL_HIST_F32_HALO = 1e-6   # float_level 0: see DESIGN.md section 2 (float rounding flips of single ghost values)
+
+
+class MultiRankGolden:
+    """per-rank hierarchies exactly as the reference laid them out + its own outputs"""
+
+    def __init__(self, name=None, parts=None):
+        if parts is None:
+            d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+            n = int(d["ranks"][0])
+            parts = [{k[len(f"r{r}."):]: d[k] for k in d.files if k.startswith(f"r{r}.")} for r in range(n)]
+        self.name, self.parts, self.nranks = name, parts, len(parts)
+        self.hiers = [hierarchy_from_arrays({k[5:]: p[k] for k in p if k.startswith("hier.")}) for p in parts]
+        self.rhs = [p["rhs"] for p in parts]
+        self.iters = int(parts[0]["iters"][0])
+        self.hist = parts[0]["hist"]
+        self.u = [p["u"] for p in parts]
+
+    def inputs(self, l):
+        """the seeded global vectors of level l, sliced per rank (what oracle/mp_worker.py fed the reference)"""
+        hs = self.hiers
+        g = np.random.default_rng(1000 + l)
+        Mbig = max(h.levels[l].A.Mbig for h in hs)
+        v_all, b_all = g.uniform(-1, 1, Mbig), g.uniform(-1, 1, Mbig)
+        sl = [(h.levels[l].A.row_offset, h.levels[l].A.M) for h in hs]
+        v, b = [v_all[o:o + m] for o, m in sl], [b_all[o:o + m] for o, m in sl]
+        vc = None
+        if hs[0].levels[l].P is not None:
+            vc_all = g.uniform(-1, 1, max(h.levels[l].P.Nbig for h in hs))
+            vc = [vc_all[h.levels[l].P.col_offset:h.levels[l].P.col_offset + h.levels[l].P.n_local_cols] for h in hs]
+        return v, b, vc
+
+    def want(self, l, key):
+        return [p.get(f"out.L{l}.{key}", np.zeros(0)) for p in self.parts]
+
+
+def check_multirank_against_golden(apply, g: MultiRankGolden, tol=TOL_OP):
+    """apply(op_name, level, *per-rank inputs) -> per-rank outputs; op_name in A / cheb3 / jac2 / P / R"""
+    worst = {}
+    cat = np.concatenate
+    for l in range(len(g.hiers[0].levels)):
+        v, b, vc = g.inputs(l)
+        worst[f"L{l}.A"] = rel(cat(apply("A", l, v)), cat(g.want(l, "A_matvec")))
+        worst[f"L{l}.cheb3"] = rel(cat(apply("cheb3", l, v, b)), cat(g.want(l, "chebyshev3")))
+        worst[f"L{l}.jac2"] = rel(cat(apply("jac2", l, v, b)), cat(g.want(l, "jacobi2")))
+        if vc is not None:
+            worst[f"L{l}.P"] = rel(cat(apply("P", l, vc)), cat(g.want(l, "P_matvec")))
+            worst[f"L{l}.R"] = rel(cat(apply("R", l, v)), cat(g.want(l, "R_matvec")))
+    bad = {k: e for k, e in worst.items() if not e <= tol}
+    assert not bad, f"{g.name}: beyond {tol:g}: {bad}"
+    return worst
