@@ -78,8 +78,36 @@ saena_b200_ctx *new_context(MPI_Comm comm, int &rank, int &nprocs) {
     return ctx;
 }
 
+// The communicator of a level shrinks as the levels get small (saena_matrix_shrink.cpp): every rank
+// number in that level's halo plans, displacement tables and Grid::repart_u plans is a rank of the
+// LEVEL's communicator.  The device context is built once on grids[0].A->comm, so everything is
+// translated to ranks of that communicator here.  (The same translation, on the same arrays, is what
+// oracle/ref.py does for the multi-rank oracle -- checked against the reference on 2..8 ranks in
+// tests/test_multirank_reference.py.)
+struct LevelComm {
+    std::vector<int> world;  // world[rank in the level's communicator] = rank in grids[0].A->comm; empty: not a member
+    int me = -1;             // my rank in the level's communicator
+};
+
+LevelComm level_comm(saena_matrix *A, int world_rank, int world_size) {
+    LevelComm lc;
+    if (!A || !A->active) return lc;
+    if (world_size == 1) { lc.world.assign(1, 0); lc.me = 0; return lc; }
+    int n = 0;
+    MPI_Comm_size(A->comm, &n);
+    MPI_Comm_rank(A->comm, &lc.me);
+    lc.world.resize(n);
+    MPI_Allgather(&world_rank, 1, MPI_INT, lc.world.data(), 1, MPI_INT, A->comm);
+    return lc;
+}
+
+// halo plan of one operator with world ranks: owns the translated tables the descriptor points to
+struct WorldPlan {
+    std::vector<int32_t> sendRank, recvRank, vdispls, rdispls;
+};
+
 template <class Op>
-void fill_plan(saena_b200_operator_desc &d, Op &op) {
+void fill_plan(saena_b200_operator_desc &d, Op &op, const LevelComm &lc, int world_size, WorldPlan &wp) {
     d.nnz_remote = op.nnz_l_remote;
     d.col_remote_size = (int32_t)op.col_remote_size;
     d.row_remote = op.nnz_l_remote ? &op.row_remote[0] : nullptr;
@@ -87,38 +115,65 @@ void fill_plan(saena_b200_operator_desc &d, Op &op) {
     d.nnzPerCol_remote = op.nnzPerCol_remote.empty() ? nullptr : op.nnzPerCol_remote.data();
     d.vIndexSize = (int32_t)op.vIndexSize;
     d.vIndex = op.vIndex.empty() ? nullptr : op.vIndex.data();
+    wp.vdispls.assign(world_size, 0);
+    wp.rdispls.assign(world_size, 0);
+    for (size_t r = 0; r < lc.world.size(); ++r) {   // a one-rank communicator builds no tables at all
+        if (r < op.vdispls.size()) wp.vdispls[lc.world[r]] = op.vdispls[r];
+        if (r < op.rdispls.size()) wp.rdispls[lc.world[r]] = op.rdispls[r];
+    }
+    wp.sendRank.clear();
+    wp.recvRank.clear();
+    for (int i = 0; i < (int)op.numSendProc; ++i) wp.sendRank.push_back(lc.world[op.sendProcRank[i]]);
+    for (int i = 0; i < (int)op.numRecvProc; ++i) wp.recvRank.push_back(lc.world[op.recvProcRank[i]]);
     d.numSendProc = (int32_t)op.numSendProc;
-    d.sendProcRank = op.sendProcRank.data();
+    d.sendProcRank = wp.sendRank.data();
     d.sendProcCount = op.sendProcCount.data();
-    d.vdispls = op.vdispls.data();
+    d.vdispls = wp.vdispls.data();
     d.numRecvProc = (int32_t)op.numRecvProc;
-    d.recvProcRank = op.recvProcRank.data();
+    d.recvProcRank = wp.recvRank.data();
     d.recvProcCount = op.recvProcCount.data();
-    d.rdispls = op.rdispls.data();
+    d.rdispls = wp.rdispls.data();
     d.use_double = op.use_double ? 1 : 0;
 }
 
-// saena_matrix keeps its local/remote arrays as raw pointers (saena_matrix.h:107-113)
-void upload_A(saena_b200_ctx *ctx, saena_matrix *A, int level, int rank) {
+// a level this rank is not a member of: operators with no rows, no columns, no plan
+void upload_empty(saena_b200_ctx *ctx, int kind, int level, int world_size) {
+    static const int32_t none = 0;
+    std::vector<int32_t> zeros(world_size, 0);
     saena_b200_operator_desc d{};
+    d.kind = kind;
+    d.level = level;
+    d.nnzPerRow_local = &none;
+    d.vdispls = zeros.data();
+    d.rdispls = zeros.data();
+    d.use_double = 1;
+    CK(ctx, saena_b200_upload_operator(ctx, &d), "upload empty operator");
+}
+
+// saena_matrix keeps its local/remote arrays as raw pointers (saena_matrix.h:107-113)
+void upload_A(saena_b200_ctx *ctx, saena_matrix *A, int level, const LevelComm &lc, int world_size) {
+    saena_b200_operator_desc d{};
+    WorldPlan wp;
     d.kind = SAENA_B200_KIND_A;
     d.level = level;
     d.M = (int32_t)A->M;
     d.n_local_cols = (int32_t)A->M;
-    d.col_offset = (int32_t)A->split[rank];
+    d.col_offset = (int32_t)A->split[lc.me];
     d.nnz_local = A->nnz_l_local;
     d.nnzPerRow_local = A->nnzPerRow_local.data();
     d.col_local = A->col_local;
     d.val_local = A->val_local;
-    fill_plan(d, *A);
+    fill_plan(d, *A, lc, world_size, wp);
     d.row_remote = A->row_remote;
     d.val_remote = A->val_remote;
     CK(ctx, saena_b200_upload_operator(ctx, &d), "upload A");
 }
 
 template <class Op>
-void upload_PR(saena_b200_ctx *ctx, Op &op, int kind, int level, int n_rows, int col_offset, int n_local_cols) {
+void upload_PR(saena_b200_ctx *ctx, Op &op, int kind, int level, int n_rows, int col_offset, int n_local_cols,
+               const LevelComm &lc, int world_size) {
     saena_b200_operator_desc d{};
+    WorldPlan wp;
     d.kind = kind;
     d.level = level;
     d.M = n_rows;
@@ -128,7 +183,7 @@ void upload_PR(saena_b200_ctx *ctx, Op &op, int kind, int level, int n_rows, int
     d.nnzPerRow_local = op.nnzPerRow_local.data();
     d.col_local = op.col_local.data();
     d.val_local = op.val_local.data();
-    fill_plan(d, op);
+    fill_plan(d, op, lc, world_size, wp);
     CK(ctx, saena_b200_upload_operator(ctx, &d), kind == SAENA_B200_KIND_P ? "upload P" : "upload R");
 }
 
@@ -140,33 +195,46 @@ DeviceSide &device_side(saena_object *obj) {
     saena_matrix *A0 = obj->grids[0].A;
     ds.ctx = new_context(A0->comm, ds.rank, ds.nprocs);
     const int L = obj->max_level;
+    const std::vector<double> no_diag(1, 0.0);
     for (int l = 0; l <= L; ++l) {
         Grid &g = obj->grids[l];
         saena_matrix *A = g.A;
+        const LevelComm lc = level_comm(A, ds.rank, ds.nprocs);   // collective over the level's communicator
+        if (lc.world.empty()) {
+            // a shrink left this rank out of level l: it owns nothing of it
+            upload_empty(ds.ctx, SAENA_B200_KIND_A, l, ds.nprocs);
+            if (l < L) {
+                upload_empty(ds.ctx, SAENA_B200_KIND_P, l, ds.nprocs);
+                upload_empty(ds.ctx, SAENA_B200_KIND_R, l, ds.nprocs);
+            }
+            CK(ds.ctx, saena_b200_upload_level_aux(ds.ctx, l, no_diag.data(), 1.0, 0, 0, 0, nullptr, 0, nullptr),
+               "upload level aux");
+            continue;
+        }
         if (A->use_dense) {
             std::printf("Error: saena_b200: dense coarse operators (switch_to_dense) are not supported\n");
             std::exit(EXIT_FAILURE);
         }
-        int rank_l = 0;
-        if (A->active) MPI_Comm_rank(A->comm, &rank_l);
-        upload_A(ds.ctx, A, l, rank_l);
+        upload_A(ds.ctx, A, l, lc, ds.nprocs);
         std::vector<saena_b200_block> send, recv;
         int M_old = 0, M_new = 0;
         if (l < L) {
             prolong_matrix &P = g.P;
             restrict_matrix &R = g.R;
-            upload_PR(ds.ctx, P, SAENA_B200_KIND_P, l, (int)P.M, (int)P.splitNew[rank_l],
-                      (int)(P.splitNew[rank_l + 1] - P.splitNew[rank_l]));
-            upload_PR(ds.ctx, R, SAENA_B200_KIND_R, l, (int)R.M, (int)R.split[rank_l],
-                      (int)(R.split[rank_l + 1] - R.split[rank_l]));
+            // fine side: A's split; coarse side: splitNew, the partition R writes into (before Grid::repart_u)
+            upload_PR(ds.ctx, P, SAENA_B200_KIND_P, l, (int)P.M, (int)P.splitNew[lc.me],
+                      (int)(P.splitNew[lc.me + 1] - P.splitNew[lc.me]), lc, ds.nprocs);
+            upload_PR(ds.ctx, R, SAENA_B200_KIND_R, l, (int)R.M, (int)A->split[lc.me],
+                      (int)(A->split[lc.me + 1] - A->split[lc.me]), lc, ds.nprocs);
             M_old = (int)g.Ac.M_old;
-            M_new = (int)g.Ac.M;
-            // Grid::repart_u plan (grid.cpp:99-130): receive rcount3[i] values from rproc_id[i] at
-            // rdispls2[rproc_id[i]]; send scount3[i] values to sproc_id[i] from sdispls2[sproc_id[i]]
+            M_new = g.Ac.active ? (int)g.Ac.M : 0;
+            // Grid::repart_u plan (grid.cpp:99-130, on Ac.comm_old = this level's communicator): receive
+            // rcount3[i] values from rproc_id[i] at rdispls2[rproc_id[i]]; send scount3[i] values to
+            // sproc_id[i] from sdispls2[sproc_id[i]]
             for (size_t i = 0; i < g.scount3.size(); ++i)
-                send.push_back({g.sproc_id[i], g.sdispls2[g.sproc_id[i]], g.scount3[i]});
+                send.push_back({lc.world[g.sproc_id[i]], g.sdispls2[g.sproc_id[i]], g.scount3[i]});
             for (size_t i = 0; i < g.rcount3.size(); ++i)
-                recv.push_back({g.rproc_id[i], g.rdispls2[g.rproc_id[i]], g.rcount3[i]});
+                recv.push_back({lc.world[g.rproc_id[i]], g.rdispls2[g.rproc_id[i]], g.rcount3[i]});
             // a one-rank plan that only copies the vector onto itself is the identity
             if (ds.nprocs == 1) { send.clear(); recv.clear(); }
         }
@@ -178,7 +246,9 @@ DeviceSide &device_side(saena_object *obj) {
     }
     // coarsest operator: the COO entries setup_SuperLU passes on (saena_object_solve.cpp:282-308)
     saena_matrix *Ac = obj->grids[L].A;
-    if (Ac->active && Ac->M == Ac->Mbig) {
+    if (!Ac || !Ac->active) {
+        CK(ds.ctx, saena_b200_upload_coarsest(ds.ctx, 0, 0, nullptr, nullptr, nullptr), "upload coarsest");
+    } else if (Ac->M == Ac->Mbig) {
         std::vector<int32_t> r(Ac->entry.size()), c(Ac->entry.size());
         std::vector<double> v(Ac->entry.size());
         for (size_t i = 0; i < Ac->entry.size(); ++i) {
@@ -295,7 +365,7 @@ void saena::matrix::matvec(std::vector<value_t> &v, std::vector<value_t> &w) {
     if (it == g_matrices.end()) {
         DeviceSide ds;
         ds.ctx = new_context(A->comm, ds.rank, ds.nprocs);
-        upload_A(ds.ctx, A, 0, ds.rank);
+        upload_A(ds.ctx, A, 0, level_comm(A, ds.rank, ds.nprocs), ds.nprocs);
         CK(ds.ctx, saena_b200_upload_level_aux(ds.ctx, 0, A->inv_diag, A->eig_max_of_invdiagXA, 0, 0, 0, nullptr, 0,
                                                nullptr), "upload level aux");
         // a lone operator: one level, no coarsest factor needed for matvec

@@ -154,6 +154,43 @@ def main():
         if rank == 0:
             print(f"{tag}: pcg iters {it} (oracle {it_o}), history err {herr:.2e}, u err {uerr:.2e}, "
                   f"{replays} V-cycles replayed from a graph", flush=True)
+    # ---- the reference's OWN multi-rank layout (tests/golden/*_np{2,4}.npz: per-rank hierarchies exactly as the
+    #      reference on `world` MPI ranks laid them out -- shrunk coarse levels, Grid::repart_u plans, float halo --
+    #      and its own outputs).  What the drop-in adaptor uploads in a multi-rank run.  Opt-in until its first run
+    #      on GPUs (SAENA_MG_REFERENCE_GOLDEN=1): written after the round's GPU budget was spent.
+    if os.environ.get("SAENA_MG_REFERENCE_GOLDEN") == "1" and world in (2, 4):
+        from tests.util import TOL_HIST_F32_HALO, MultiRankGolden, check_multirank_against_golden
+        g = MultiRankGolden({2: "poisson10_np2", 4: "poisson14_np4"}[world])
+        mine = g.hiers[rank]
+        dist.barrier()
+        ctx.upload_hierarchy(mine)
+        setup_p2p_halo(ctx)
+        ctx.autotune_halo(3)
+
+        def apply(name, l, *a):
+            sizes = [h.levels[l].A.M for h in g.hiers]
+            if name == "A":
+                out = ctx.matvec(l, KIND_A, a[0][rank])
+            elif name == "P":
+                out = ctx.matvec(l, KIND_P, a[0][rank])
+            elif name == "R":
+                out, sizes = ctx.matvec(l, KIND_R, a[0][rank]), [h.levels[l].R.M for h in g.hiers]
+            else:
+                out = ctx.smooth(l, "chebyshev" if name == "cheb3" else "jacobi", 3 if name == "cheb3" else 2,
+                                 a[0][rank], a[1][rank])
+            return gather(out, sizes, rank, world)
+
+        w2 = check_multirank_against_golden(apply, g)
+        u, it, h = ctx.solve_pcg(g.rhs[rank], 50, 1e-8, "chebyshev", 3, 3)
+        assert it == g.iters, (it, g.iters)
+        n = min(len(h), len(g.hist))
+        herr = float(np.max(np.abs(h[:n] - g.hist[:n]) / g.hist[:n]))
+        assert herr <= TOL_HIST_F32_HALO, herr
+        uerr = rel(np.concatenate(gather(u, [len(x) for x in g.u], rank, world)), np.concatenate(g.u))
+        assert uerr <= 1e-8, uerr
+        if rank == 0:
+            print(f"{g.name}: the reference's own {world}-rank layout: worst op err {max(w2.values()):.2e}, pcg iters {it} "
+                  f"(reference {g.iters}), history err {herr:.2e}, u err {uerr:.2e}", flush=True)
     bad = {k: e for k, e in worst.items() if not e <= TOL_OP}
     assert not bad, bad
     dist.barrier()
