@@ -73,3 +73,23 @@ def test_multirank_oracle_matches_the_live_multirank_reference(ranks, mx, tmp_pa
         d = np.load(os.path.join(out, f"rank{r}.npz"))
         parts.append({k: d[k] for k in d.files})
     _check(MultiRankGolden(f"live np{ranks} mx{mx}", parts))
+
+
+@pytest.mark.ref
+def test_multirank_reference_agrees_with_the_one_rank_reference(tmp_path):
+    """sanity of the stand-in itself: the reference on 4 ranks and on 1 rank solve the same system (their
+    hierarchies differ -- aggregation is partition-dependent -- so the solutions agree to the solver
+    tolerance, not to rounding)"""
+    from oracle import mprun, ref
+    if not ref.mp_available():
+        pytest.skip("oracle/_ref/libsaena_ref_mp.so not built (make -C oracle ref_mp)")
+    out = str(tmp_path / "mp")
+    assert mprun.run(4, [sys.executable, "-m", "oracle.mp_worker", "poisson", "18", out], timeout=600,
+                     env=dict(os.environ, PYTHONPATH=ROOT)) == 0
+    u4 = np.concatenate([np.load(os.path.join(out, f"rank{r}.npz"))["u"] for r in range(4)])
+    s = ref.RefSolver.poisson(18)
+    try:
+        u1, it1, _ = s.solve_pcg()
+    finally:
+        s.close()
+    assert u4.shape == u1.shape and rel(u4, u1) < 1e-6
