@@ -65,13 +65,32 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
     const int M = d->M;
 
     // ---- halo-dominated operator: one CSR over [local | ghost] columns (see DevOperator::merged)
-    int n_rows_with_remote = 0;
+    // Merged when most rows touch ghost columns (deep coarse levels: every row couples to every rank).
+    // Also merged when the rows with remote entries are few but SCATTERED: the split path overlaps ONE
+    // contiguous run of clean rows with the exchange and sends every other row through the boundary-row
+    // kernel (8 or 32 lanes per row, CSR, local + ghost segment) -- right for a slab partition (ghost rows
+    // at the two ends of the block), a cliff for transfer operators between a re-split coarse level and
+    // the fine level above, or for unstructured matrices: 5 % of scattered rows leave no run worth the
+    // name and ~all rows would take the boundary kernel.  (For slab partitions the rows outside the
+    // longest clean run ARE the rows with remote entries, and the first rule alone decides, as before.)
+    int n_rows_with_remote = 0, n_outside_clean_run = 0;
     if (d->nnz_remote > 0) {
         std::vector<char> has(M, 0);
         for (int64_t k = 0; k < d->nnz_remote; ++k)
             if (d->row_remote[k] >= 0 && d->row_remote[k] < M && !has[d->row_remote[k]]) { has[d->row_remote[k]] = 1; ++n_rows_with_remote; }
+        int best = 0;
+        for (int i = 0; i < M;) {
+            if (has[i]) { ++i; continue; }
+            int j = i;
+            while (j < M && !has[j]) ++j;
+            best = std::max(best, j - i);
+            i = j;
+        }
+        n_outside_clean_run = M - best;
     }
-    op.merged = d->nnz_remote > 0 && n_rows_with_remote * 4 >= M;
+    op.merged = d->nnz_remote > 0 &&
+                ((int64_t)n_rows_with_remote * 4 >= M ||
+                 ((int64_t)n_outside_clean_run * 4 >= M && n_outside_clean_run >= 2 * n_rows_with_remote));
     if (op.merged) {
         const int64_t nl = d->nnz_local, nr = d->nnz_remote, nt = nl + nr;
         std::vector<int64_t> rp(M + 1, 0);
