@@ -46,6 +46,12 @@ int saena_b200_nccl_unique_id(void *id_out);
 
 /* nccl_id may be NULL when nranks == 1 (no communicator is created). */
 int saena_b200_init(saena_b200_ctx **ctx_out, int device_id, int rank, int nranks, const void *nccl_id);
+/* Profiling aid: rank `rank`'s share of an nranks-way partition on one GPU with no peer behind it
+ * (no NCCL, no peer memory).  Uploads and finalize work as usual; any operation that needs a peer
+ * fails loudly; saena_b200_time_matvec_compute_only times the compute side of the distributed
+ * kernels on that share -- the way to put the fused halo kernel under ncu, which cannot follow a
+ * multi-rank command. */
+int saena_b200_init_detached(saena_b200_ctx **ctx_out, int device_id, int rank, int nranks);
 int saena_b200_destroy(saena_b200_ctx *ctx);
 const char *saena_b200_last_error(const saena_b200_ctx *ctx); /* ctx may be NULL: error of a failed init */
 
@@ -213,6 +219,10 @@ int saena_b200_time_matvec_parts(saena_b200_ctx *ctx, int level, int kind, int r
 /* CUDA-event stopwatch on the context's compute stream (the stream every kernel of this library
  * is launched on): start records an event, stop records a second one, waits for it and returns
  * the device time between them. */
+/* ms per application of one operator's compute side only (no pack, no flags, no exchange; ghost values
+ * as they lie): fused != 0 through the fused halo kernel, else the separate interior + boundary kernels */
+int saena_b200_time_matvec_compute_only(saena_b200_ctx *ctx, int level, int kind, int fused, int reps, int do_flush,
+                                        float *ms_out);
 int saena_b200_timer_start(saena_b200_ctx *ctx);
 /* ms per V-cycle entered at `level` from a zero iterate (reps back-to-back, eager, collective over
  * the ranks); the difference between consecutive levels is one level's cost inside a solve */

@@ -40,11 +40,26 @@ static int init_body(saena_b200_ctx *ctx, const void *nccl_id) {
     SB_CUDA(cudaMalloc((void **)&ctx->scalars, sizeof(double) * S_COUNT));
     SB_CUDA(cudaMemset(ctx->scalars, 0, sizeof(double) * S_COUNT));
     SB_CUDA(cudaMallocHost((void **)&ctx->scalars_host, sizeof(double) * S_COUNT));
-    SB_TRY(sb_nccl_init(ctx, nccl_id));
+    if (!ctx->detached) SB_TRY(sb_nccl_init(ctx, nccl_id));
     return 0;
 }
 
+static int init_common(saena_b200_ctx **ctx_out, int device_id, int rank, int nranks, const void *nccl_id, bool detached);
+
 int saena_b200_init(saena_b200_ctx **ctx_out, int device_id, int rank, int nranks, const void *nccl_id) {
+    return init_common(ctx_out, device_id, rank, nranks, nccl_id, false);
+}
+
+// Profiling aid: one rank's share of an nranks-way partition on ONE GPU, with no peer behind it.
+// Nothing that needs a peer works (any exchange fails loudly); what does work is the compute side
+// of the distributed kernels on that share -- saena_b200_time_matvec_compute_only -- which is how
+// the fused halo kernel's interior / ghost-row roles get under ncu (ncu cannot follow a multi-rank
+// command).  Ghost values are whatever the landing areas hold (zeros).
+int saena_b200_init_detached(saena_b200_ctx **ctx_out, int device_id, int rank, int nranks) {
+    return init_common(ctx_out, device_id, rank, nranks, nullptr, true);
+}
+
+static int init_common(saena_b200_ctx **ctx_out, int device_id, int rank, int nranks, const void *nccl_id, bool detached) {
     *ctx_out = nullptr;
     if (nranks < 1 || rank < 0 || rank >= nranks) {
         g_sb_init_error = "init: bad rank / nranks";
@@ -54,6 +69,7 @@ int saena_b200_init(saena_b200_ctx **ctx_out, int device_id, int rank, int nrank
     ctx->device = device_id;
     ctx->rank = rank;
     ctx->nranks = nranks;
+    ctx->detached = detached;
     if (const char *gm = getenv("SAENA_B200_GRAPH_MULTI")) ctx->use_graphs_multi = atoi(gm) != 0;
     if (const char *hf = getenv("SAENA_B200_HALO_FUSED")) ctx->fused_default = atoi(hf) != 0;
     if (init_body(ctx, nccl_id)) {
@@ -677,6 +693,24 @@ int saena_b200_find_eig(saena_b200_ctx *ctx, int level, int max_iter, const doub
         sb_invalidate_graphs(ctx);  // the captured V-cycle carries the old Chebyshev constants
     }
     return 0;
+}
+
+// compute side only (apply_mode 1: no pack, no flags, no exchange; ghost values as they lie) of one
+// operator, through the fused kernel (fused != 0) or the separate interior + boundary kernels.  The one
+// timing hook a detached context (saena_b200_init_detached) supports; also valid on a live one.
+int saena_b200_time_matvec_compute_only(saena_b200_ctx *ctx, int level, int kind, int fused, int reps, int do_flush,
+                                        float *ms_out) {
+    SB_ENTER();
+    DevOperator *op = get_op(ctx, level, kind);
+    if (!op) SB_FAIL("time_matvec_compute_only: no such operator");
+    const bool was = op->fused;
+    op->fused = fused != 0;
+    ctx->apply_mode = 1;
+    int rc = saena_b200_time_matvec(ctx, level, kind, 3, 0, ms_out);
+    if (!rc) rc = saena_b200_time_matvec(ctx, level, kind, reps, do_flush, ms_out);
+    ctx->apply_mode = 0;
+    op->fused = was;
+    return rc;
 }
 
 // halo overlap of one operator: full application, local kernels alone, pack + exchange alone

@@ -213,6 +213,7 @@ struct VcycleGraph {
 
 struct saena_b200_ctx {
     int device = 0, rank = 0, nranks = 1;
+    bool detached = false;  // saena_b200_init_detached: a rank's share with no peer (compute-only profiling)
     std::string error;
     cudaStream_t stream = nullptr;  // compute
     cudaStream_t comm_stream = nullptr;

@@ -124,6 +124,7 @@ int sb_halo_exchange(saena_b200_ctx *ctx, DevOperator &op, cudaStream_t s) {
 
 int sb_allreduce_sum(saena_b200_ctx *ctx, double *dev_vals, int count, cudaStream_t s) {
     if (ctx->nranks == 1) return 0;
+    if (!ctx->nccl_comm) SB_FAIL("all-reduce without a communicator (a detached context has no peers)");
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     SB_NCCL(g_nccl.AllReduce(dev_vals, dev_vals, (size_t)count, ncclDouble, ncclSum, comm, s));
     return 0;

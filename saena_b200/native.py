@@ -58,6 +58,7 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_last_error.argtypes = [vp]
     L.saena_b200_nccl_unique_id.argtypes = [vp]
     L.saena_b200_init.argtypes = [ctypes.POINTER(vp), i, i, i, vp]
+    L.saena_b200_init_detached.argtypes = [ctypes.POINTER(vp), i, i, i]
     L.saena_b200_destroy.argtypes = [vp]
     L.saena_b200_upload_operator.argtypes = [vp, ctypes.POINTER(OperatorDesc)]
     L.saena_b200_upload_band_operator.argtypes = [vp, i, i, i, i]
@@ -89,6 +90,7 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_time_smooth_sweep.argtypes = [vp, i, i, i, i, ctypes.POINTER(ctypes.c_float)]
     L.saena_b200_time_matvec_parts.argtypes = [vp, i, i, i] + [ctypes.POINTER(ctypes.c_float)] * 3
     L.saena_b200_time_vcycle.argtypes = [vp, i, i, i, i, i, ctypes.POINTER(ctypes.c_float)]
+    L.saena_b200_time_matvec_compute_only.argtypes = [vp, i, i, i, i, i, ctypes.POINTER(ctypes.c_float)]
     L.saena_b200_timer_start.argtypes = [vp]
     L.saena_b200_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.saena_b200_launch_count.restype = ctypes.c_int64
@@ -105,7 +107,7 @@ def load_library(path: Optional[str] = None):
 
 
 EXPORTED_SYMBOLS = [
-    "saena_b200_nccl_unique_id", "saena_b200_init", "saena_b200_destroy", "saena_b200_last_error",
+    "saena_b200_nccl_unique_id", "saena_b200_init", "saena_b200_init_detached", "saena_b200_time_matvec_compute_only", "saena_b200_destroy", "saena_b200_last_error",
     "saena_b200_upload_operator", "saena_b200_upload_band_operator", "saena_b200_upload_level_aux", "saena_b200_upload_level_scale",
     "saena_b200_upload_coarsest",
     "saena_b200_set_coarsest_solver", "saena_b200_set_graphs", "saena_b200_finalize",
@@ -154,11 +156,17 @@ def smoother_id(name) -> int:
 class Context:
     """One rank's device context: an uploaded hierarchy and the solve entry points."""
 
-    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None):
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None,
+                 detached: bool = False):
+        """detached=True: this rank's share of an nranks-way partition with no peer behind it (profiling of the
+        compute side of the distributed kernels on one GPU; anything that needs a peer fails)"""
         self._L = load_library()
         self._h = ctypes.c_void_p()
         idbuf = ctypes.create_string_buffer(nccl_id, NCCL_ID_BYTES) if nccl_id else None
-        rc = self._L.saena_b200_init(ctypes.byref(self._h), device, rank, nranks, idbuf)
+        if detached:
+            rc = self._L.saena_b200_init_detached(ctypes.byref(self._h), device, rank, nranks)
+        else:
+            rc = self._L.saena_b200_init(ctypes.byref(self._h), device, rank, nranks, idbuf)
         if rc:
             raise NativeError(self._L.saena_b200_last_error(None).decode())
         self.rank, self.nranks, self.device = rank, nranks, device
@@ -389,6 +397,12 @@ class Context:
         self._ck(self._L.saena_b200_time_matvec_parts(self._h, level, kind, reps, ctypes.byref(f), ctypes.byref(l),
                                                       ctypes.byref(h)))
         return f.value, l.value, h.value
+
+    def time_matvec_compute_only(self, level, kind, fused: bool, reps=20, flush_l2=False) -> float:
+        ms = ctypes.c_float(0)
+        self._ck(self._L.saena_b200_time_matvec_compute_only(self._h, level, kind, int(fused), reps, int(flush_l2),
+                                                             ctypes.byref(ms)))
+        return ms.value
 
     def time_vcycle(self, level: int, smoother="chebyshev", pre=3, post=3, reps=10) -> float:
         ms = ctypes.c_float(0)
