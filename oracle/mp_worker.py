@@ -22,8 +22,18 @@ def main():
     warmup = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     L = ref.lib()
     rank, size = L.sref_rank(), L.sref_size()
-    assert what == "poisson"
-    s = ref.RefSolver.poisson(mx)
+    if what == "poisson":
+        s = ref.RefSolver.poisson(mx)
+    elif what == "unstructured":
+        # BASELINE.json configs[4]'s synthetic shape, g = mx: every rank hands the reference its own block of
+        # rows of the COO (saena::matrix::set + assemble repartition it by nnz)
+        from saena_b200.sa_setup import unstructured2d_coo, unstructured2d_rhs
+        n, row, col, val = unstructured2d_coo(mx)
+        lo, hi = n * rank // size, n * (rank + 1) // size
+        keep = (row >= lo) & (row < hi)
+        s = ref.RefSolver.from_coo(n, row[keep], col[keep], val[keep], unstructured2d_rhs(n)[lo:hi], rhs_offset=lo)
+    else:
+        raise SystemExit(f"unknown workload {what}")
     u, iters, hist = s.solve_pcg()
     res = dict(u=u, iters=np.array([iters]), hist=hist, rank=np.array([rank]), size=np.array([size]))
     if os.environ.get("SAENA_MP_DUMP"):

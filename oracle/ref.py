@@ -124,11 +124,19 @@ class RefSolver:
         return cls(lib().sref_poisson_new_scaled(int(mx), ctypes.byref(c), int(quiet), 0), opts)
 
     @classmethod
-    def from_coo(cls, n, row, col, val, rhs, opts: RefOptions | None = None, quiet: bool = True) -> "RefSolver":
+    def from_coo(cls, n, row, col, val, rhs, opts: RefOptions | None = None, quiet: bool = True,
+                 rhs_offset: int = 0) -> "RefSolver":
+        """one rank: the whole matrix and rhs.  Several ranks (oracle.mprun): each rank passes its own share of the
+        entries (any rows) and a contiguous block of the rhs starting at global index rhs_offset"""
         opts = opts or RefOptions()
         c = opts._c()
         row, col = np.ascontiguousarray(row, I32), np.ascontiguousarray(col, I32)
         val, rhs = np.ascontiguousarray(val, F64), np.ascontiguousarray(rhs, F64)
+        if rhs_offset or len(rhs) != n:
+            f = lib().sref_coo_new_part
+            f.restype = ctypes.c_void_p
+            return cls(f(ctypes.c_long(len(val)), _p(row), _p(col), _p(val), int(len(rhs)), int(rhs_offset), _p(rhs),
+                         ctypes.byref(c), int(quiet)), opts)
         return cls(lib().sref_coo_new(int(n), ctypes.c_long(len(val)), _p(row), _p(col), _p(val), _p(rhs),
                                       ctypes.byref(c), int(quiet)), opts)
 

@@ -161,6 +161,28 @@ void sref_barrier() { ensure_mpi(); MPI_Barrier(MPI_COMM_WORLD); }
 double sref_wtime() { return MPI_Wtime(); }
 void sref_finalize() { int inited = 0; MPI_Initialized(&inited); if (inited) MPI_Finalize(); }
 
+// Several ranks: every rank contributes its own entries (global ids) and a contiguous block of the rhs
+// starting at rhs_offset (saena::vector::set(values, size, offset)); assemble() repartitions.
+void *sref_coo_new_part(long nnz, const int *row, const int *col, const double *val, int rhs_n, int rhs_offset,
+                        const double *rhs, const sref_opts *o, int quiet) {
+    ensure_mpi();
+    MPI_Comm comm = MPI_COMM_WORLD;
+    Handle *h = new Handle();
+    {
+        QuietStdout q(quiet != 0);
+        h->A = new saena::matrix(comm);
+        for (long i = 0; i < nnz; ++i) h->A->set(row[i], col[i], val[i]);
+        h->A->set_remove_boundary(false);
+        h->A->assemble(false);
+    }
+    h->rhs = new saena::vector(comm);
+    h->rhs->set(rhs, rhs_n, rhs_offset);
+    h->rhs->assemble();
+    h->opts = make_opts(o);
+    finish_setup(h, h->rhs, quiet != 0);
+    return h;
+}
+
 void sref_free(void *hv) {
     Handle *h = (Handle *)hv;
     if (!h) return;

@@ -20,10 +20,10 @@ from oracle import mprun  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def make(name, ranks, mx):
+def make(name, ranks, mx, what="poisson"):
     out = tempfile.mkdtemp(prefix="saena_golden_mp_")
     try:
-        rc = mprun.run(ranks, [sys.executable, "-m", "oracle.mp_worker", "poisson", str(mx), out], timeout=600,
+        rc = mprun.run(ranks, [sys.executable, "-m", "oracle.mp_worker", what, str(mx), out], timeout=600,
                        env=dict(os.environ, SAENA_MP_DUMP="1", PYTHONPATH=ROOT))
         assert rc == 0, rc
         merged = {"ranks": np.array([ranks]), "mx": np.array([mx])}
@@ -42,3 +42,5 @@ def make(name, ranks, mx):
 if __name__ == "__main__":
     make("poisson10_np2", 2, 12)
     make("poisson14_np4", 4, 16)
+    # BASELINE.json configs[4]'s synthetic unstructured shape (irregular rows, several neighbours per rank)
+    make("unstructured40_np3", 3, 40, "unstructured")

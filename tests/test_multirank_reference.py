@@ -52,27 +52,28 @@ def test_multirank_oracle_matches_the_multirank_reference_golden(name):
     # (4 ranks) a coarse level that left some ranks
     assert any(h.levels[0].A.nnz_remote > 0 and len(h.levels[0].A.sendProcRank) for h in hs)
     assert not any(h.levels[0].A.use_double for h in hs)          # float_level 0: ghost values travel as float
-    if g.nranks == 4:
+    if name == "poisson14_np4":
         assert any(h.levels[l].A.M == 0 for h in hs for l in range(1, len(h.levels) - 1))
         assert any(lv.repart_send or lv.repart_recv for h in hs for lv in h.levels)
     assert sum(h.levels[-1].A.M > 0 for h in hs) == 1             # the coarsest level lives on one rank
 
 
 @pytest.mark.ref
-@pytest.mark.parametrize("ranks,mx", [(2, 14), (3, 12), (5, 18), (8, 22)])
-def test_multirank_oracle_matches_the_live_multirank_reference(ranks, mx, tmp_path):
+@pytest.mark.parametrize("ranks,mx,what", [(2, 14, "poisson"), (3, 12, "poisson"), (5, 18, "poisson"), (8, 22, "poisson"),
+                                           (4, 48, "unstructured"), (6, 64, "unstructured")])
+def test_multirank_oracle_matches_the_live_multirank_reference(ranks, mx, what, tmp_path):
     from oracle import mprun, ref
     if not ref.mp_available():
         pytest.skip("oracle/_ref/libsaena_ref_mp.so not built (make -C oracle ref_mp)")
     out = str(tmp_path / "mp")
-    rc = mprun.run(ranks, [sys.executable, "-m", "oracle.mp_worker", "poisson", str(mx), out], timeout=600,
+    rc = mprun.run(ranks, [sys.executable, "-m", "oracle.mp_worker", what, str(mx), out], timeout=600,
                    env=dict(os.environ, SAENA_MP_DUMP="1", PYTHONPATH=ROOT))
     assert rc == 0
     parts = []
     for r in range(ranks):
         d = np.load(os.path.join(out, f"rank{r}.npz"))
         parts.append({k: d[k] for k in d.files})
-    _check(MultiRankGolden(f"live np{ranks} mx{mx}", parts))
+    _check(MultiRankGolden(f"live {what} np{ranks} {mx}", parts))
 
 
 @pytest.mark.ref

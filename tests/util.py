@@ -98,7 +98,7 @@ def check_pcg(iters, hist, u, ref_iters, ref_hist, ref_u, tol_hist=TOL_HIST):
 
 
 # ---- multi-rank goldens: the reference itself on N MPI ranks (tests/golden/make_golden_multirank.py) ----
-GOLDEN_MULTIRANK = ["poisson10_np2", "poisson14_np4"]
+GOLDEN_MULTIRANK = ["poisson10_np2", "poisson14_np4", "unstructured40_np3"]
 TOL_HIST_F32_HALO = 1e-6   # float_level 0: see DESIGN.md section 2 (float rounding flips of single ghost values)
 
 
