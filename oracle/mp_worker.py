@@ -16,6 +16,66 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import ref  # noqa: E402
 
 
+def check_adaptor_upload(L, s, rank, size, out):
+    """The library loaded here is the reference + the drop-in adaptor + a stand-in for libsaena_b200.so that
+    records what is uploaded (oracle/abi_recorder.cpp).  One solve through the public API
+    (saena::amg::solve_pCG = the adaptor) makes the adaptor walk saena_object::grids on this rank; the recording
+    must equal, array by array, what oracle/ref.py extracts from the same solver object."""
+    import ctypes
+    s.time_solve_pcg(1)
+    I32, F64 = np.int32, np.float64
+    info = [ctypes.c_int(0) for _ in range(5)]
+    assert L.rec_info(*[ctypes.byref(x) for x in info]) == 0, "the adaptor never created a context"
+    r_rank, r_n, r_levels, r_coarse_n, r_solves = (x.value for x in info)
+    h = s.hierarchy()
+    assert (r_rank, r_n, r_levels, r_solves) == (rank, size, len(h.levels), 1), (r_rank, r_n, r_levels, r_solves)
+    L.rec_op_array.restype = L.rec_level_array.restype = L.rec_coarsest.restype = ctypes.c_long
+
+    def arr(fn, args, dt):
+        n = fn(*args, None)
+        a = np.zeros(max(n, 0), dt)
+        if n > 0:
+            fn(*args, a.ctypes.data_as(ctypes.c_void_p))
+        return a
+
+    fields = [("nnzPerRow_local", I32), ("col_local", I32), ("val_local", F64), ("row_remote", I32), ("val_remote", F64),
+              ("nnzPerCol_remote", I32), ("vIndex", I32), ("sendProcRank", I32), ("sendProcCount", I32), ("vdispls", I32),
+              ("recvProcRank", I32), ("recvProcCount", I32), ("rdispls", I32)]
+    checked = 0
+    for l, lv in enumerate(h.levels):
+        for k, op in ((0, lv.A), (1, lv.P), (2, lv.R)):
+            if op is None:
+                continue
+            sc = (ctypes.c_long * 8)()
+            L.rec_op_scalars(l, k, sc)
+            want = (1, op.M, op.n_local_cols, op.col_offset, int(op.use_double), op.nnz_local, op.nnz_remote,
+                    op.col_remote_size)
+            assert tuple(sc) == want or (op.M == 0 and tuple(sc)[:4] == (1, 0, 0, 0)), (l, k, tuple(sc), want)
+            for f, (name, dt) in enumerate(fields):
+                got, ref_a = arr(L.rec_op_array, (l, k, f), dt), np.asarray(getattr(op, name), dt)
+                assert got.shape == ref_a.shape and np.array_equal(got, ref_a), (l, "APR"[k], name, got[:8], ref_a[:8])
+                checked += 1
+        eig, mo, mn = ctypes.c_double(0), ctypes.c_int(0), ctypes.c_int(0)
+        assert L.rec_level_aux(l, ctypes.byref(eig), ctypes.byref(mo), ctypes.byref(mn)) == 0
+        assert np.array_equal(arr(L.rec_level_array, (l, 0), F64), lv.inv_diag), (l, "inv_diag")
+        if lv.A.M:
+            assert eig.value == lv.eig_max
+        if lv.P is not None:
+            assert (mo.value, mn.value) == (lv.M_coarse_old, lv.M_coarse), (l, mo.value, mn.value, lv.M_coarse_old, lv.M_coarse)
+            if size > 1:
+                assert arr(L.rec_level_array, (l, 1), I32).reshape(-1, 3).tolist() == [list(b) for b in lv.repart_send], (l, "send")
+                assert arr(L.rec_level_array, (l, 2), I32).reshape(-1, 3).tolist() == [list(b) for b in lv.repart_recv], (l, "recv")
+    assert r_coarse_n == h.coarse_n
+    if h.coarse_n:
+        assert np.array_equal(arr(L.rec_coarsest, (0,), I32), h.coarse_row)
+        assert np.array_equal(arr(L.rec_coarsest, (1,), I32), h.coarse_col)
+        assert np.array_equal(arr(L.rec_coarsest, (2,), F64), h.coarse_val)
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, f"adaptor_ok_{rank}"), "w") as f:
+        f.write(f"{checked} arrays, {len(h.levels)} levels, "
+                f"{sum(lv.A.M == 0 for lv in h.levels)} level(s) this rank is not a member of\n")
+
+
 def main():
     what, mx, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
     reps = int(sys.argv[4]) if len(sys.argv) > 4 else 0
@@ -34,6 +94,12 @@ def main():
         s = ref.RefSolver.from_coo(n, row[keep], col[keep], val[keep], unstructured2d_rhs(n)[lo:hi], rhs_offset=lo)
     else:
         raise SystemExit(f"unknown workload {what}")
+    if os.environ.get("SAENA_MP_ADAPTOR_CHECK"):
+        check_adaptor_upload(L, s, rank, size, out)
+        s.close()
+        L.sref_barrier()
+        L.sref_finalize()
+        return
     u, iters, hist = s.solve_pcg()
     res = dict(u=u, iters=np.array([iters]), hist=hist, rank=np.array([rank]), size=np.array([size]))
     if os.environ.get("SAENA_MP_DUMP"):

@@ -20,7 +20,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # the ranks of `python -m oracle.mprun` (SBMPI_SIZE set) load the build against the multi-process MPI
 # stand-in (make -C oracle ref_mp); everything else the one-rank build
 MP_LIB_PATH = os.path.join(_HERE, "_ref", "libsaena_ref_mp.so")
-LIB_PATH = MP_LIB_PATH if os.environ.get("SBMPI_SIZE") else os.path.join(_HERE, "_ref", "libsaena_ref.so")
+LIB_PATH = (os.environ.get("SAENA_REF_LIB_PATH")     # an explicit build, e.g. the adaptor-recording one
+            or (MP_LIB_PATH if os.environ.get("SBMPI_SIZE") else os.path.join(_HERE, "_ref", "libsaena_ref.so")))
+REC_LIB_PATH = os.path.join(_HERE, "_ref", "libsaena_dropin_rec_mp.so")
 
 
 def mp_available() -> bool:
