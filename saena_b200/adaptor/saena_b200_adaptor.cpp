@@ -72,6 +72,7 @@ saena_b200_ctx *new_context(MPI_Comm comm, int &rank, int &nprocs) {
     const char *lr = std::getenv("OMPI_COMM_WORLD_LOCAL_RANK");
     if (!lr) lr = std::getenv("MV2_COMM_WORLD_LOCAL_RANK");
     if (!lr) lr = std::getenv("LOCAL_RANK");
+    if (!lr) lr = std::getenv("SBMPI_RANK");   // oracle/mprun.py (the tests' multi-process MPI stand-in, one node)
     const int device = lr ? std::atoi(lr) : 0;
     saena_b200_ctx *ctx = nullptr;
     CK(nullptr, saena_b200_init(&ctx, device, rank, nprocs, nprocs > 1 ? id : nullptr), "init");

@@ -35,3 +35,29 @@ def test_public_api_solve_pcg_on_gpu_matches_reference_cpu_solve(mx):
     assert hg[ng.value - 1] / hg[0] < 1e-8
     assert du.value < 1e-8
     assert dmv.value < TOL_OP
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+LIB_MP = os.path.join(os.path.dirname(LIB), "libsaena_dropin_mp.so")
+
+
+@pytest.mark.skipif(not os.path.exists(LIB_MP) or _ngpu() < 2, reason="needs libsaena_dropin_mp.so and >= 2 GPUs")
+@pytest.mark.xfail(strict=False, reason="first run of the drop-in on several MPI ranks with GPUs behind it (written after "
+                                        "the round's GPU budget was spent); its upload walk is green on CPU: "
+                                        "tests/test_adaptor_multirank.py")
+@pytest.mark.parametrize("ranks,mx", [(2, 18), (4, 26)])
+def test_public_api_on_several_mpi_ranks_matches_the_multirank_reference(ranks, mx):
+    """the reference's driver on `ranks` MPI ranks (multi-process MPI stand-in), one GPU per rank: GPU solve through
+    the public API vs the reference's own multi-rank CPU solve on the same hierarchy object"""
+    import sys
+    from oracle import mprun
+    if _ngpu() < ranks:
+        pytest.skip(f"needs {ranks} GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rc, outs = mprun.run(ranks, [sys.executable, os.path.join(root, "tests", "dropin_mp_worker.py"), str(mx)], timeout=600,
+                         env=dict(os.environ, PYTHONPATH=root), capture=True)
+    assert rc == 0, "\n".join(o[-2000:] for o in outs)
