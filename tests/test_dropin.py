@@ -58,6 +58,6 @@ def test_public_api_on_several_mpi_ranks_matches_the_multirank_reference(ranks, 
     if _ngpu() < ranks:
         pytest.skip(f"needs {ranks} GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    rc, outs = mprun.run(ranks, [sys.executable, os.path.join(root, "tests", "dropin_mp_worker.py"), str(mx)], timeout=600,
+    rc, outs = mprun.run(ranks, [sys.executable, os.path.join(root, "tests", "dropin_mp_worker.py"), str(mx)], timeout=180,
                          env=dict(os.environ, PYTHONPATH=root), capture=True)
     assert rc == 0, "\n".join(o[-2000:] for o in outs)

@@ -41,7 +41,7 @@ def test_reference_multirank_layout_on_gpus(world):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                           "--master-addr", "127.0.0.1", "--master-port", str(29560 + world),
                           os.path.join(ROOT, "tests", "multigpu_check.py")],
-                         capture_output=True, text=True, timeout=900,
+                         capture_output=True, text=True, timeout=300,
                          env=dict(os.environ, MASTER_ADDR="127.0.0.1", SAENA_MG_REFERENCE_GOLDEN="1"))
     assert out.returncode == 0, out.stdout[-6000:]
     assert "the reference's own" in out.stdout
