@@ -75,6 +75,23 @@ class RefOptions:
                      self.filter_max, self.filter_start, self.filter_rate)
 
 
+def write_options_xml(path: str, o: "RefOptions | None" = None) -> str:
+    """an options file for the reference's drivers (attributes are read POSITIONALLY, src/saena.cpp:456-539) with
+    the values of RefOptions -- data/options006_poisson.xml's, so the drivers run where /root/reference is absent"""
+    o = o or RefOptions()
+    attrs = [("solver_max_iter", o.max_iter), ("solver_tol", f"{o.tol:g}"), ("smoother", o.smoother),
+             ("preSmooth", o.pre), ("postSmooth", o.post), ("PSmoother", o.psmoother), ("conn_str", f"{o.conn_str:g}"),
+             ("dynamic_levels", int(o.dynamic_levels)), ("max_level", o.max_level), ("float_level", o.float_level),
+             ("filter_thre", f"{o.filter_thre:g}"), ("filter_max", f"{o.filter_max:g}"), ("filter_start", o.filter_start),
+             ("filter_rate", o.filter_rate), ("switch_to_dense", 0), ("dense_thre", "0.1"), ("dense_sz_thre", 5000),
+             ("petsc", ""), ("eig", 0)]
+    with open(path, "w") as f:
+        f.write('<?xml version="1.0" encoding="utf-8" ?>\n<SAENA>\n    <OPTIONS\n')
+        f.write("\n".join(f'\t{k}="{v}"' for k, v in attrs))
+        f.write("/>\n</SAENA>\n")
+    return path
+
+
 def available() -> bool:
     return os.path.exists(LIB_PATH)
 

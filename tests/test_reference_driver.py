@@ -20,6 +20,15 @@ OPTS = "/root/reference/data/options006_poisson.xml"
 def test_the_reference_driver_runs_config0(ranks):
     from oracle import mprun
     rc, outs = mprun.run(ranks, [EXE, "34", OPTS], timeout=600, capture=True)
+    if ranks == 1:
+        # the options file oracle.ref.write_options_xml generates (for boxes without /root/reference) is equivalent
+        from oracle import ref
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            rc2, outs2 = mprun.run(1, [EXE, "34", ref.write_options_xml(os.path.join(d, "o.xml"))], timeout=600, capture=True)
+        assert rc2 == 0
+        pick = lambda t: re.findall(r"(Smoother:.*|Max iter.*|Filter:.*|stopped at iteration.*|number of levels.*)", t)  # noqa: E731
+        assert pick(outs2[0]) == pick(outs[0])
     assert rc == 0, outs[0][-2000:]
     text = outs[0]
     assert f"Number of MPI tasks: {ranks}" in text
