@@ -72,6 +72,7 @@ static int init_common(saena_b200_ctx **ctx_out, int device_id, int rank, int nr
     ctx->detached = detached;
     if (const char *gm = getenv("SAENA_B200_GRAPH_MULTI")) ctx->use_graphs_multi = atoi(gm) != 0;
     if (const char *hf = getenv("SAENA_B200_HALO_FUSED")) ctx->fused_default = atoi(hf) != 0;
+    if (const char *nv = getenv("SAENA_B200_NVTX")) ctx->nvtx = atoi(nv) != 0;
     if (init_body(ctx, nccl_id)) {
         g_sb_init_error = ctx->error;
         delete ctx;
@@ -368,16 +369,17 @@ static int pcg_device(saena_b200_ctx *ctx, const double *rhs, double *u, int max
     const double THRSHLD = init_dot * tol * tol;  // :2558
     SB_TRY(sb_dot(ctx, r, l0.u[l0.cur], n, S_RHO_RES));  // first <r,rho> (:2580)
     for (i = 0; i < max_iter; i++) {
+        SbRange it_range(ctx, "pcg iteration");
         EpiArgs e{};
         e.out = h;
-        SB_TRY(sb_apply(ctx, l0.A, p, EPI_PLAIN, e));  // h = A p (:2571)
-        SB_TRY(sb_dot(ctx, p, h, n, S_PDOTH));         // :2581
+        { SbRange rg(ctx, "L0matvec"); SB_TRY(sb_apply(ctx, l0.A, p, EPI_PLAIN, e)); }  // h = A p (:2571)
+        { SbRange rg(ctx, "dots"); SB_TRY(sb_dot(ctx, p, h, n, S_PDOTH)); }             // :2581
         SB_TRY(sb_pcg_update(ctx, n, u, r, p, h));     // :2588-2603
         SB_TRY(sb_read_scalars(ctx));
         current_dot = ctx->scalars_host[S_RR];
         push_hist(current_dot, hist, hist_cap, nh);
         if (!(current_dot >= THRSHLD)) break;          // :2620 (NaN also stops)
-        SB_TRY(sb_vcycle_from_zero(ctx, smoother, pre, post, r));  // :2640-2641
+        { SbRange rg(ctx, "vcycle_pCG"); SB_TRY(sb_vcycle_from_zero(ctx, smoother, pre, post, r)); }  // :2640-2641
         SB_TRY(sb_dot(ctx, r, l0.u[l0.cur], n, S_BETA_NUM));      // :2655
         SB_TRY(sb_pcg_p_update(ctx, n, p, l0.u[l0.cur]));          // :2662-2667
     }

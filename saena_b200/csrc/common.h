@@ -223,6 +223,7 @@ struct saena_b200_ctx {
     std::vector<DevLevel> levels;
     bool finalized = false;
     bool use_graphs = true;
+    bool nvtx = false;               // SAENA_B200_NVTX=1
     bool use_graphs_multi = true;   // capture with nranks > 1 too (SAENA_B200_GRAPH_MULTI=0 turns it off)
     int64_t graph_replays = 0;
     std::vector<VcycleGraph> graphs;
@@ -275,6 +276,17 @@ static const int SB_MAPPING_SELL = 100;   // forced_mapping / set_mapping code o
 static const int STREAM_TILE = 2048;      // nnz per row block of the streaming kernel (16 KB of products)
 static const int STREAM_THREADS = 256;
 static const int RED_MAX_BLOCKS = 1184;   // 148 SMs x 8
+
+// ---------------------------------------------------------------------------------------------
+// NVTX ranges (SAENA_B200_NVTX=1): the stages the reference's PROFILE_PCG / PROFILE_VCYCLE builds time
+// (/root/reference/include/saena_object.h:24-26, :434-440 -- Rtransfer, Ptransfer, smooth, coarsest, residual,
+// repart, dots, level-0 matvec), as named ranges for a timeline profiler.  Off by default: no call is made.
+// ---------------------------------------------------------------------------------------------
+struct SbRange {
+    bool on;
+    SbRange(const saena_b200_ctx *ctx, const char *name, int level = -1);
+    ~SbRange();
+};
 
 // ---- operator.cu
 int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d);

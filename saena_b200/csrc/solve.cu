@@ -86,6 +86,7 @@ int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const
     DevLevel &lv = ctx->levels[l];
     // solve.cpp:991-1057 coarsest level: direct solve on the rank that owns it
     if (l == max_level) {
+        SbRange rg(ctx, "coarsest", l);
         if (lv.M > 0 && ctx->coarsest_cg) {
             // direct_solver == "CG" (:998-999): u is the initial guess of solve_coarsest_CG
             if (!lv.A.sends.empty() || !lv.A.recvs.empty()) SB_FAIL("vcycle: the coarsest level must live on one rank");
@@ -99,12 +100,13 @@ int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const
     }
     DevLevel &cl = ctx->levels[l + 1];
     // 1. pre-smooth (:1105-1107)
-    if (pre) SB_TRY(sb_smooth(ctx, l, smoother, pre, rhs, u_is_zero));
+    if (pre) { SbRange rg(ctx, "pre-smooth", l); SB_TRY(sb_smooth(ctx, l, smoother, pre, rhs, u_is_zero)); }
     else if (u_is_zero) SB_TRY(sb_fill_zero(ctx, lv.u[lv.cur], lv.M));
     // 2. residual res = A u - rhs (:1140); with a zero iterate and no pre-smoothing it is -rhs
     if (pre == 0 && u_is_zero) {
         SB_TRY(sb_negate_copy(ctx, lv.M, rhs, lv.res));
     } else {
+        SbRange rg(ctx, "residual", l);
         EpiArgs e{};
         e.rhs = rhs;
         e.out = lv.res;
@@ -112,6 +114,7 @@ int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const
     }
     // 3. restrict (:1175) into the coarse grid's rhs, through the old partition if they differ
     {
+        SbRange rg(ctx, "Rtransfer", l);
         EpiArgs e{};
         const bool ident = lv.repart.identity();
         e.out = ident ? cl.rhs : lv.xfer_old;
@@ -126,6 +129,7 @@ int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const
     if (ctx->scale) SB_TRY(sb_scale_vector(ctx, cl.M, cl.u[cl.cur], cl.inv_sq_diag));
     // 5. + 6. prolong and correct: u -= P e_c (:1301-1303, :1325, :1360-1361)
     {
+        SbRange rg(ctx, "Ptransfer", l);
         const double *ec = cl.u[cl.cur];
         if (!lv.repart.identity()) {
             SB_TRY(sb_repart(ctx, lv.repart, true, ec, lv.xfer_old, ctx->stream));
@@ -137,7 +141,7 @@ int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const
         SB_TRY(sb_apply(ctx, lv.P, ec, EPI_SUB, e));
     }
     // 7. post-smooth (:1397-1399)
-    if (post) SB_TRY(sb_smooth(ctx, l, smoother, post, rhs, false));
+    if (post) { SbRange rg(ctx, "post-smooth", l); SB_TRY(sb_smooth(ctx, l, smoother, post, rhs, false)); }
     return 0;
 }
 

@@ -7,6 +7,9 @@
 // Reductions are deterministic: every CTA writes one partial, the last CTA to finish (atomic
 // ticket) adds the partials in index order.  The scalars of the Krylov recurrences live in
 // device memory (ctx->scalars) so alpha/beta never round-trip through the host.
+#include <nvtx3/nvToolsExt.h>
+#include <stdio.h>
+
 #include "common.h"
 
 static inline int red_blocks(const saena_b200_ctx *ctx, int n) {
@@ -314,4 +317,17 @@ int sb_read_scalars(saena_b200_ctx *ctx) {
                             ctx->stream));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NVTX ranges (see common.h)
+// ---------------------------------------------------------------------------------------------
+SbRange::SbRange(const saena_b200_ctx *ctx, const char *name, int level) : on(ctx->nvtx) {
+    if (!on) return;
+    char buf[64];
+    if (level >= 0) snprintf(buf, sizeof(buf), "%s L%d", name, level);
+    nvtxRangePushA(level >= 0 ? buf : name);
+}
+SbRange::~SbRange() {
+    if (on) nvtxRangePop();
 }
