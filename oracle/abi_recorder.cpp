@@ -44,6 +44,7 @@ struct saena_b200_ctx {
 };
 
 static saena_b200_ctx *g_last = nullptr;
+static int g_inits = 0;
 
 template <class T>
 static void copy_in(std::vector<T> &dst, const T *src, size_t n) {
@@ -60,6 +61,7 @@ int saena_b200_init(saena_b200_ctx **ctx_out, int device_id, int rank, int nrank
     c->rank = rank; c->nranks = nranks;
     *ctx_out = c;
     g_last = c;
+    ++g_inits;
     return 0;
 }
 int saena_b200_destroy(saena_b200_ctx *ctx) { if (g_last == ctx) g_last = nullptr; delete ctx; return 0; }
@@ -148,6 +150,7 @@ int rec_info(int *rank, int *nranks, int *levels, int *coarse_n, int *solves) {
     *coarse_n = g_last->coarse_n; *solves = g_last->solves;
     return 0;
 }
+int rec_inits() { return g_inits; }
 // out[8]: present, M, n_local_cols, col_offset, use_double, nnz_local, nnz_remote, col_remote_size
 int rec_op_scalars(int level, int kind, long *out) {
     const RecOp &o = g_last->levels[level].op[kind];

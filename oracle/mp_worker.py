@@ -70,6 +70,17 @@ def check_adaptor_upload(L, s, rank, size, out):
         assert np.array_equal(arr(L.rec_coarsest, (0,), I32), h.coarse_row)
         assert np.array_equal(arr(L.rec_coarsest, (1,), I32), h.coarse_col)
         assert np.array_equal(arr(L.rec_coarsest, (2,), F64), h.coarse_val)
+    if os.environ.get("SAENA_MP_ADAPTOR_UPDATE"):
+        # what a lazy update does (grids[0].A replaced by a matrix with other values; update1/2/3 themselves are
+        # compiled out in this version of the reference): the next solve through the public API must upload again,
+        # and what it uploads must be the new values
+        before = arr(L.rec_op_array, (0, 0, 2), F64).copy()
+        assert L.rec_inits() == 1
+        L.sref_replace_A0_scaled_poisson(s._h, int(os.environ["SAENA_MP_ADAPTOR_UPDATE"]), ctypes.c_double(3.0))
+        s.time_solve_pcg(1)
+        assert L.rec_inits() == 2, "the adaptor kept solving on the stale device copy"
+        after = arr(L.rec_op_array, (0, 0, 2), F64)
+        assert after.shape == before.shape and np.allclose(after, 3.0 * before, rtol=1e-15)
     os.makedirs(out, exist_ok=True)
     with open(os.path.join(out, f"adaptor_ok_{rank}"), "w") as f:
         f.write(f"{checked} arrays, {len(h.levels)} levels, "

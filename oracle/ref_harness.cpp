@@ -154,6 +154,30 @@ void *sref_coo_new(int n, long nnz, const int *row, const int *col, const double
     return h;
 }
 
+// What a lazy update does to the solver object -- grids[0].A replaced by a matrix of the same pattern and other
+// values, the coarse operators kept (saena_object::update1, src/saena_object_lazy.cpp:7-35).  In this version of
+// the reference the bodies of update1/2/3 are compiled out (#if 0), so the replacement is done here directly;
+// the point is the drop-in's reaction (tests/test_adaptor_multirank.py).  The new matrix is kept alive.
+int sref_replace_A0_scaled_poisson(void *hv, int mx, double factor) {
+    Handle *h = (Handle *)hv;
+    MPI_Comm comm = MPI_COMM_WORLD;
+    QuietStdout q(true);
+    saena::matrix *A2 = new saena::matrix(comm);
+    saena::laplacian3D(A2, mx, mx, mx);
+    A2->set_remove_boundary(true);
+    A2->assemble(false);
+    saena_matrix *m = A2->get_internal_matrix();
+    for (nnz_t i = 0; i < m->nnz_l_local; ++i) m->val_local[i] *= factor;
+    for (nnz_t i = 0; i < m->nnz_l_remote; ++i) m->val_remote[i] *= factor;
+    for (index_t i = 0; i < m->M; ++i) m->inv_diag[i] /= factor;
+    for (auto &e : m->entry) e.val *= factor;
+    saena_object *o = obj(h);
+    m->eig_max_of_invdiagXA = o->grids[0].A->eig_max_of_invdiagXA;   // as update1 does
+    m->use_double = o->grids[0].A->use_double;
+    o->grids[0].A = m;
+    return 0;
+}
+
 // multi-rank runs (oracle/mprun.py): who am I, and a clean shutdown of the MPI stand-in
 int sref_rank() { ensure_mpi(); int r = 0; MPI_Comm_rank(MPI_COMM_WORLD, &r); return r; }
 int sref_size() { ensure_mpi(); int s = 1; MPI_Comm_size(MPI_COMM_WORLD, &s); return s; }

@@ -41,6 +41,11 @@ namespace {
 struct DeviceSide {
     saena_b200_ctx *ctx = nullptr;
     int rank = 0, nprocs = 1;
+    // what the upload was made from: a second set_matrix, or a lazy update (saena_object::update1/2/3,
+    // src/saena_object_lazy.cpp:7-209 -- bodies compiled out in this version of the reference), replaces
+    // grids[0].A; the device copy is then stale and is rebuilt on the next solve
+    const saena_matrix *A0 = nullptr;
+    int max_level = -1;
 };
 
 std::map<const saena_object *, DeviceSide> g_solvers;
@@ -191,9 +196,17 @@ void upload_PR(saena_b200_ctx *ctx, Op &op, int kind, int level, int n_rows, int
 // Walk saena_object::grids (include/saena_object.h:189, include/grid.h) and upload once.
 DeviceSide &device_side(saena_object *obj) {
     auto it = g_solvers.find(obj);
-    if (it != g_solvers.end()) return it->second;
+    if (it != g_solvers.end()) {
+        if (it->second.A0 == obj->grids[0].A && it->second.max_level == obj->max_level) return it->second;
+        // the hierarchy changed under the solver object (update1/2/3, set_matrix again): upload it anew
+        if (g_verbose && it->second.rank == 0) std::printf("saena_b200: hierarchy changed, uploading again\n");
+        saena_b200_destroy(it->second.ctx);
+        g_solvers.erase(it);
+    }
     DeviceSide ds;
     saena_matrix *A0 = obj->grids[0].A;
+    ds.A0 = A0;
+    ds.max_level = obj->max_level;
     ds.ctx = new_context(A0->comm, ds.rank, ds.nprocs);
     const int L = obj->max_level;
     const std::vector<double> no_diag(1, 0.0);

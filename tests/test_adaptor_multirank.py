@@ -29,3 +29,19 @@ def test_adaptor_uploads_what_the_reference_laid_out(ranks, what, size, tmp_path
                                   PYTHONPATH=ROOT), capture=True)
     assert rc == 0, "\n".join(o[-1500:] for o in outs)
     assert len(glob.glob(os.path.join(out, "adaptor_ok_*"))) == ranks
+
+
+@pytest.mark.parametrize("ranks", [1, 3])
+def test_adaptor_uploads_again_after_a_lazy_update(ranks, tmp_path):
+    """a lazy update (saena::amg::update1, src/saena_object_lazy.cpp:7-35 -- compiled out in this version of the
+    reference, so its effect is applied directly) replaces grids[0].A with a matrix of other values; the drop-in
+    keeps its device copy keyed by the solver object, so it must notice and upload again"""
+    from oracle import mprun, ref
+    if not os.path.exists(ref.REC_LIB_PATH):
+        pytest.skip("oracle/_ref/libsaena_dropin_rec_mp.so not built (make -C oracle dropin_rec_mp)")
+    out = str(tmp_path / "rec")
+    rc, outs = mprun.run(ranks, [sys.executable, "-m", "oracle.mp_worker", "poisson", "14", out], timeout=600,
+                         env=dict(os.environ, SAENA_MP_ADAPTOR_CHECK="1", SAENA_MP_ADAPTOR_UPDATE="14",
+                                  SAENA_REF_LIB_PATH=ref.REC_LIB_PATH, PYTHONPATH=ROOT), capture=True)
+    assert rc == 0, "\n".join(o[-1500:] for o in outs)
+    assert len(glob.glob(os.path.join(out, "adaptor_ok_*"))) == ranks
