@@ -142,10 +142,10 @@ def cpu_reference_solve_multirank(reps: int, warmup: int, ranks: int, mx: int):
 def cpu_reference_solve(reps: int, warmup: int = 0, mx: int = CPU_SAMPLE_MX):
     from oracle import ref
     n = (mx - 2) ** 3
-    ranks = min(host_cores(), int(os.environ.get("SAENA_BENCH_CPU_RANKS", 16)))
+    ranks = min(host_cores(), int(os.environ.get("SAENA_BENCH_CPU_RANKS", 32)))
     if ref.mp_available() and ranks > 1:
         try:
-            # a larger sample than the one-rank arm: 64^3 unknowns keep >= 16 k rows per rank at 16 ranks
+            # a larger sample than the one-rank arm: 64^3 unknowns keep >= 8 k rows per rank at 32 ranks
             return cpu_reference_solve_multirank(reps, warmup, ranks, int(os.environ.get("SAENA_BENCH_CPU_MX_MP", 66)))
         except Exception as e:   # fall back to the one-rank build below
             log(f"[reference arm] multi-rank run failed ({e!r}); falling back to one rank")
