@@ -93,8 +93,11 @@ def main():
     warmup = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     L = ref.lib()
     rank, size = L.sref_rank(), L.sref_size()
+    # SAENA_MP_FLOAT_LEVEL: the options file's float_level (0 = the drivers' value: ghost values travel as float on
+    # every level; >= the level count: every halo in double)
+    opts = ref.RefOptions(float_level=int(os.environ.get("SAENA_MP_FLOAT_LEVEL", "0")))
     if what == "poisson":
-        s = ref.RefSolver.poisson(mx)
+        s = ref.RefSolver.poisson(mx, opts)
     elif what == "unstructured":
         # BASELINE.json configs[4]'s synthetic shape, g = mx: every rank hands the reference its own block of
         # rows of the COO (saena::matrix::set + assemble repartition it by nnz)
@@ -102,7 +105,7 @@ def main():
         n, row, col, val = unstructured2d_coo(mx)
         lo, hi = n * rank // size, n * (rank + 1) // size
         keep = (row >= lo) & (row < hi)
-        s = ref.RefSolver.from_coo(n, row[keep], col[keep], val[keep], unstructured2d_rhs(n)[lo:hi], rhs_offset=lo)
+        s = ref.RefSolver.from_coo(n, row[keep], col[keep], val[keep], unstructured2d_rhs(n)[lo:hi], opts, rhs_offset=lo)
     else:
         raise SystemExit(f"unknown workload {what}")
     if os.environ.get("SAENA_MP_ADAPTOR_CHECK"):
