@@ -1,0 +1,27 @@
+"""The distributed setup that feeds the multi-GPU bench (saena_b200/sa_setup_dist.py) on N CPU processes over
+gloo, against the one-process setup -- tests/dist_setup_check.py does the comparing."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("world,args,env", [
+    (2, ["poisson", "12", "esc", "double"], {}),
+    (2, ["poisson", "16", "dense", "double"], {}),          # sparse x dense column blocks on every level
+    (3, ["poisson", "20"], {}),                             # float halo (float_level 0, the drivers' value)
+    (3, ["unstructured", "60", "double"], {"DSC_AGG_BELOW": "50"}),
+    (4, ["poisson", "14", "double"], {"DSC_AGG_BELOW": "20"}),   # nothing agglomerated but the coarsest level
+], ids=["np2-poisson12-esc", "np2-poisson16-dense", "np3-poisson20-floathalo", "np3-unstructured60", "np4-poisson14"])
+def test_distributed_setup_equals_the_one_process_setup(world, args, env):
+    port = 29720 + world + len(args[1])
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(ROOT, "tests", "dist_setup_check.py"), *args],
+                         capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1", **env))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-6000:]
+    assert "DIST_SETUP_OK" in out.stdout
