@@ -210,6 +210,10 @@ def main():
     ap.add_argument("--row-lengths", default="6,8,10", help="unstructured2d: entries per row drawn from these "
                                                             "(donor P2: 6,8,10; P8: 24,32,40)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dist-setup", default="auto", choices=["auto", "on", "off"],
+                    help="N>1: build the hierarchy row-partitioned over the ranks (saena_b200/sa_setup_dist.py) instead of "
+                         "redundantly on every GPU; auto = on when the problem is beyond one GPU's setup (n > 320: "
+                         "BASELINE.json configs[2], 512^3 on 8 GPUs)")
     ap.add_argument("--agglomerate-below", type=int, default=10_000,
                     help="N>1: levels with fewer global rows live on rank 0 (the reference's shrink-to-one-rank)")
     ap.add_argument("--rebalance-above", type=float, default=float(os.environ.get("SAENA_BENCH_REBALANCE", 1.10)),
@@ -245,21 +249,35 @@ def main():
     # ---- setup (untimed): hierarchy of the reference's shape, built on this rank's GPU
     n = args.n
     t0 = time.perf_counter()
-    if args.workload == "poisson3d":
-        N, row, col, val = poisson3d_coo(n)
+    dist_setup = world > 1 and args.workload == "poisson3d" and (args.dist_setup == "on" or
+                                                                 (args.dist_setup == "auto" and n > 320))
+    verbose = rank == 0 and bool(os.environ.get("SAENA_BENCH_VERBOSE"))
+    agg_sweep = []
+    if dist_setup:
+        # every rank generates and coarsens only its own rows; what comes out is already this rank's share
+        from saena_b200 import sa_setup_dist as sd
+        comm = sd.Comm(torch.device("cuda", local))
+        N = n ** 3
+        hier, summary = sd.build_distributed_hierarchy(sd.poisson3d_dcsr(n, comm), agglomerate_below=args.agglomerate_below,
+                                                       rebalance_above=args.rebalance_above, verbose=verbose, comm=comm)
+        if rank == 0:
+            log(f"[setup] hierarchy built on {world} ranks in {time.perf_counter() - t0:.1f}s\n" + "\n".join(summary))
     else:
-        lengths = tuple(int(x) for x in args.row_lengths.split(","))
-        weights = (16, 48, 20) if len(lengths) == 3 else (1,) * len(lengths)   # the donors' 16:48:20 proportions
-        N, row, col, val = unstructured2d_coo(args.g, row_lengths=lengths, weights=weights)
-    dh = build_device_hierarchy(N, row, col, val, verbose=(rank == 0 and bool(os.environ.get("SAENA_BENCH_VERBOSE"))))
-    del row, col, val
-    if rank == 0:
-        log(f"[setup] hierarchy built in {time.perf_counter() - t0:.1f}s\n{dh.summary()}")
-    hier = dh.to_rank(rank, world, agglomerate_below=args.agglomerate_below if world > 1 else 0,
-                      rebalance_above=args.rebalance_above if world > 1 else 0.0)
-    agg_sweep = [int(x) for x in filter(None, os.environ.get("SAENA_BENCH_AGG_SWEEP", "").split(","))] if world > 1 else []
-    if not agg_sweep:
-        del dh
+        if args.workload == "poisson3d":
+            N, row, col, val = poisson3d_coo(n)
+        else:
+            lengths = tuple(int(x) for x in args.row_lengths.split(","))
+            weights = (16, 48, 20) if len(lengths) == 3 else (1,) * len(lengths)   # the donors' 16:48:20 proportions
+            N, row, col, val = unstructured2d_coo(args.g, row_lengths=lengths, weights=weights)
+        dh = build_device_hierarchy(N, row, col, val, verbose=verbose)
+        del row, col, val
+        if rank == 0:
+            log(f"[setup] hierarchy built in {time.perf_counter() - t0:.1f}s\n{dh.summary()}")
+        hier = dh.to_rank(rank, world, agglomerate_below=args.agglomerate_below if world > 1 else 0,
+                          rebalance_above=args.rebalance_above if world > 1 else 0.0)
+        agg_sweep = [int(x) for x in filter(None, os.environ.get("SAENA_BENCH_AGG_SWEEP", "").split(","))] if world > 1 else []
+        if not agg_sweep:
+            del dh
     torch.cuda.empty_cache()
     ctx = native.Context(device=local, rank=rank, nranks=world, nccl_id=nccl_id)
     ctx.upload_hierarchy(hier)
@@ -281,9 +299,12 @@ def main():
     if rank == 0:
         log(f"[setup] uploaded in {time.perf_counter() - t0:.1f}s total")
     l0 = hier.levels[0].A
-    rhs_full = poisson3d_rhs(n) if args.workload == "poisson3d" else unstructured2d_rhs(N)
-    rhs_host = torch.from_numpy(rhs_full[l0.row_offset:l0.row_offset + l0.M].copy()).pin_memory()
-    del rhs_full
+    if dist_setup:
+        rhs_host = torch.from_numpy(sd.poisson3d_rhs_rows(n, l0.row_offset, l0.row_offset + l0.M)).pin_memory()
+    else:
+        rhs_full = poisson3d_rhs(n) if args.workload == "poisson3d" else unstructured2d_rhs(N)
+        rhs_host = torch.from_numpy(rhs_full[l0.row_offset:l0.row_offset + l0.M].copy()).pin_memory()
+        del rhs_full
     u_host = torch.empty(l0.M, dtype=torch.float64).pin_memory()
     rhs_dev = rhs_host.cuda()
     u_dev = torch.zeros(l0.M, dtype=torch.float64, device="cuda")
@@ -436,7 +457,7 @@ def main():
     if args.workload == "poisson3d":
         metric = METRIC
         workload = (f"3D 7-point Poisson {n}^3 = {total_unknowns} unknowns, AMG-PCG to 1e-8 "
-                    f"(BASELINE.json configs[1] at n=256)")
+                    + ("(BASELINE.json configs[2])" if n == 512 else "(BASELINE.json configs[1] at n=256)"))
     else:
         metric = "AMG-PCG solve throughput, synthetic 2D Helmholtz-like unstructured matrix, rel. residual 1e-8 (unknowns solved per second)"
         workload = (f"synthetic 2D Helmholtz-like matrix, unstructured-mesh pattern, {args.g}^2 = {total_unknowns} rows, "
@@ -446,7 +467,10 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload,
                        "options": "options006_poisson.xml: chebyshev 3+3, conn_str 0.2, float_level 0, max_iter 50",
-                       "levels": len(hier.levels), "partition": f"{world} row block(s), nnz-balanced" + (
+                       "levels": len(hier.levels),
+                       "setup": ("row-partitioned over the ranks (saena_b200/sa_setup_dist.py), untimed" if dist_setup else
+                                 "on one device (saena_b200/sa_setup.py), every rank keeps its share, untimed"),
+                       "partition": f"{world} row block(s), nnz-balanced" + (
                            f"; coarse levels follow the level above, re-split when a rank exceeds "
                            f"{args.rebalance_above:g}x the mean nnz; levels under {args.agglomerate_below} rows on rank 0"
                            if world > 1 else ""),

@@ -8,7 +8,11 @@ values to summation order, same Chebyshev bounds.  Then the multi-rank oracle so
 shares (halo plan, repartition plan and agglomeration included) and must reproduce the one-rank
 oracle's PCG run on the one-process hierarchy.
 
-usage: dist_setup_check.py poisson <n> | unstructured <g>   [dense]"""
+With DSC_GPU=1 (one process per GPU, NCCL; tests/test_multigpu.py) the setup runs on the GPUs and every rank
+also uploads its share and solves with the CUDA library: same iteration count and residual history as the
+multi-rank oracle on the same shares.
+
+usage: dist_setup_check.py poisson <n> | unstructured <g>   [dense|esc] [double]"""
 import os
 import sys
 
@@ -50,7 +54,13 @@ def global_coo(ops):
 
 
 def main():
-    dist.init_process_group("gloo")
+    on_gpu = bool(os.environ.get("DSC_GPU"))
+    if on_gpu:
+        local = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     what, size = sys.argv[1], int(sys.argv[2])
     dense = True if "dense" in sys.argv[3:] else (False if "esc" in sys.argv[3:] else None)
@@ -74,7 +84,7 @@ def main():
     shares = [None] * world
     dist.gather_object(h, shares if rank == 0 else None, dst=0)
     if rank == 0:
-        ref = sa_setup.build_device_hierarchy(n, row, col, val, opts, device="cpu")
+        ref = sa_setup.build_device_hierarchy(n, row, col, val, opts, device="cuda" if on_gpu else "cpu")
         assert len(ref.levels) == len(h.levels), (len(ref.levels), len(h.levels))
         for l, lv in enumerate(ref.levels):
             mats = [("A", lv.A, [s.levels[l].A for s in shares])]
@@ -83,13 +93,13 @@ def main():
             for name, M, ops in mats:
                 r, c, v = global_coo(ops)
                 assert sum(op.M for op in ops) == M.n_rows and ops[0].Mbig == M.n_rows and ops[0].Nbig == M.n_cols
-                rr, cc, vv = M.row.numpy(), M.col.numpy(), M.val.numpy()
+                rr, cc, vv = M.row.cpu().numpy(), M.col.cpu().numpy(), M.val.cpu().numpy()
                 assert len(r) == len(rr), (l, name, len(r), len(rr))
                 assert np.array_equal(r, rr) and np.array_equal(c, cc), (l, name, "pattern")
                 err = np.max(np.abs(v - vv)) / np.max(np.abs(vv))
                 assert err < 1e-13, (l, name, err)
             inv = np.concatenate([s.levels[l].inv_diag for s in shares])
-            assert np.allclose(inv, lv.inv_diag.numpy(), rtol=1e-13, atol=0)
+            assert np.allclose(inv, lv.inv_diag.cpu().numpy(), rtol=1e-13, atol=0)
             assert abs(shares[0].levels[l].eig_max - lv.eig_max) < 1e-9 * lv.eig_max, (l, shares[0].levels[l].eig_max, lv.eig_max)
             assert all(s.levels[l].eig_max == shares[0].levels[l].eig_max for s in shares)
             assert all(s.levels[l].A.use_double == lv.a_use_double for s in shares)
@@ -120,6 +130,27 @@ def main():
         assert dev <= tol, dev
         un = np.concatenate(un)
         assert np.linalg.norm(un - u1) / np.linalg.norm(u1) < 1e-7
+        expect = [itn, hn]
+    if on_gpu:
+        # the CUDA library on the shares the distributed setup produced
+        from saena_b200 import native
+        from saena_b200.distributed import exchange_nccl_id, setup_p2p_halo
+        expect = expect if rank == 0 else [None, None]
+        dist.broadcast_object_list(expect, src=0)
+        ctx = native.Context(device=local, rank=rank, nranks=world, nccl_id=exchange_nccl_id(native.nccl_unique_id))
+        ctx.upload_hierarchy(h)
+        setup_p2p_halo(ctx)
+        l0 = h.levels[0].A
+        u, it_gpu, h_gpu = ctx.solve_pcg(rhs[l0.row_offset:l0.row_offset + l0.M])
+        assert it_gpu == expect[0], (it_gpu, expect[0])
+        k = min(len(h_gpu), len(expect[1]))
+        gdev = np.max(np.abs(np.asarray(h_gpu)[:k] - expect[1][:k]) / expect[1][:k])
+        assert gdev <= (1e-9 if float_level else 1e-6), gdev
+        dist.barrier()
+        ctx.close()
+        if rank == 0:
+            print(f"DIST_SETUP_GPU_OK hist_dev={gdev:.2e}", flush=True)
+    if rank == 0:
         print(f"DIST_SETUP_OK world={world} {what} {size} levels={L} spread_levels={len(spread) + 1} iters={itn} "
               f"hist_dev={dev:.2e}\n" + "\n".join(summary), flush=True)
     dist.barrier()
