@@ -25,3 +25,22 @@ def test_distributed_setup_equals_the_one_process_setup(world, args, env):
                          env=dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1", **env))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-6000:]
     assert "DIST_SETUP_OK" in out.stdout
+
+
+def test_one_rank_distributed_setup_is_the_one_process_setup():
+    """no process group: the distributed code path on a single rank gives the one-process hierarchy, array by array"""
+    import numpy as np
+    from saena_b200 import sa_setup, sa_setup_dist as sd
+    from saena_b200.hierarchy import hierarchy_to_arrays
+    n, row, col, val = sa_setup.poisson3d_coo(14)
+    comm = sd.Comm()
+    assert comm.world == 1
+    h, summary = sd.build_distributed_hierarchy(sd.poisson3d_dcsr(14, comm), comm=comm)
+    ref = sa_setup.build_hierarchy(n, row, col, val, device="cpu")
+    a, b = hierarchy_to_arrays(h), hierarchy_to_arrays(ref)
+    assert a.keys() == b.keys() and len(summary) == len(ref.levels)
+    for k in a:
+        if a[k].dtype.kind == "f":
+            assert a[k].shape == b[k].shape and np.allclose(a[k], b[k], rtol=1e-12, atol=1e-300), k
+        else:
+            assert np.array_equal(a[k], b[k]), k
