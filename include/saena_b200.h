@@ -126,6 +126,17 @@ int saena_b200_upload_level_scale(saena_b200_ctx *ctx, int level, const double *
 int saena_b200_upload_coarsest(saena_b200_ctx *ctx, int n, int64_t nnz, const int32_t *row, const int32_t *col,
                                const double *val);
 
+/* saena_matrix::use_dense of an uploaded A operator (include/saena_matrix.h:191; set by the setup when
+ * switch_to_dense is on, the coarse operator's density exceeds dense_thre and Mbig <= dense_sz_thre,
+ * src/saena_object_setup2.cpp:328-329).  The reference then applies the operator through
+ * saena_matrix_dense::matvec (include/saena_matrix.tpp:5-7, src/saena_matrix_dense.cpp:181-340): the same
+ * matrix and the same product, except that with use_double == 0 the WHOLE input vector is cast to float
+ * before it is multiplied -- the rank's own part too (:281-282), where matvec_sparse_float only casts the
+ * ghost values.  The device keeps applying the operator from its sparse arrays (such levels hold at most
+ * dense_sz_thre = 5000 rows: latency-bound either way) and reproduces that cast: the input is rounded
+ * through float on the way into the kernel.  Call after saena_b200_upload_operator, before finalize. */
+int saena_b200_set_operator_dense(saena_b200_ctx *ctx, int level, int kind, int use_dense);
+
 /* saena_object::direct_solver (include/saena_object.h:165): 0 = the direct solve (default, "SuperLU"
  * in the reference, the dense factor here), 1 = solve_coarsest_CG (src/saena_object_solve.cpp:14-114). */
 int saena_b200_set_coarsest_solver(saena_b200_ctx *ctx, int use_cg);

@@ -45,6 +45,7 @@ struct saena_b200_ctx {
 
 static saena_b200_ctx *g_last = nullptr;
 static int g_inits = 0;
+static std::vector<int> g_dense_levels;   // levels the adaptor flagged as saena_matrix::use_dense (last upload)
 
 template <class T>
 static void copy_in(std::vector<T> &dst, const T *src, size_t n) {
@@ -62,6 +63,7 @@ int saena_b200_init(saena_b200_ctx **ctx_out, int device_id, int rank, int nrank
     *ctx_out = c;
     g_last = c;
     ++g_inits;
+    g_dense_levels.clear();
     return 0;
 }
 int saena_b200_destroy(saena_b200_ctx *ctx) { if (g_last == ctx) g_last = nullptr; delete ctx; return 0; }
@@ -108,6 +110,15 @@ int saena_b200_upload_coarsest(saena_b200_ctx *ctx, int n, int64_t nnz, const in
     return 0;
 }
 int saena_b200_set_coarsest_solver(saena_b200_ctx *, int) { return 0; }
+int saena_b200_set_operator_dense(saena_b200_ctx *, int level, int kind, int use_dense) {
+    if (kind == 0 && use_dense) g_dense_levels.push_back(level);
+    return 0;
+}
+extern "C" int rec_dense_levels(int *out, int cap) {
+    int n = 0;
+    for (int l : g_dense_levels) if (n < cap) out[n++] = l;
+    return (int)g_dense_levels.size();
+}
 int saena_b200_finalize(saena_b200_ctx *ctx) {
     for (RecLevel &lv : ctx->levels) if (!lv.op[0].present || !lv.aux) { ctx->error = "finalize: a level lacks A or its aux data"; return 1; }
     ctx->finalized = true;

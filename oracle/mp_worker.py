@@ -65,6 +65,10 @@ def check_adaptor_upload(L, s, rank, size, out):
             if size > 1:
                 assert arr(L.rec_level_array, (l, 1), I32).reshape(-1, 3).tolist() == [list(b) for b in lv.repart_send], (l, "send")
                 assert arr(L.rec_level_array, (l, 2), I32).reshape(-1, 3).tolist() == [list(b) for b in lv.repart_recv], (l, "recv")
+    # levels the reference applies through saena_matrix_dense (switch_to_dense): flagged, not refused
+    buf = (ctypes.c_int * 64)()
+    nd = L.rec_dense_levels(buf, 64)
+    assert sorted(buf[:nd]) == [l for l, lv in enumerate(h.levels) if lv.A.use_dense and lv.A.M], (list(buf[:nd]),)
     assert r_coarse_n == h.coarse_n
     if h.coarse_n:
         assert np.array_equal(arr(L.rec_coarsest, (0,), I32), h.coarse_row)

@@ -32,7 +32,8 @@ class _Op(ctypes.Structure):
                 ("nnzPerProcScan", c_long_p), ("vIndexSize", ctypes.c_int), ("vIndex", c_int_p),
                 ("vdispls", c_int_p), ("rdispls", c_int_p), ("numSendProc", ctypes.c_int),
                 ("sendProcRank", c_int_p), ("sendProcCount", c_int_p), ("numRecvProc", ctypes.c_int),
-                ("recvProcRank", c_int_p), ("recvProcCount", c_int_p), ("use_double", ctypes.c_int)]
+                ("recvProcRank", c_int_p), ("recvProcCount", c_int_p), ("use_double", ctypes.c_int),
+                ("use_dense", ctypes.c_int)]
 
 
 class _Block(ctypes.Structure):
@@ -178,7 +179,7 @@ class Oracle:
                    _ip(a["nnzPerCol_remote"]), _lp(a["nnzPerProcScan"]), op.vIndexSize, _ip(a["vIndex"]),
                    _ip(a["vdispls"]), _ip(a["rdispls"]), len(op.sendProcRank), _ip(a["sendProcRank"]),
                    _ip(a["sendProcCount"]), len(op.recvProcRank), _ip(a["recvProcRank"]), _ip(a["recvProcCount"]),
-                   int(op.use_double))
+                   int(op.use_double), int(op.use_dense))
 
     # ---- helpers ----
     def _ops(self, l, kind):

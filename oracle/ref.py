@@ -48,7 +48,8 @@ class _LevelInfo(ctypes.Structure):
                 ("nnz_l", ctypes.c_long), ("nnz_local", ctypes.c_long), ("nnz_remote", ctypes.c_long),
                 ("col_remote_size", ctypes.c_int), ("vIndexSize", ctypes.c_int), ("recvSize", ctypes.c_int),
                 ("numRecvProc", ctypes.c_int), ("numSendProc", ctypes.c_int),
-                ("use_double", ctypes.c_int), ("active", ctypes.c_int), ("eig_max", ctypes.c_double)]
+                ("use_double", ctypes.c_int), ("active", ctypes.c_int), ("eig_max", ctypes.c_double),
+                ("use_dense", ctypes.c_int)]
 
 
 @dataclass
@@ -209,13 +210,13 @@ class RefSolver:
                             nnzPerRow_local=self._arr(l, kind, F_NNZ_PER_ROW_LOCAL, I32),
                             col_local=self._arr(l, kind, F_COL_LOCAL, I32),
                             val_local=self._arr(l, kind, F_VAL_LOCAL, F64),
-                            use_double=bool(info.use_double))
+                            use_double=bool(info.use_double), use_dense=bool(info.use_dense))
         comm = self.level_comm(l)
         if len(comm) == 0:   # not a member of this level's communicator: an empty operator
             return Operator(kind=kind, level=l, M=0, Mbig=0, Nbig=0, row_offset=0, col_offset=0, n_local_cols=0,
                             nnzPerRow_local=np.zeros(0, I32), col_local=np.zeros(0, I32), val_local=np.zeros(0, F64),
                             nnzPerProcScan=np.zeros(W + 1, np.int64), vdispls=np.zeros(W, I32), rdispls=np.zeros(W, I32),
-                            use_double=bool(info.use_double), nprocs=W, rank=me)
+                            use_double=bool(info.use_double), use_dense=bool(info.use_dense), nprocs=W, rank=me)
         rl = int(np.flatnonzero(comm == me)[0])
         # row / column partitions: the fine side is A's split, the coarse side splitNew (the partition R
         # writes into, before Grid::repart_u); P and R do not each fill both of their own copies
@@ -254,7 +255,7 @@ class RefSolver:
                         sendProcRank=comm[self._arr(l, kind, F_SEND_PROC_RANK, I32)].astype(I32),
                         sendProcCount=self._arr(l, kind, F_SEND_PROC_COUNT, I32),
                         recvProcRank=comm[rpr].astype(I32), recvProcCount=rpc,
-                        use_double=bool(info.use_double), nprocs=W, rank=me)
+                        use_double=bool(info.use_double), use_dense=bool(info.use_dense), nprocs=W, rank=me)
 
     def _repart(self, l, which, comm):
         n = lib().sref_repart_plan(self._h, int(l), which, None, None, None)

@@ -97,10 +97,15 @@ struct sref_opts {
     int filter_start, filter_rate;
 };
 
+// switch_to_dense / dense_thre / dense_sz_thre (data/options006_poisson.xml: 0 / 0.1 / 5000) come from the
+// environment so that the options struct the Python side mirrors keeps its layout:
+// SREF_SWITCH_TO_DENSE=1 [SREF_DENSE_THRE=0.1] [SREF_DENSE_SZ_THRE=5000]
 static saena::options *make_opts(const sref_opts *o) {
+    const char *sd = getenv("SREF_SWITCH_TO_DENSE"), *dt = getenv("SREF_DENSE_THRE"), *ds = getenv("SREF_DENSE_SZ_THRE");
     return new saena::options(o->max_iter, o->tol, o->smoother, o->pre, o->post, o->psmoother, o->conn_str,
                               o->dynamic_levels != 0, o->max_level, o->float_level, o->filter_thre,
-                              o->filter_max, o->filter_start, o->filter_rate, false, 0.1f, 5000);
+                              o->filter_max, o->filter_start, o->filter_rate, sd && atoi(sd) != 0,
+                              dt ? (float)atof(dt) : 0.1f, ds ? atoi(ds) : 5000);
 }
 
 void *sref_poisson_new_scaled(int mx, const sref_opts *o, int quiet, int scale);
@@ -230,6 +235,7 @@ struct sref_level_info {
     int col_remote_size, vIndexSize, recvSize, numRecvProc, numSendProc;
     int use_double, active;
     double eig_max;
+    int use_dense;   // saena_matrix::use_dense: matvec goes through saena_matrix_dense (kind 0 only)
 };
 
 static saena_matrix *level_A(Handle *h, int l) { return obj(h)->grids[l].A; }
@@ -249,6 +255,7 @@ int sref_level_info_get(void *hv, int l, int kind, sref_level_info *out) {
         out->col_remote_size = A->col_remote_size; out->vIndexSize = A->vIndexSize; out->recvSize = A->recvSize;
         out->numRecvProc = A->numRecvProc; out->numSendProc = A->numSendProc;
         out->use_double = A->use_double; out->active = A->active; out->eig_max = A->eig_max_of_invdiagXA;
+        out->use_dense = A->use_dense ? 1 : 0;
     } else if (l >= obj(h)->max_level) {
         return 1;
     } else if (kind == 1) {

@@ -19,7 +19,61 @@ static double *dalloc(long n) { return (double *)calloc((size_t)(n > 0 ? n : 1),
 /* ------------------------------------------------------------------ matvec
  * src/saena_matrix_matvec.cpp:9-113 (double halo) and :448-550 (float halo);
  * prolong_matrix.cpp:489-758 and restrict_matrix.cpp:612-871 are the same loops. */
+/* ------------------------------------------------------------------ dense matvec
+ * src/saena_matrix_dense.cpp:181-260 (matvec_dense) and :262-340 (matvec_dense_float), selected by
+ * saena_matrix::matvec when use_dense is set (include/saena_matrix.tpp:5-7).  The dense copy holds the same
+ * entries (convert_saena_matrix, :763-793) and the product is taken block by block, the owner of the
+ * block going round the ring from the rank itself (k = rank .. rank + nprocs - 1, :214-256): per block a
+ * row sum over ascending columns into `tmp`, then w[i] += tmp.  The explicit zeros of the dense rows add
+ * nothing, so the sums below run over the stored entries in the same order.  The float variant casts
+ * the WHOLE vector to float before anything is multiplied (:281-282), the rank's own block included --
+ * unlike matvec_sparse_float, which only casts what travels. */
+static void so_matvec_dense(const so_operator *const *ops, int nranks, const double *const *v, double *const *w) {
+    for (int r = 0; r < nranks; ++r) {
+        const so_operator *A = ops[r];
+        const int dbl = A->use_double;
+        double *tmp = dalloc(A->M);
+        for (int i = 0; i < A->M; ++i) w[r][i] = 0.0;
+        for (int step = 0; step < nranks; ++step) {
+            const int owner = (r + step) % nranks;
+            if (owner == r) {
+                const double *v_p = v[r] - A->col_offset;
+                long iter = 0;
+                for (int i = 0; i < A->M; ++i) {
+                    const int jend = A->nnzPerRow_local[i];
+                    double t = 0.0;
+                    for (int j = 0; j < jend; ++j) {
+                        const double x = v_p[A->col_local[iter + j]];
+                        t += A->val_local[iter + j] * (dbl ? x : (double)(float)x);
+                    }
+                    w[r][i] += t;
+                    iter += jend;
+                }
+                continue;
+            }
+            int k = -1;
+            for (int q = 0; q < A->numRecvProc; ++q)
+                if (A->recvProcRank[q] == owner) k = q;
+            if (k < 0) continue;   /* nothing stored in that block: a block of zeros */
+            for (int i = 0; i < A->M; ++i) tmp[i] = 0.0;
+            long it = A->nnzPerProcScan[owner];
+            const int *npc = A->nnzPerCol_remote + A->rdispls[owner];
+            const int *ids = ops[owner]->vIndex + ops[owner]->vdispls[r];   /* the owner's local ids of my ghost columns */
+            for (int j = 0; j < A->recvProcCount[k]; ++j) {
+                const double x = v[owner][ids[j]];
+                const double xr = dbl ? x : (double)(float)x;
+                for (int i = 0; i < npc[j]; ++i) tmp[A->row_remote[it + i]] += A->val_remote[it + i] * xr;
+                it += npc[j];
+            }
+            for (int i = 0; i < A->M; ++i) w[r][i] += tmp[i];
+        }
+        free(tmp);
+    }
+}
+
 void so_matvec(const so_operator *const *ops, int nranks, const double *const *v, double *const *w) {
+    for (int r = 0; r < nranks; ++r)
+        if (ops[r]->use_dense) { so_matvec_dense(ops, nranks, v, w); return; }
     /* :25-26 / :463-464  pack vSend (as float when !use_double) */
     double **vSend = (double **)calloc((size_t)nranks, sizeof(double *));
     for (int r = 0; r < nranks; ++r) {

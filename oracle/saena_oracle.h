@@ -47,6 +47,7 @@ typedef struct so_operator {
     int numRecvProc;
     const int *recvProcRank, *recvProcCount;
     int use_double;              /* 0: ghost values are cast to float (matvec_sparse_float) */
+    int use_dense;               /* saena_matrix::use_dense: the product goes through saena_matrix_dense */
 } so_operator;
 
 /* (peer, offset, count) block of Grid::repart_u / repart_back_u (grid.cpp:99-163) */

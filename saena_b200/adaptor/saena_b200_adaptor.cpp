@@ -225,11 +225,12 @@ DeviceSide &device_side(saena_object *obj) {
                "upload level aux");
             continue;
         }
-        if (A->use_dense) {
-            std::printf("Error: saena_b200: dense coarse operators (switch_to_dense) are not supported\n");
-            std::exit(EXIT_FAILURE);
-        }
         upload_A(ds.ctx, A, l, lc, ds.nprocs);
+        // switch_to_dense: the reference applies this level through saena_matrix_dense (include/saena_matrix.tpp:5-7).
+        // The sparse arrays uploaded above hold the same matrix (generate_dense_matrix leaves them in place,
+        // src/saena_matrix_setup.cpp:1638-1646); the flag makes the device reproduce the dense path's float cast of
+        // the whole input vector when the level runs in float precision (src/saena_matrix_dense.cpp:281-282)
+        if (A->use_dense) CK(ds.ctx, saena_b200_set_operator_dense(ds.ctx, l, SAENA_B200_KIND_A, 1), "set operator dense");
         std::vector<saena_b200_block> send, recv;
         int M_old = 0, M_new = 0;
         if (l < L) {

@@ -816,6 +816,19 @@ int saena_b200_set_mapping_deferred(saena_b200_ctx *ctx, int level, int kind, in
     return 0;
 }
 
+int saena_b200_set_operator_dense(saena_b200_ctx *ctx, int level, int kind, int use_dense) {
+    if (!ctx) return 1;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    DevOperator *op = get_op(ctx, level, kind);
+    if (!op) SB_FAIL("set_operator_dense: no such operator");
+    if (kind != SAENA_B200_KIND_A) SB_FAIL("set_operator_dense: only A operators have a dense form (saena_matrix::use_dense)");
+    op->use_dense = use_dense != 0;
+    if (op->use_dense && !op->use_double && !op->x_round)
+        SB_CUDA(cudaMalloc((void **)&op->x_round, sizeof(double) * (size_t)std::max(op->n_local_cols, 1)));
+    sb_invalidate_graphs(ctx);
+    return 0;
+}
+
 int saena_b200_set_coarsest_solver(saena_b200_ctx *ctx, int use_cg) {
     if (!ctx) return 1;
     ctx->coarsest_cg = use_cg != 0;

@@ -104,6 +104,10 @@ struct DevOperator {
     int64_t nnz_local = 0, nnz_remote = 0;
     bool use_double = true;
     bool wide_offsets = false;  // 64-bit row offsets (nnz_local >= 2^31)
+    // saena_matrix::use_dense (saena_b200_set_operator_dense): with use_double false the reference's dense
+    // product casts the whole input vector to float; x_round holds that rounded copy during an application
+    bool use_dense = false;
+    double *x_round = nullptr;  // [n_local_cols], allocated when use_dense && !use_double
 
     // local block: CSR, column ids LOCAL (global - col_offset)
     void *rowptr = nullptr;  // int32[M+1] or int64[M+1]

@@ -37,6 +37,7 @@ void sb_free_operator(DevOperator &op) {
     cudaFree(op.p2p_segs); cudaFree(op.p2p_ticket); cudaFree(op.p2p_signal_consumed);
     // ghost_buf / x_ext belong to the context's halo arena
     cudaFree(op.sell_ptr); cudaFree(op.sell_col); cudaFree(op.sell_val);
+    cudaFree(op.x_round);
     op = DevOperator();
 }
 
@@ -643,8 +644,22 @@ static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, cons
     return 0;
 }
 
+// matvec_dense_float (src/saena_matrix_dense.cpp:281-282): v_send_f = float(v) for the whole vector
+static __global__ void round_through_float_kernel(int n, const double *__restrict__ in, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)(float)in[i];
+}
+
 int sb_apply(saena_b200_ctx *ctx, DevOperator &op, const double *x, int epi, const EpiArgs &args) {
     if (!op.present) SB_FAIL("apply: operator was not uploaded");
+    if (op.use_dense && !op.use_double && op.n_local_cols > 0) {
+        // a level the reference applies through saena_matrix_dense with float precision: the operand of
+        // the product is float(x) everywhere (the epilogue still reads the unrounded iterate, args.u_in)
+        if (!op.x_round) SB_FAIL("apply: dense operator without its rounded-input buffer");
+        ++ctx->launches;
+        round_through_float_kernel<<<(op.n_local_cols + 255) / 256, 256, 0, ctx->stream>>>(op.n_local_cols, x, op.x_round);
+        x = op.x_round;
+    }
     switch (epi) {
         case EPI_PLAIN: return apply_epi<EPI_PLAIN>(ctx, op, x, args);
         case EPI_RESIDUAL: return apply_epi<EPI_RESIDUAL>(ctx, op, x, args);

@@ -65,6 +65,11 @@ class Operator:
     recvProcRank: np.ndarray = field(default_factory=lambda: np.zeros(0, I32))
     recvProcCount: np.ndarray = field(default_factory=lambda: np.zeros(0, I32))
     use_double: bool = True      # False: ghost values travel as float (matvec_sparse_float)
+    # saena_matrix::use_dense (A only; set by the setup when switch_to_dense is on, density > dense_thre and
+    # Mbig <= dense_sz_thre, src/saena_object_setup2.cpp:328-329): the reference applies the operator through
+    # saena_matrix_dense (src/saena_matrix_dense.cpp:181-340).  Same matrix, same product -- except that with
+    # use_double false the dense path casts the WHOLE input vector to float, the rank's own part included (:281).
+    use_dense: bool = False
     nprocs: int = 1
     rank: int = 0
 
@@ -341,6 +346,8 @@ def partition_hierarchy(h: Hierarchy, nprocs: int, agglomerate_below: int = 0,
     for l, lv in enumerate(h.levels):
         ip, ix, dv = operator_to_global_csr(lv.A)
         A_parts = split_operator(KIND_A, l, ip, ix, dv, lv.A.Nbig, splits[l], splits[l], lv.A.use_double)
+        for part in A_parts:
+            part.use_dense = lv.A.use_dense
         P_parts = R_parts = None
         split_old_next = None
         if lv.P is not None:
@@ -382,7 +389,7 @@ _OP_ARRAYS = ("nnzPerRow_local", "col_local", "val_local", "row_remote", "val_re
               "nnzPerProcScan", "vIndex", "vdispls", "rdispls", "sendProcRank", "sendProcCount", "recvProcRank",
               "recvProcCount")
 _OP_SCALARS = ("kind", "level", "M", "Mbig", "Nbig", "row_offset", "col_offset", "n_local_cols", "use_double",
-               "nprocs", "rank")
+               "nprocs", "rank", "use_dense")   # fixtures written before use_dense existed hold 11 values: zip stops there
 
 
 def hierarchy_to_arrays(h: Hierarchy) -> dict:
@@ -421,6 +428,7 @@ def hierarchy_from_arrays(d) -> Hierarchy:
             q = p + name + "."
             sc = dict(zip(_OP_SCALARS, (int(x) for x in d[q + "scalars"])))
             sc["use_double"] = bool(sc["use_double"])
+            sc["use_dense"] = bool(sc.get("use_dense", 0))
             return Operator(**sc, **{a: np.array(d[q + a]) for a in _OP_ARRAYS})
 
         lv = Level(level=l, A=op("A"), inv_diag=np.array(d[p + "inv_diag"]), eig_max=float(eig), active=bool(active),

@@ -66,6 +66,7 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_upload_level_scale.argtypes = [vp, i, dp]
     L.saena_b200_upload_coarsest.argtypes = [vp, i, ctypes.c_int64, c_i32_p, c_i32_p, dp]
     L.saena_b200_set_coarsest_solver.argtypes = [vp, i]
+    L.saena_b200_set_operator_dense.argtypes = [vp, i, i, i]
     L.saena_b200_set_graphs.argtypes = [vp, i]
     L.saena_b200_finalize.argtypes = [vp]
     L.saena_b200_p2p_export.argtypes = [vp, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
@@ -110,7 +111,7 @@ EXPORTED_SYMBOLS = [
     "saena_b200_nccl_unique_id", "saena_b200_init", "saena_b200_init_detached", "saena_b200_time_matvec_compute_only", "saena_b200_destroy", "saena_b200_last_error",
     "saena_b200_upload_operator", "saena_b200_upload_band_operator", "saena_b200_upload_level_aux", "saena_b200_upload_level_scale",
     "saena_b200_upload_coarsest",
-    "saena_b200_set_coarsest_solver", "saena_b200_set_graphs", "saena_b200_finalize",
+    "saena_b200_set_coarsest_solver", "saena_b200_set_operator_dense", "saena_b200_set_graphs", "saena_b200_finalize",
     "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_find_eig", "saena_b200_p2p_enable", "saena_b200_autotune_halo", "saena_b200_halo_choice", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
@@ -208,6 +209,8 @@ class Context:
         """Upload once: what the adaptor does at the end of amg::set_matrix (INTEGRATION.md)."""
         for lv in h.levels:
             self.upload_operator(lv.A)
+            if lv.A.use_dense:   # saena_matrix::use_dense: the reference's dense product (float input when !use_double)
+                self._ck(self._L.saena_b200_set_operator_dense(self._h, lv.level, lv.A.kind, 1))
             if lv.P is not None:
                 self.upload_operator(lv.P)
                 self.upload_operator(lv.R)

@@ -119,7 +119,8 @@ def make_find_eig():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["poisson12_cheb", "poisson9_cheb", "helmholtz2d_p8", "homg33", "band8_1500", "find_eig"]
+    which = sys.argv[1:] or ["poisson12_cheb", "poisson9_cheb", "helmholtz2d_p8", "homg33", "band8_1500", "find_eig",
+                             "poisson12_dense"]
     if "find_eig" in which:
         make_find_eig()
     rng = np.random.default_rng(2024)
@@ -127,6 +128,15 @@ if __name__ == "__main__":
         make("poisson12_cheb", 12, RefOptions())
     if "poisson9_cheb" in which:
         make("poisson9_cheb", 9, RefOptions())
+    if "poisson12_dense" in which:
+        # switch_to_dense on (data/options006_poisson.xml has it off): the coarse levels whose density exceeds
+        # dense_thre = 0.1 are applied through saena_matrix_dense -- with float_level 0 that product casts the whole
+        # input vector to float (src/saena_matrix_dense.cpp:262-340), which the sparse path does not
+        # (dense_thre lowered to 0.05 so that level 1 of this small problem -- 500 rows, density 0.097 -- is
+        # dense too: a dense level that is smoothed inside the V-cycle, not only the coarsest one)
+        os.environ["SREF_SWITCH_TO_DENSE"], os.environ["SREF_DENSE_THRE"] = "1", "0.05"
+        make("poisson12_dense", 12, RefOptions())
+        del os.environ["SREF_SWITCH_TO_DENSE"], os.environ["SREF_DENSE_THRE"]
     if "helmholtz2d_p8" in which:
         # BASELINE.json configs[4]'s shape donor: irregular rows (24..40 non-zeros), general storage
         coo = read_mtx(f"{DATA}/Helmholtz2D_CG_curved_tri/Helmholtz2D_CG_P8_Modes_curved_tri.mtx")

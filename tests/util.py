@@ -20,7 +20,9 @@ GOLDEN = ["poisson9_cheb", "poisson12_cheb"]
 # 50-iteration history is the fixture), and the band pattern of configs[3] (experiments/banded.cpp;
 # per-operator outputs only, 1/(i+j+1) is not a system one solves)
 GOLDEN_EXTRA = ["helmholtz2d_p8", "homg33", "band8_1500"]
-GOLDEN_ALL = GOLDEN + GOLDEN_EXTRA
+# switch_to_dense on: coarse levels applied through saena_matrix_dense (Operator.use_dense), float precision
+GOLDEN_DENSE = ["poisson12_dense"]
+GOLDEN_ALL = GOLDEN + GOLDEN_EXTRA + GOLDEN_DENSE
 
 # tolerances of BASELINE.json's north_star
 TOL_OP = 1e-12       # each SpMV, smoother sweep and transfer: relative error in the 2-norm
