@@ -32,6 +32,7 @@ rank's `Hierarchy` in the reference layout, ready for `saena_b200_upload_operato
 """
 from __future__ import annotations
 
+import os
 import sys
 import time
 from typing import List, Optional, Sequence
@@ -431,6 +432,9 @@ def galerkin_dist(comm: Comm, A: DCsr, cm: ColMap, col_ext: torch.Tensor, P: DCs
     through sparse x dense products, column block by column block; everything else expand / sort / compress)."""
     dev = A.val.device
     nc = P.n_cols
+    # tests shrink both work sizes so that several column blocks / product chunks are exercised on small inputs
+    dense_budget_bytes = float(os.environ.get("SAENA_SETUP_DENSE_BUDGET", dense_budget_bytes))
+    chunk = int(os.environ.get("SAENA_SETUP_CHUNK_PRODUCTS", 300_000_000))
     P_ext = fetch_rows(comm, P, cm)
     A_x = _Csr(A.m, cm.n_ext, A.row, col_ext, A.val)
     if dense is None:
@@ -438,12 +442,16 @@ def galerkin_dist(comm: Comm, A: DCsr, cm: ColMap, col_ext: torch.Tensor, P: DCs
     uc, inv = torch.unique(P.col, return_inverse=True)                 # coarse rows my P rows reach
     Pt = _transpose(_Csr(A.m, max(int(uc.numel()), 1), P.row, inv, P.val))        # compact coarse rows x my fine rows
     if not dense:
-        AP = _spgemm(A_x, P_ext)
-        C = _spgemm(Pt, AP)
+        AP = _spgemm(A_x, P_ext, chunk)
+        C = _spgemm(Pt, AP, chunk)
         del AP
         return _add_partial_rows(comm, nc, coarse_split, uc[C.row] if C.nnz else C.row, C.col, C.val)
     # dense column blocks: AP[:, c0:c1] = A_x P_ext[:, c0:c1]; partial coarse rows P_local^T AP summed over ranks
-    w = int(max(1, min(nc, dense_budget_bytes / 8 / max(cm.n_ext + A.m + nc, 1))))
+    # the block width must be the same on every rank (one all-reduce per block): sized for the largest rank
+    rows_here = torch.tensor([cm.n_ext + A.m], dtype=torch.int64, device=dev)
+    if comm.world > 1:
+        dist.all_reduce(rows_here, op=dist.ReduceOp.MAX)
+    w = int(max(1, min(nc, dense_budget_bytes / 8 / max(int(rows_here.item()) + nc, 1))))
     A_csr = _to_torch_csr(A_x) if A.m else None
     Pt_csr = _to_torch_csr(_transpose(_Csr(A.m, nc, P.row, P.col, P.val))) if A.m else None
     c0r, c1r = int(coarse_split[comm.rank]), int(coarse_split[comm.rank + 1])

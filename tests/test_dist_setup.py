@@ -12,12 +12,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize("world,args,env", [
     (2, ["poisson", "12", "esc", "double"], {}),
     (2, ["poisson", "16", "dense", "double"], {}),          # sparse x dense column blocks on every level
+    # many narrow column blocks (the width is agreed between the ranks) / many small product chunks
+    (3, ["poisson", "12", "dense", "double"], {"SAENA_SETUP_DENSE_BUDGET": "400000"}),
+    (3, ["poisson", "12", "esc", "double"], {"SAENA_SETUP_CHUNK_PRODUCTS": "5000"}),
     (3, ["poisson", "20"], {}),                             # float halo (float_level 0, the drivers' value)
     (3, ["unstructured", "60", "double"], {"DSC_AGG_BELOW": "50"}),
     (4, ["poisson", "14", "double"], {"DSC_AGG_BELOW": "20"}),   # nothing agglomerated but the coarsest level
-], ids=["np2-poisson12-esc", "np2-poisson16-dense", "np3-poisson20-floathalo", "np3-unstructured60", "np4-poisson14"])
+], ids=["np2-poisson12-esc", "np2-poisson16-dense", "np3-narrow-dense-blocks", "np3-small-esc-chunks", "np3-poisson20-floathalo", "np3-unstructured60", "np4-poisson14"])
 def test_distributed_setup_equals_the_one_process_setup(world, args, env):
-    port = 29720 + world + len(args[1])
+    port = 29720 + world + 7 * len(args) + len(env) * 13 + len(args[1])
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                           "--master-addr", "127.0.0.1", "--master-port", str(port),
                           os.path.join(ROOT, "tests", "dist_setup_check.py"), *args],
