@@ -293,6 +293,12 @@ def main():
                     halo_transport += "; per-operator choice fused / separate launches measured at setup"
             else:
                 halo_transport = "nvlink peer memory (pack kernel stores into the neighbour's ghost buffer)"
+    map_tune = None
+    if world == 1 and os.environ.get("SAENA_BENCH_AUTOTUNE_MAP"):
+        # tuning (off by default until measured): per-operator row mapping picked by timing the neighbours of the
+        # heuristic's choice at setup
+        map_tune = [dict(zip(("level", "kind", "before", "after", "ms_before", "ms_after"), (l, "APR"[k], a, b, t0, t1)))
+                    for l, k, a, b, t0, t1 in ctx.autotune_mapping(10)]
     for spec in filter(None, os.environ.get("SAENA_BENCH_MAP", "").split(",")):   # tuning: "level:kind:mapping"
         lvl, kind, mp = (int(x) for x in spec.split(":"))
         ctx.set_mapping(lvl, kind, mp)
@@ -486,6 +492,8 @@ def main():
             "levels": levels_tbl}
     if halo is not None:
         line["halo_overlap"] = halo
+    if map_tune is not None:
+        line["mapping_autotune"] = map_tune
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "poisson3d":
         try:
             line["cpu_baseline"], _, cpu_iters, _ = cpu_reference_solve(5)

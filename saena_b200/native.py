@@ -434,5 +434,38 @@ class Context:
     def get_mapping(self, level, kind) -> int:
         return int(self._L.saena_b200_get_mapping(self._h, level, kind))
 
+    def autotune_mapping(self, reps: int = 10, min_gain: float = 0.03):
+        """One rank only (setup time, untimed): for every uploaded operator, time the row mappings around the one
+        `sb_choose_mapping` picked from nnz/row (half / double / four times the threads per row; the sliced layout
+        only where the heuristic chose it -- building it costs a second copy of the operator) with the library's own
+        per-launch timer and keep the fastest if it wins by more than `min_gain`.  Composes saena_b200_set_mapping and
+        saena_b200_time_matvec; returns [(level, kind, before, after, ms_before, ms_after)].
+        Not collective-safe: with several ranks every timed application is an exchange and the candidate lists
+        would have to agree -- callers gate on nranks == 1."""
+        if self.nranks != 1:
+            raise RuntimeError("autotune_mapping: one rank only")
+        out = []
+        for l, lv in enumerate(self.hier.levels):
+            for kind, op in ((0, lv.A), (1, lv.P), (2, lv.R)):
+                if op is None or op.M == 0:
+                    continue
+                cur = self.get_mapping(l, kind)
+                if cur <= 0 or cur == 100:
+                    continue                       # sliced / streaming: measured choices, left alone
+                flush = self.operator_bytes(l, kind) < 300e6
+                cands = sorted({c for c in (cur // 4, cur // 2, cur * 2, cur * 4) if 1 <= c <= 256 and c != cur})
+                best, t0 = cur, self.time_matvec(l, kind, reps, flush_l2=flush)
+                tb = t0
+                for c in cands:
+                    self.set_mapping(l, kind, c)
+                    t = self.time_matvec(l, kind, reps, flush_l2=flush)
+                    if t < tb:
+                        best, tb = c, t
+                if tb > (1.0 - min_gain) * t0:
+                    best, tb = cur, t0
+                self.set_mapping(l, kind, best)
+                out.append((l, kind, cur, best, t0, tb))
+        return out
+
     def operator_bytes(self, level, kind) -> int:
         return int(self._L.saena_b200_operator_bytes(self._h, level, kind))

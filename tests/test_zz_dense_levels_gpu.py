@@ -55,3 +55,21 @@ def test_without_the_flag_the_same_levels_miss_the_reference():
             assert rel(got, g[f"out.L{l}.A_matvec"]) > 1e-9                      # != the reference's dense product
     finally:
         ctx.close()
+
+
+def test_mapping_autotune_keeps_parity():
+    """the setup-time row-mapping autotuner (native.Context.autotune_mapping: times the neighbours of the heuristic's
+    choice per operator) may change mappings, never results"""
+    from tests.util import GOLDEN_EXTRA
+    g = Golden(GOLDEN_EXTRA[0])     # irregular rows
+    ctx = Context()
+    try:
+        ctx.upload_hierarchy(g.hier)
+        table = ctx.autotune_mapping(reps=3)
+        assert table and all(t1 <= t0 for *_, t0, t1 in table)
+        for l, kind, before, after, *_ in table:
+            assert ctx.get_mapping(l, kind) == after
+        check_ops_against_golden(ctx, g)
+        check_vcycle_against_golden(ctx, g)
+    finally:
+        ctx.close()
