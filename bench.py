@@ -253,6 +253,10 @@ def main():
                                                                  (args.dist_setup == "auto" and n > 320))
     verbose = rank == 0 and bool(os.environ.get("SAENA_BENCH_VERBOSE"))
     agg_sweep = []
+    if args.workload == "poisson3d" and n > 320 and not dist_setup:
+        # 256^3 already takes 17 GB of operators and ~100 GB of setup buffers on one device
+        raise SystemExit(f"bench.py: a {n}^3 hierarchy cannot be built on one device; run on 8 GPUs (torchrun, "
+                         f"--gpus 8) where the setup is row-partitioned (--dist-setup)")
     if dist_setup:
         # every rank generates and coarsens only its own rows; what comes out is already this rank's share
         from saena_b200 import sa_setup_dist as sd

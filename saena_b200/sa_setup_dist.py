@@ -41,7 +41,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .hierarchy import F64, I32, I64, KIND_A, KIND_P, KIND_R, Hierarchy, Level, Operator
+from .hierarchy import F64, I64, KIND_A, KIND_P, KIND_R, Hierarchy, Level, Operator
 from .sa_setup import (ALMOST_ZERO, BIG, JACOBI_OMEGA, SetupOptions, _coalesce, _Csr, _expand_segments, _spgemm,
                        _to_torch_csr, _transpose)
 

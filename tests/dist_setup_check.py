@@ -24,7 +24,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from saena_b200 import sa_setup, sa_setup_dist as sd  # noqa: E402
-from saena_b200.hierarchy import Operator  # noqa: E402
 
 
 def global_coo(ops):
