@@ -114,6 +114,17 @@ int saena_b200_set_operator_dense(saena_b200_ctx *, int level, int kind, int use
     if (kind == 0 && use_dense) g_dense_levels.push_back(level);
     return 0;
 }
+static std::vector<int> g_timed_levels;    // saena_b200_time_matvec calls (saena::amg::profile_matvecs through the adaptor)
+int saena_b200_time_matvec(saena_b200_ctx *, int level, int kind, int reps, int, float *ms_out) {
+    if (kind == 0 && reps == 5) g_timed_levels.push_back(level);
+    *ms_out = 0.25f * (float)(level + 1);
+    return 0;
+}
+extern "C" int rec_timed_levels(int *out, int cap) {
+    int n = 0;
+    for (int l : g_timed_levels) if (n < cap) out[n++] = l;
+    return (int)g_timed_levels.size();
+}
 extern "C" int rec_dense_levels(int *out, int cap) {
     int n = 0;
     for (int l : g_dense_levels) if (n < cap) out[n++] = l;

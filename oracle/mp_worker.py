@@ -69,6 +69,11 @@ def check_adaptor_upload(L, s, rank, size, out):
     buf = (ctypes.c_int * 64)()
     nd = L.rec_dense_levels(buf, 64)
     assert sorted(buf[:nd]) == [l for l, lv in enumerate(h.levels) if lv.A.use_dense and lv.A.M], (list(buf[:nd]),)
+    # saena::amg::profile_matvecs through the public API (experiments/Poisson.cpp:262) = the adaptor's device timings:
+    # one saena_b200_time_matvec of 5 applications per level, on every rank
+    L.sref_profile_matvecs(s._h)
+    nt = L.rec_timed_levels(buf, 64)
+    assert list(buf[:nt]) == list(range(len(h.levels))), list(buf[:nt])
     assert r_coarse_n == h.coarse_n
     if h.coarse_n:
         assert np.array_equal(arr(L.rec_coarsest, (0,), I32), h.coarse_row)

@@ -527,4 +527,12 @@ double sref_time_solve_pcg(void *hv, int reps) {
     return MPI_Wtime() - t0;
 }
 
+// saena::amg::profile_matvecs through the public API (experiments/Poisson.cpp:262): the reference's host loop in
+// the reference builds, the adaptor's device timings in the drop-in builds.  Prints "matvec level l" lines.
+void sref_profile_matvecs(void *hv) {
+    Handle *h = (Handle *)hv;
+    h->solver->profile_matvecs();
+    fflush(stdout);
+}
+
 }  // extern "C"

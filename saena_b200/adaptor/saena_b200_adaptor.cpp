@@ -374,6 +374,24 @@ int saena::amg::solve_smoother(value_t *&u, saena::options *opts) {
     return 0;
 }
 
+void saena::amg::profile_matvecs() {
+    // saena_object::profile_matvecs (src/saena_object.cpp:618-638; called by experiments/Poisson.cpp:262 and
+    // profile_file.cpp:235): 5 timed A_l matvecs per level, the average printed through print_time_all over the
+    // level's communicator.  Here the device's applications of the same operators, each launch timed with CUDA
+    // events on the library's stream (saena_b200_time_matvec), printed through the same function: the driver's
+    // "matvec level l" lines become the GPU's.  Every rank calls for every level (a rank a shrink left out of a
+    // level holds an empty operator there and prints nothing, as in the reference).
+    saena_object *obj = m_pImpl;
+    DeviceSide &ds = device_side(obj);
+    const int iter = 5;
+    for (int l = 0; l <= obj->max_level; ++l) {
+        float ms = 0.f;
+        CK(ds.ctx, saena_b200_time_matvec(ds.ctx, l, SAENA_B200_KIND_A, iter, 0, &ms), "time matvec");
+        if (obj->grids[l].active && obj->grids[l].A && obj->grids[l].A->active)
+            print_time_all(1e-3 * ms, "matvec level " + std::to_string(l), obj->grids[l].A->comm);
+    }
+}
+
 void saena::matrix::matvec(std::vector<value_t> &v, std::vector<value_t> &w) {
     saena_matrix *A = m_pImpl;
     auto it = g_matrices.find(A);

@@ -88,3 +88,7 @@ def test_the_reference_driver_itself_with_the_dropin_linked(ranks, tmp_path):
     it_c = [int(m) for m in re.findall(r"stopped at iteration\s+= (\d+)", out_c[0])]
     rel_g = [float(m) for m in re.findall(r"relative residual\s+= ([0-9.e+-]+)", out_g[0])]
     assert it_g and it_c and abs(it_g[0] - it_c[0]) <= 1 and all(r < 1e-8 for r in rel_g)
+    # the driver's own SpMV report (solver.profile_matvecs(), experiments/Poisson.cpp:262): same lines, the device's times
+    mv_g = [float(m) for m in re.findall(r"matvec level 0\s*\n\s*min: ([0-9.e+-]+)", out_g[0])]
+    mv_c = [float(m) for m in re.findall(r"matvec level 0\s*\n\s*min: ([0-9.e+-]+)", out_c[0])]
+    assert mv_g and mv_c and 0 < mv_g[0] < mv_c[0]
