@@ -66,7 +66,9 @@ int saena_b200_init(saena_b200_ctx **ctx_out, int device_id, int rank, int nrank
     g_dense_levels.clear();
     return 0;
 }
-int saena_b200_destroy(saena_b200_ctx *ctx) { if (g_last == ctx) g_last = nullptr; delete ctx; return 0; }
+static int g_destroys = 0;
+int saena_b200_destroy(saena_b200_ctx *ctx) { if (g_last == ctx) g_last = nullptr; delete ctx; ++g_destroys; return 0; }
+extern "C" int rec_destroys() { return g_destroys; }
 const char *saena_b200_last_error(const saena_b200_ctx *ctx) { return ctx ? ctx->error.c_str() : "recorder"; }
 
 int saena_b200_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {

@@ -119,7 +119,9 @@ def main():
         raise SystemExit(f"unknown workload {what}")
     if os.environ.get("SAENA_MP_ADAPTOR_CHECK"):
         check_adaptor_upload(L, s, rank, size, out)
-        s.close()
+        before = L.rec_destroys()
+        s.close()                      # saena::amg::destroy() through the public API releases the device copy
+        assert L.rec_destroys() == before + 1, "saena::amg::destroy() left the device context behind"
         L.sref_barrier()
         L.sref_finalize()
         return

@@ -46,6 +46,7 @@ struct DeviceSide {
     // grids[0].A; the device copy is then stale and is rebuilt on the next solve
     const saena_matrix *A0 = nullptr;
     int max_level = -1;
+    MPI_Comm comm = MPI_COMM_NULL;   // the communicator the context was created on (grids[0].A->comm)
 };
 
 std::map<const saena_object *, DeviceSide> g_solvers;
@@ -64,6 +65,15 @@ std::vector<double> g_last_history;
 }
 
 #define CK(ctx, call, what) do { if (call) die(ctx, what); } while (0)
+
+// Collective, like every call of the reference's API: on several ranks nobody unmaps its peer-memory arena while a
+// neighbour's last kernel may still be raising flags in it.
+void release(DeviceSide &ds) {
+    if (!ds.ctx) return;
+    if (ds.nprocs > 1 && ds.comm != MPI_COMM_NULL) MPI_Barrier(ds.comm);
+    saena_b200_destroy(ds.ctx);
+    ds.ctx = nullptr;
+}
 
 saena_b200_ctx *new_context(MPI_Comm comm, int &rank, int &nprocs) {
     MPI_Comm_rank(comm, &rank);
@@ -200,7 +210,7 @@ DeviceSide &device_side(saena_object *obj) {
         if (it->second.A0 == obj->grids[0].A && it->second.max_level == obj->max_level) return it->second;
         // the hierarchy changed under the solver object (update1/2/3, set_matrix again): upload it anew
         if (g_verbose && it->second.rank == 0) std::printf("saena_b200: hierarchy changed, uploading again\n");
-        saena_b200_destroy(it->second.ctx);
+        release(it->second);
         g_solvers.erase(it);
     }
     DeviceSide ds;
@@ -208,6 +218,7 @@ DeviceSide &device_side(saena_object *obj) {
     ds.A0 = A0;
     ds.max_level = obj->max_level;
     ds.ctx = new_context(A0->comm, ds.rank, ds.nprocs);
+    ds.comm = A0->comm;
     const int L = obj->max_level;
     const std::vector<double> no_diag(1, 0.0);
     for (int l = 0; l <= L; ++l) {
@@ -374,6 +385,16 @@ int saena::amg::solve_smoother(value_t *&u, saena::options *opts) {
     return 0;
 }
 
+void saena::amg::destroy() {
+    // src/saena.cpp:882-884 forwards to saena_object::destroy; the device copy of the hierarchy goes first
+    auto it = g_solvers.find(m_pImpl);
+    if (it != g_solvers.end()) {
+        release(it->second);
+        g_solvers.erase(it);
+    }
+    m_pImpl->destroy();
+}
+
 void saena::amg::profile_matvecs() {
     // saena_object::profile_matvecs (src/saena_object.cpp:618-638; called by experiments/Poisson.cpp:262 and
     // profile_file.cpp:235): 5 timed A_l matvecs per level, the average printed through print_time_all over the
@@ -398,6 +419,7 @@ void saena::matrix::matvec(std::vector<value_t> &v, std::vector<value_t> &w) {
     if (it == g_matrices.end()) {
         DeviceSide ds;
         ds.ctx = new_context(A->comm, ds.rank, ds.nprocs);
+        ds.comm = A->comm;
         upload_A(ds.ctx, A, 0, level_comm(A, ds.rank, ds.nprocs), ds.nprocs);
         CK(ds.ctx, saena_b200_upload_level_aux(ds.ctx, 0, A->inv_diag, A->eig_max_of_invdiagXA, 0, 0, 0, nullptr, 0,
                                                nullptr), "upload level aux");
@@ -417,18 +439,19 @@ extern "C" {
 
 void saena_b200_adaptor_set_verbose(int v) { g_verbose = v; }
 
-// Free the device side of one solver (call before saena::amg::destroy()), or of everything (NULL).
+// Free the device side of one solver (saena::amg::destroy() does it too), or of everything (NULL) -- the
+// stand-alone saena::matrix::matvec contexts included, which no reference call releases.  Collective.
 void saena_b200_adaptor_release(saena::amg *solver) {
     if (solver) {
         auto it = g_solvers.find(solver->get_object());
         if (it != g_solvers.end()) {
-            saena_b200_destroy(it->second.ctx);
+            release(it->second);
             g_solvers.erase(it);
         }
         return;
     }
-    for (auto &kv : g_solvers) saena_b200_destroy(kv.second.ctx);
-    for (auto &kv : g_matrices) saena_b200_destroy(kv.second.ctx);
+    for (auto &kv : g_solvers) release(kv.second);
+    for (auto &kv : g_matrices) release(kv.second);
     g_solvers.clear();
     g_matrices.clear();
 }
