@@ -31,8 +31,47 @@ def band_rows(n, b, v, rows):
     return out
 
 
+def cpu_baseline(n: int, b: int, reps: int = 3):
+    """The CPU side of the same point (the reference's CPU path timed beside it).  The reference's
+    own assembler cannot build this matrix at size (std::set inserts, and saena::band_matrix's fill is compiled out,
+    src/aux_functions2.cpp:1344-1371), so the C restatement of saena_matrix::matvec (oracle/saena_oracle.c:so_matvec,
+    pinned against the reference on the band pattern by golden band8_1500) runs on the arrays written out directly:
+    kind "port", one core -- the loop of src/saena_matrix_matvec.cpp:55-80 is single-threaded in the reference too.
+    The fused smoother sweep has no CPU counterpart: the reference's chebyshev is the SpMV + two vector passes."""
+    from oracle.oracle import Oracle
+    from saena_b200.hierarchy import Hierarchy, Level, Operator
+    i = np.arange(n, dtype=np.int64)
+    lo, hi = np.maximum(i - b, 0), np.minimum(i + b, n - 1)
+    counts = (hi - lo + 1).astype(np.int32)
+    rows = np.repeat(i, counts)
+    first = np.cumsum(counts) - counts
+    cols = (np.arange(len(rows), dtype=np.int64) - np.repeat(first, counts)) + np.repeat(lo, counts)
+    vals = 1.0 / (rows + cols + 1.0)
+    op = Operator(kind=KIND_A, level=0, M=n, Mbig=n, Nbig=n, row_offset=0, col_offset=0, n_local_cols=n,
+                  nnzPerRow_local=counts, col_local=cols.astype(np.int32), val_local=vals)
+    h = Hierarchy([Level(0, op, inv_diag=2.0 * i + 1.0, eig_max=2.0)], coarse_n=0)
+    o = Oracle(h)
+    v = np.random.default_rng(12345).uniform(-1, 1, n)
+    w = o.matvec(0, KIND_A, v)
+    sample = np.unique(np.concatenate((np.arange(min(n, 20)), np.arange(max(n - 20, 0), n))))
+    assert np.allclose(w[sample], band_rows(n, b, v, sample), rtol=1e-12)
+    t = time.perf_counter()
+    for _ in range(reps):
+        o.matvec(0, KIND_A, v)
+    sec = (time.perf_counter() - t) / reps
+    nnz = int(counts.sum())
+    mv_bytes = 12 * nnz + 20 * n
+    print(json.dumps({"cpu_baseline": {"value": round(mv_bytes / sec / 1e9, 2), "unit": "GB/s", "cores": 1, "kind": "port",
+                                       "sample": f"oracle so_matvec (C restatement of saena_matrix::matvec) on the band "
+                                                 f"pattern, {n} rows, half bandwidth {b}, {nnz} non-zeros; {reps} "
+                                                 f"applications, {sec * 1e3:.1f} ms each"},
+                      "n": n, "half_bandwidth": b, "nnz": nnz, "spmv_ms": round(sec * 1e3, 2)}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--cpu-only", action="store_true", help="only the CPU baseline points (no GPU needed)")
+    ap.add_argument("--cpu-sizes", default="1000000", help="rows of the CPU baseline points (half bandwidth 64 and 1)")
     ap.add_argument("--sizes", default="1000000,10000000,50000000")
     ap.add_argument("--bands", default="0,1,2,4,8,16,32,64")
     ap.add_argument("--peak", type=float, default=None)
@@ -41,6 +80,11 @@ def main():
     if peak is None:
         p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
         peak = float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+    for n in (int(x) for x in filter(None, a.cpu_sizes.split(","))):
+        for b in (64, 1):
+            cpu_baseline(n, b)
+    if a.cpu_only:
+        return
     ctx = Context()
     rng = np.random.default_rng(12345)
     for n in (int(x) for x in a.sizes.split(",")):
