@@ -1,0 +1,75 @@
+"""Size-independent properties of the solve path, checked at any size through any implementation that exposes
+matvec / smooth / vcycle / solve_pcg (the CUDA Context at BASELINE.json's full 256^3, the C oracle at sizes it
+finishes in seconds).  No reference output is needed: each property follows from what the path computes.
+
+  row sums      A_0 * 1 against the 7-point stencil written out: (6 - #neighbours) / h^2, every row
+  symmetry      <A_l x, y> = <x, A_l y> on every level (Galerkin operators of a symmetric A_0 with R = P^T)
+  adjointness   <R_l r, e> = <r, P_l e> on every level (restrict_matrix::transposeP: R is P^T entry for entry)
+  linearity     the Chebyshev sweeps are linear in (u, rhs) jointly; the V-cycle from a zero iterate is linear in rhs
+  SPD V-cycle   <V x, y> = <x, V y>: equal pre- and post-sweeps of a polynomial smoother, R = P^T, exact coarsest solve --
+                what makes the V-cycle admissible as a CG preconditioner
+  PCG           reaches the tolerance, and the residual recomputed from the returned u, b - A u, agrees with the
+                recurrence's last <r,r> (the timed answer is an answer)
+"""
+import numpy as np
+
+from saena_b200.hierarchy import KIND_A, KIND_P, KIND_R
+
+
+def _dot(a, b):
+    return float(np.dot(a, b))
+
+
+def check(impl, hier, n, rhs, tol=1e-12, seed=7):
+    rng = np.random.default_rng(seed)
+    out = {}
+    # ---- row sums of the fine operator, all rows
+    idx = np.arange(n ** 3, dtype=np.int64)
+    i, j, k = idx % n, (idx // n) % n, idx // (n * n)
+    nb = ((i > 0).astype(np.int64) + (i < n - 1) + (j > 0) + (j < n - 1) + (k > 0) + (k < n - 1))
+    want = (6 - nb) * float((n + 1) ** 2)
+    got = impl.matvec(0, KIND_A, np.ones(n ** 3))
+    out["row_sums"] = float(np.max(np.abs(got - want)) / (6.0 * (n + 1) ** 2))
+    assert out["row_sums"] <= 1e-14, out
+    del idx, i, j, k, nb, want, got
+    # ---- per level: symmetry, adjointness, linearity of the smoother
+    for l, lv in enumerate(hier.levels):
+        M = lv.A.M
+        x, y = rng.uniform(-1, 1, M), rng.uniform(-1, 1, M)
+        ax, ay = impl.matvec(l, KIND_A, x), impl.matvec(l, KIND_A, y)
+        s = abs(_dot(ax, y) - _dot(x, ay)) / (np.linalg.norm(ax) * np.linalg.norm(y))
+        out[f"L{l}.symmetry"] = s
+        assert s <= tol, (l, "symmetry", s)
+        if lv.P is not None:
+            e = rng.uniform(-1, 1, lv.P.n_local_cols)
+            rr, pe = impl.matvec(l, KIND_R, x), impl.matvec(l, KIND_P, e)
+            a = abs(_dot(rr, e) - _dot(x, pe)) / (np.linalg.norm(rr) * np.linalg.norm(e))
+            out[f"L{l}.adjoint"] = a
+            assert a <= tol, (l, "adjointness", a)
+        if l < len(hier.levels) - 1:
+            b1, b2 = rng.uniform(-1, 1, M), rng.uniform(-1, 1, M)
+            s12 = impl.smooth(l, "chebyshev", 3, x + y, b1 + b2)
+            s1, s2 = impl.smooth(l, "chebyshev", 3, x, b1), impl.smooth(l, "chebyshev", 3, y, b2)
+            lin = float(np.linalg.norm(s12 - (s1 + s2)) / np.linalg.norm(s12))
+            out[f"L{l}.smoother_linear"] = lin
+            assert lin <= tol, (l, "smoother linearity", lin)
+    # ---- V-cycle from a zero iterate: linear and symmetric
+    M0 = hier.levels[0].A.M
+    x, y = rng.uniform(-1, 1, M0), rng.uniform(-1, 1, M0)
+    z = np.zeros(M0)
+    vx, vy, vxy = impl.vcycle(0, z, x), impl.vcycle(0, z, y), impl.vcycle(0, z, 2.0 * x - 3.0 * y)
+    out["vcycle_linear"] = float(np.linalg.norm(vxy - (2.0 * vx - 3.0 * vy)) / np.linalg.norm(vxy))
+    out["vcycle_symmetric"] = abs(_dot(vx, y) - _dot(x, vy)) / (np.linalg.norm(vx) * np.linalg.norm(y))
+    assert out["vcycle_linear"] <= 1e-10 and out["vcycle_symmetric"] <= 1e-10, out
+    assert _dot(vx, x) > 0 and _dot(vy, y) > 0          # positive definite on the samples
+    # ---- the solve
+    u, iters, hist = impl.solve_pcg(rhs)
+    hist = np.asarray(hist)
+    out["iterations"], out["rel_residual"] = int(iters), float(hist[-1] / hist[0])
+    assert out["rel_residual"] < 1e-8 and iters <= 15, out
+    r = rhs - impl.matvec(0, KIND_A, u)
+    true_rel = float(np.linalg.norm(r) / np.linalg.norm(rhs))
+    out["true_rel_residual"] = true_rel
+    assert true_rel < 1e-8 and abs(true_rel - out["rel_residual"]) <= 1e-3 * out["rel_residual"], out
+    assert np.all(np.diff(hist) < 0)                     # this problem's history decreases monotonically
+    return out

@@ -1,0 +1,36 @@
+"""BASELINE.json configs[1] at its full size (3D 7-point Poisson, 256^3 = 16 777 216 unknowns, the bench's
+hierarchy) through the CUDA path: the oracle cannot run there, so parity is checked through properties that
+hold at any size (tests/full_size_properties.py): stencil row sums on every row, symmetry of every level's
+operator, R = P^T adjointness, linearity of the fused smoother sweeps and of the V-cycle, symmetry and
+positivity of the V-cycle as a preconditioner, and the PCG answer against the residual recomputed from u.
+The same checker runs through the oracle at small sizes (tests/test_full_size_properties.py).
+(Sorted last: ~2 min of GPU time, most of it the untimed setup; first GPU run at round end.)"""
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.timeout(1500)
+def test_full_size_256_cubed_properties():
+    import torch
+
+    from saena_b200 import sa_setup
+    from saena_b200.native import Context
+    from tests.full_size_properties import check
+
+    n = int(os.environ.get("SAENA_TEST_FULL_N", 256))
+    dh = sa_setup.build_device_hierarchy(*sa_setup.poisson3d_coo(n), device="cuda")
+    hier = dh.to_rank(0, 1)
+    del dh
+    torch.cuda.empty_cache()
+    ctx = Context()
+    try:
+        ctx.upload_hierarchy(hier)
+        out = check(ctx, hier, n, sa_setup.poisson3d_rhs(n))
+        if n == 256:
+            assert out["iterations"] == 9        # the bench's count (profiles/r01_bench_levels.md)
+        assert ctx.launch_count() > 0
+    finally:
+        ctx.close()
