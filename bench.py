@@ -194,6 +194,37 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def verify_properties(ctx, hier, rank, world):
+    """SAENA_BENCH_VERIFY=1 (untimed, collective): size-independent properties of the uploaded, row-partitioned
+    hierarchy -- what stands in for the oracle at sizes it cannot run (tests/full_size_properties.py is the one-rank
+    version): <A x, y> = <x, A y> and <R x, e> = <x, P e> on every level, dots summed over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from saena_b200.hierarchy import KIND_A, KIND_P, KIND_R
+
+    def gsum(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+        if world > 1:
+            dist.all_reduce(t)
+        return t.tolist()
+
+    out = {}
+    for l, lv in enumerate(hier.levels):
+        rng = np.random.default_rng(1000 * l + rank)
+        x, y = rng.uniform(-1, 1, lv.A.M), rng.uniform(-1, 1, lv.A.M)
+        ax, ay = ctx.matvec(l, KIND_A, x), ctx.matvec(l, KIND_A, y)
+        axy, xay, nax, ny = gsum(float(ax @ y), float(x @ ay), float(ax @ ax), float(y @ y))
+        out[f"L{l}.symmetry"] = abs(axy - xay) / max(np.sqrt(nax * ny), 1e-300)
+        if lv.P is not None:
+            e = rng.uniform(-1, 1, lv.P.n_local_cols)
+            rx, pe = ctx.matvec(l, KIND_R, x), ctx.matvec(l, KIND_P, e)
+            rxe, xpe, nrx, ne = gsum(float(rx @ e), float(x @ pe), float(rx @ rx), float(e @ e))
+            out[f"L{l}.adjoint"] = abs(rxe - xpe) / max(np.sqrt(nrx * ne), 1e-300)
+    out["worst"] = max(out.values())
+    out["ok"] = bool(out["worst"] <= 1e-6 if any(not lv.A.use_double for lv in hier.levels) and world > 1 else out["worst"] <= 1e-12)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -510,6 +541,11 @@ def main():
         line["halo_overlap"] = halo
     if map_tune is not None:
         line["mapping_autotune"] = map_tune
+    if os.environ.get("SAENA_BENCH_VERIFY"):
+        try:
+            line["verify"] = verify_properties(ctx, hier, rank, world)
+        except Exception as e:
+            line["verify"] = {"ok": False, "error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "poisson3d":
         try:
             line["cpu_baseline"], _, cpu_iters, _ = cpu_reference_solve(5)

@@ -40,3 +40,15 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_verify_properties_through_the_oracle():
+    """bench.py's SAENA_BENCH_VERIFY check (symmetry / R = P^T adjointness on every level) is implementation-agnostic:
+    here through the C oracle on one rank"""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle.oracle import Oracle
+    from tests.util import GOLDEN, Golden
+    g = Golden(GOLDEN[1])
+    out = bench.verify_properties(Oracle(g.hier), g.hier, 0, 1)
+    assert out["ok"] and out["worst"] <= 1e-14, out
