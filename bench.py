@@ -280,8 +280,8 @@ def main():
     # ---- setup (untimed): hierarchy of the reference's shape, built on this rank's GPU
     n = args.n
     t0 = time.perf_counter()
-    dist_setup = world > 1 and args.workload == "poisson3d" and (args.dist_setup == "on" or
-                                                                 (args.dist_setup == "auto" and n > 320))
+    dist_setup = world > 1 and (args.dist_setup == "on" or
+                                (args.dist_setup == "auto" and args.workload == "poisson3d" and n > 320))
     verbose = rank == 0 and bool(os.environ.get("SAENA_BENCH_VERBOSE"))
     agg_sweep = []
     if args.workload == "poisson3d" and n > 320 and not dist_setup:
@@ -292,9 +292,19 @@ def main():
         # every rank generates and coarsens only its own rows; what comes out is already this rank's share
         from saena_b200 import sa_setup_dist as sd
         comm = sd.Comm(torch.device("cuda", local))
-        N = n ** 3
-        hier, summary = sd.build_distributed_hierarchy(sd.poisson3d_dcsr(n, comm), agglomerate_below=args.agglomerate_below,
+        if args.workload == "poisson3d":
+            N = n ** 3
+            A0 = sd.poisson3d_dcsr(n, comm)
+        else:
+            # every rank generates the whole synthetic matrix on the host (numpy, seeded) and keeps its rows
+            lengths = tuple(int(x) for x in args.row_lengths.split(","))
+            weights = (16, 48, 20) if len(lengths) == 3 else (1,) * len(lengths)
+            N, row, col, val = unstructured2d_coo(args.g, row_lengths=lengths, weights=weights)
+            A0 = sd.coo_dcsr(N, row, col, val, comm)
+            del row, col, val
+        hier, summary = sd.build_distributed_hierarchy(A0, agglomerate_below=args.agglomerate_below,
                                                        rebalance_above=args.rebalance_above, verbose=verbose, comm=comm)
+        del A0
         if rank == 0:
             log(f"[setup] hierarchy built on {world} ranks in {time.perf_counter() - t0:.1f}s\n" + "\n".join(summary))
     else:
@@ -340,7 +350,7 @@ def main():
     if rank == 0:
         log(f"[setup] uploaded in {time.perf_counter() - t0:.1f}s total")
     l0 = hier.levels[0].A
-    if dist_setup:
+    if dist_setup and args.workload == "poisson3d":
         rhs_host = torch.from_numpy(sd.poisson3d_rhs_rows(n, l0.row_offset, l0.row_offset + l0.M)).pin_memory()
     else:
         rhs_full = poisson3d_rhs(n) if args.workload == "poisson3d" else unstructured2d_rhs(N)
