@@ -338,12 +338,6 @@ def main():
                     halo_transport += "; per-operator choice fused / separate launches measured at setup"
             else:
                 halo_transport = "nvlink peer memory (pack kernel stores into the neighbour's ghost buffer)"
-    map_tune = None
-    if world == 1 and os.environ.get("SAENA_BENCH_AUTOTUNE_MAP"):
-        # tuning (off by default until measured): per-operator row mapping picked by timing the neighbours of the
-        # heuristic's choice at setup
-        map_tune = [dict(zip(("level", "kind", "before", "after", "ms_before", "ms_after"), (l, "APR"[k], a, b, t0, t1)))
-                    for l, k, a, b, t0, t1 in ctx.autotune_mapping(10)]
     for spec in filter(None, os.environ.get("SAENA_BENCH_MAP", "").split(",")):   # tuning: "level:kind:mapping"
         lvl, kind, mp = (int(x) for x in spec.split(":"))
         ctx.set_mapping(lvl, kind, mp)
@@ -391,6 +385,26 @@ def main():
     ms_step = max_over_ranks(ms_total / args.steps)
     clk = clocks.summary()
     graph_info = {"vcycles_replayed_from_graph": ctx.graph_replays()}
+    map_tune = None
+    if world == 1 and os.environ.get("SAENA_BENCH_AUTOTUNE_MAP"):
+        # in-run A/B (not the bench value, off by default until measured): per-operator row mapping picked by timing the
+        # neighbours of the heuristic's choice, then the same solves again.  SAENA_BENCH_AUTOTUNE_MAP=keep leaves the tuned
+        # mappings in place for the per-level tables below; anything else restores the heuristic's.
+        table = ctx.autotune_mapping(10)
+        for _ in range(2):
+            ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+        barrier()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+        tuned_ms = ctx.timer_stop() / args.steps
+        barrier()
+        map_tune = {"ms_per_step_heuristic": ms_step, "ms_per_step_autotuned": tuned_ms,
+                    "changed": [dict(zip(("level", "kind", "before", "after", "ms_before", "ms_after"), (l, "APR"[k], a, b, t0, t1)))
+                                for l, k, a, b, t0, t1 in table if a != b]}
+        if os.environ["SAENA_BENCH_AUTOTUNE_MAP"] != "keep":
+            for l, k, a, b, _, _ in table:
+                ctx.set_mapping(l, k, a)
     if world > 1 and ctx.graph_replays() > 0 and not os.environ.get("SAENA_BENCH_NO_AB"):
         # A/B on the same uploaded hierarchy: the same solves with eager launches (not the bench value)
         ctx.set_graphs(False)
