@@ -47,6 +47,13 @@ struct DeviceSide {
     const saena_matrix *A0 = nullptr;
     int max_level = -1;
     MPI_Comm comm = MPI_COMM_NULL;   // the communicator the context was created on (grids[0].A->comm)
+    // The side tables are keyed by object addresses, and an address can be handed out again after a destroy():
+    // what the upload was made from is remembered too (array address, sizes) and compared before every use.
+    const void *vals = nullptr;
+    long nnz = -1;
+    int M = -1;
+    void remember(const saena_matrix *A) { vals = A->val_local; nnz = (long)A->nnz_l; M = (int)A->M; }
+    bool made_from(const saena_matrix *A) const { return vals == A->val_local && nnz == (long)A->nnz_l && M == (int)A->M; }
 };
 
 std::map<const saena_object *, DeviceSide> g_solvers;
@@ -207,7 +214,9 @@ void upload_PR(saena_b200_ctx *ctx, Op &op, int kind, int level, int n_rows, int
 DeviceSide &device_side(saena_object *obj) {
     auto it = g_solvers.find(obj);
     if (it != g_solvers.end()) {
-        if (it->second.A0 == obj->grids[0].A && it->second.max_level == obj->max_level) return it->second;
+        if (it->second.A0 == obj->grids[0].A && it->second.max_level == obj->max_level &&
+            it->second.made_from(obj->grids[0].A))
+            return it->second;
         // the hierarchy changed under the solver object (update1/2/3, set_matrix again): upload it anew
         if (g_verbose && it->second.rank == 0) std::printf("saena_b200: hierarchy changed, uploading again\n");
         release(it->second);
@@ -219,6 +228,7 @@ DeviceSide &device_side(saena_object *obj) {
     ds.max_level = obj->max_level;
     ds.ctx = new_context(A0->comm, ds.rank, ds.nprocs);
     ds.comm = A0->comm;
+    ds.remember(A0);
     const int L = obj->max_level;
     const std::vector<double> no_diag(1, 0.0);
     for (int l = 0; l <= L; ++l) {
@@ -395,6 +405,16 @@ void saena::amg::destroy() {
     m_pImpl->destroy();
 }
 
+void saena::matrix::destroy() {
+    // src/saena.cpp:246-248 forwards to saena_matrix::destroy; a device copy made for stand-alone matvec goes first
+    auto it = g_matrices.find(m_pImpl);
+    if (it != g_matrices.end()) {
+        release(it->second);
+        g_matrices.erase(it);
+    }
+    m_pImpl->destroy();
+}
+
 void saena::amg::profile_matvecs() {
     // saena_object::profile_matvecs (src/saena_object.cpp:618-638; called by experiments/Poisson.cpp:262 and
     // profile_file.cpp:235): 5 timed A_l matvecs per level, the average printed through print_time_all over the
@@ -416,10 +436,16 @@ void saena::amg::profile_matvecs() {
 void saena::matrix::matvec(std::vector<value_t> &v, std::vector<value_t> &w) {
     saena_matrix *A = m_pImpl;
     auto it = g_matrices.find(A);
+    if (it != g_matrices.end() && !it->second.made_from(A)) {   // another matrix behind the same address
+        release(it->second);
+        g_matrices.erase(it);
+        it = g_matrices.end();
+    }
     if (it == g_matrices.end()) {
         DeviceSide ds;
         ds.ctx = new_context(A->comm, ds.rank, ds.nprocs);
         ds.comm = A->comm;
+        ds.remember(A);
         upload_A(ds.ctx, A, 0, level_comm(A, ds.rank, ds.nprocs), ds.nprocs);
         CK(ds.ctx, saena_b200_upload_level_aux(ds.ctx, 0, A->inv_diag, A->eig_max_of_invdiagXA, 0, 0, 0, nullptr, 0,
                                                nullptr), "upload level aux");
