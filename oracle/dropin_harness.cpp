@@ -1,5 +1,5 @@
 /*
- * dropin_harness.cpp -- TEST INFRASTRUCTURE for the drop-in (tests/test_dropin.py).
+ * dropin_harness.cpp -- TEST INFRASTRUCTURE for the drop-in (tests/test_public_api_dropin.py).
  *
  * Linked into oracle/_ref/libsaena_dropin.so together with the UNMODIFIED reference objects
  * (src/saena.cpp's five solve-path forwarders weakened by objcopy) and

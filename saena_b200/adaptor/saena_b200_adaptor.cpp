@@ -18,7 +18,7 @@
 // (side table keyed by the saena_object*, because the header's class layout must not change) and
 // released by saena_b200_adaptor_release() / at exit.  The reference's own CPU path stays
 // callable in the same process as `solver.get_object()->solve_pCG(u)` -- that is how
-// tests/test_dropin.py checks parity on the very same hierarchy object.
+// tests/test_public_api_dropin.py checks parity on the very same hierarchy object.
 //
 // Error convention: the reference prints and terminates; a non-zero status from
 // the C ABI is mapped to exactly that.
