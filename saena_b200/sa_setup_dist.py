@@ -690,9 +690,10 @@ def poisson3d_rhs_rows(n: int, r0: int, r1: int) -> np.ndarray:
     return 12 * math.pi ** 2 * s[i] * s[j] * s[k]
 
 
-def coo_dcsr(n: int, row, col, val, comm: Comm) -> DCsr:
-    """a global COO (every rank holds all of it: small test inputs) -> my rows of an equal-row-block partition"""
-    split = np.array([n * r // comm.world for r in range(comm.world + 1)], I64)
+def coo_dcsr(n: int, row, col, val, comm: Comm, split: Optional[np.ndarray] = None) -> DCsr:
+    """a global COO (every rank holds all of it: small test inputs) -> my rows of a row partition (equal blocks
+    unless `split` is given)"""
+    split = np.array([n * r // comm.world for r in range(comm.world + 1)], I64) if split is None else np.asarray(split, I64)
     r0, r1 = int(split[comm.rank]), int(split[comm.rank + 1])
     row, col, val = (np.asarray(row, I64), np.asarray(col, I64), np.asarray(val, F64))
     keep = (row >= r0) & (row < r1)

@@ -79,6 +79,13 @@ def main():
         n, row, col, val = sa_setup.unstructured2d_coo(size)
         A0 = sd.coo_dcsr(n, row, col, val, comm)
         rhs = sa_setup.unstructured2d_rhs(n)
+    if "skew" in sys.argv[3:]:
+        # a lopsided input partition (rank 0 holds 70 % of the rows, one rank none): the setup first moves the
+        # matrix to the nnz-balanced partition
+        cuts = [0, int(0.7 * n)] + [int(0.7 * n) + (n - int(0.7 * n)) * r // max(world - 2, 1) for r in range(1, world - 1)] + [n]
+        cuts = sorted(cuts + [n] * (world + 1 - len(cuts)))[:world + 1]
+        cuts[-1] = n
+        A0 = sd.coo_dcsr(n, row, col, val, comm, split=np.array(cuts))
     h, summary = sd.build_distributed_hierarchy(A0, opts, agglomerate_below=agg_below, rebalance_above=1.10, dense=dense)
     shares = [None] * world
     dist.gather_object(h, shares if rank == 0 else None, dst=0)

@@ -18,7 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     (3, ["poisson", "20"], {}),                             # float halo (float_level 0, the drivers' value)
     (3, ["unstructured", "60", "double"], {"DSC_AGG_BELOW": "50"}),
     (4, ["poisson", "14", "double"], {"DSC_AGG_BELOW": "20"}),   # nothing agglomerated but the coarsest level
-], ids=["np2-poisson12-esc", "np2-poisson16-dense", "np3-narrow-dense-blocks", "np3-small-esc-chunks", "np3-poisson20-floathalo", "np3-unstructured60", "np4-poisson14"])
+    (3, ["poisson", "10", "double", "skew"], {}),                # lopsided input partition, one rank starts empty
+], ids=["np2-poisson12-esc", "np2-poisson16-dense", "np3-narrow-dense-blocks", "np3-small-esc-chunks", "np3-poisson20-floathalo", "np3-unstructured60", "np4-poisson14", "np3-skewed-input"])
 def test_distributed_setup_equals_the_one_process_setup(world, args, env):
     port = 29720 + world + 7 * len(args) + len(env) * 13 + len(args[1])
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
