@@ -133,7 +133,6 @@ class Fetcher:
         self.serve_counts = comm.all_to_all_counts(self.req_counts)
         asked = comm.all_to_all(ids, self.req_counts, self.serve_counts)
         self.serve_idx = asked - int(split[comm.rank])          # local ids, grouped by the asking rank
-        self.n = int(ids.numel())
 
     def fetch(self, x_local: torch.Tensor) -> torch.Tensor:
         return self.comm.all_to_all(x_local[self.serve_idx], self.serve_counts, self.req_counts)
@@ -240,7 +239,7 @@ def fetch_rows(comm: Comm, P: DCsr, cm: ColMap) -> _Csr:
     ptr = torch.zeros(P.m + 1, dtype=torch.int64, device=dev)
     ptr[1:] = torch.cumsum(counts, 0)
     g_counts = f.fetch(counts)                                           # entries of each ghost row
-    e, seg = _expand_segments(ptr, f.serve_idx)
+    e, _ = _expand_segments(ptr, f.serve_idx)
     # entries per asking rank
     served_rows_cum = np.concatenate(([0], np.cumsum(f.serve_counts)))
     cnt_served = counts[f.serve_idx]
@@ -372,8 +371,7 @@ def aggregate_dist(comm: Comm, cm: ColMap, s_row: torch.Tensor, s_col: torch.Ten
     return cm.extend(agg_c_own), int(coarse_split[-1]), coarse_split, rounds
 
 
-def prolongator_dist(A: DCsr, col_ext: torch.Tensor, agg_c_ext: torch.Tensor, nc: int, coarse_split: np.ndarray,
-                     inv_diag: torch.Tensor) -> DCsr:
+def prolongator_dist(A: DCsr, col_ext: torch.Tensor, agg_c_ext: torch.Tensor, nc: int, inv_diag: torch.Tensor) -> DCsr:
     """sa_setup.prolongator on my rows"""
     v = -JACOBI_OMEGA * inv_diag[A.row] * A.val
     v = torch.where((A.row + A.r0) == A.col, v + 1.0, v)
@@ -386,7 +384,6 @@ def transpose_dist(comm: Comm, P: DCsr, coarse_split: np.ndarray) -> DCsr:
     """R = P^T, its rows (coarse) partitioned by coarse_split"""
     grow, gcol, val = _route_rows(comm, coarse_split, P.col, P.row + P.r0, P.val)
     c0 = int(coarse_split[comm.rank])
-    mc = int(coarse_split[comm.rank + 1]) - c0
     key = (grow - c0) * P.n_rows + gcol
     key, order = torch.sort(key)
     return DCsr(P.n_cols, P.n_rows, coarse_split, comm.rank, key // P.n_rows, key % P.n_rows, val[order])
@@ -608,7 +605,7 @@ def build_distributed_hierarchy(A0: DCsr, opts: Optional[SetupOptions] = None, a
                               np.float32(nc) / np.float32(A.n_rows) > np.float32(opts.row_reduction_up_thrshld))
         else:
             last_level = (l + 1 == opts.max_level)
-        P = prolongator_dist(A, col_ext, agg_c_ext, nc, so, inv_diag)
+        P = prolongator_dist(A, col_ext, agg_c_ext, nc, inv_diag)
         del agg_c_ext
         Ac = galerkin_dist(comm, A, cm, col_ext, P, so, dense=dense)
         del cm, col_ext
