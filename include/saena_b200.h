@@ -244,7 +244,9 @@ int64_t saena_b200_launch_count(const saena_b200_ctx *ctx);
 /* Force one operator's SpMV row mapping (tuning / profiling / tests): 0 = heuristic from nnz/row;
  * 1..16 = that many lanes per row, 32 rows per warp; 32..256 = that many threads per row, one row
  * per thread group; -1..-32 = streaming row blocks with that many lanes per row in the reduce
- * phase; 100 = sliced layout (32-row slices, column-major, one lane per row). */
+ * phase; 100 = sliced layout (32-row slices, column-major, one lane per row); 101 = the sliced
+ * layout over rows sorted by length inside 256-row windows (irregular rows: the slices' padding all
+ * but disappears; operators without a halo only, otherwise the heuristic's choice is kept). */
 int saena_b200_set_mapping(saena_b200_ctx *ctx, int level, int kind, int mapping);
 /* The same, taking effect at the next saena_b200_finalize (no layout is built for the mapping that
  * is being replaced: matters for an operator that fills half the HBM). */

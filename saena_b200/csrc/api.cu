@@ -850,6 +850,7 @@ int saena_b200_get_mapping(const saena_b200_ctx *ctx, int level, int kind) {
     const DevLevel &lv = ctx->levels[level];
     const DevOperator &op = kind == SAENA_B200_KIND_A ? lv.A : (kind == SAENA_B200_KIND_P ? lv.P : lv.R);
     if (!op.present) return 0;
+    if (op.use_sellp) return SB_MAPPING_SELLP;
     return op.use_sell ? SB_MAPPING_SELL : (op.use_stream ? -op.lanes : op.lanes);
 }
 

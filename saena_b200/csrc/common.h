@@ -126,6 +126,17 @@ struct DevOperator {
     int64_t sell_padded_est = 0;    // what the padding would be (computed at upload)
     bool sell_only = false;         // the CSR col/val were released once the sliced copy existed (no other mapping)
 
+    // sliced layout over a row permutation (mapping 101): inside every window of 256 consecutive rows (one CTA) the
+    // rows are sorted by length, longest first, so that the 32 rows of a slice have nearly the same length and the
+    // padding of irregular operators (unstructured matrices, smoothed prolongators) all but disappears.  slot -> row
+    // in sellp_perm (-1: no row); operators without a halo only.  Never chosen by the heuristic: set_mapping / autotune.
+    long long *sellp_ptr = nullptr;
+    int *sellp_perm = nullptr;
+    int *sellp_col = nullptr;
+    double *sellp_val = nullptr;
+    int64_t sellp_padded = 0;
+    bool use_sellp = false;
+
     // remote block re-sorted by row at upload: boundary rows only
     // interior rows = the contiguous range [int_lo, int_hi) (multiples of 32) that holds no row with
     // remote entries: for a slab partition the rows touching ghosts sit at the two ends of the
@@ -277,6 +288,7 @@ enum { S_RHO_RES = 0, S_PDOTH = 1, S_RR = 2, S_BETA_NUM = 3, S_TMP = 4,
        S_COUNT = 16 };
 
 static const int SB_MAPPING_SELL = 100;   // forced_mapping / set_mapping code of the sliced layout
+static const int SB_MAPPING_SELLP = 101;  // ... of the sliced layout with rows sorted by length inside 256-row windows
 static const int STREAM_TILE = 2048;      // nnz per row block of the streaming kernel (16 KB of products)
 static const int STREAM_THREADS = 256;
 static const int RED_MAX_BLOCKS = 1184;   // 148 SMs x 8

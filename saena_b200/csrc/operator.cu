@@ -37,6 +37,7 @@ void sb_free_operator(DevOperator &op) {
     cudaFree(op.p2p_segs); cudaFree(op.p2p_ticket); cudaFree(op.p2p_signal_consumed);
     // ghost_buf / x_ext belong to the context's halo arena
     cudaFree(op.sell_ptr); cudaFree(op.sell_col); cudaFree(op.sell_val);
+    cudaFree(op.sellp_ptr); cudaFree(op.sellp_perm); cudaFree(op.sellp_col); cudaFree(op.sellp_val);
     cudaFree(op.x_round);
     op = DevOperator();
 }
@@ -351,6 +352,9 @@ static int pow2_at_most(double v) {
 void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op) {
     const double avg = op.M ? double(op.nnz_local) / op.M : 0.0;
     int m = op.sell_only ? SB_MAPPING_SELL : op.forced_mapping;
+    // the sorted sliced layout permutes rows inside 256-row windows: no interior / boundary row ranges, so only for
+    // operators without a halo (one rank, or a block that happens to have no remote part)
+    if (m == SB_MAPPING_SELLP && (!op.sends.empty() || !op.recvs.empty() || op.merged || op.nnz_remote > 0)) m = 0;
     if (m == 0) {
         // short and regular rows: sliced layout (padding <= 15 %); otherwise a sub-warp per row
         // with ~4+ elements per lane.  Crossovers measured on B200, see DESIGN.md.
@@ -375,9 +379,12 @@ void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op) {
             if (m < 32 && op.M <= 32 * 32 * ctx->sm_count) m = 32;
         }
     }
-    op.use_stream = op.use_sell = false;
+    op.use_stream = op.use_sell = op.use_sellp = false;
     if (m == SB_MAPPING_SELL) {
         op.use_sell = true;
+        op.lanes = 1;
+    } else if (m == SB_MAPPING_SELLP) {
+        op.use_sellp = true;
         op.lanes = 1;
     } else if (m < 0) {
         op.use_stream = true;
@@ -497,11 +504,94 @@ static int build_sell(saena_b200_ctx *ctx, DevOperator &op) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// sorted sliced layout (mapping 101): rows sorted by length, longest first, inside windows of SELLP_WINDOW
+// consecutive rows; the permutation is made on the host from the row offsets, the entries are moved on the device
+// ---------------------------------------------------------------------------------------------
+constexpr int SELLP_WINDOW = 256;  // = the CTA size of spmv_sellp_kernel
+
+template <typename OffT>
+__global__ void sellp_fill_kernel(int n_slots, const int *__restrict__ perm, const OffT *__restrict__ rowptr,
+                                  const int *__restrict__ col, const double *__restrict__ val,
+                                  const long long *__restrict__ slice_ptr, int *__restrict__ scol,
+                                  double *__restrict__ sval) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const int slice = slot >> 5, lane = slot & 31;
+    const long long base = slice_ptr[slice];
+    const int len = (int)((slice_ptr[slice + 1] - base) >> 5);
+    const int row = perm[slot];
+    OffT a = 0, b = 0;
+    if (row >= 0) { a = rowptr[row]; b = rowptr[row + 1]; }
+    const int pad_col = (b > a) ? col[b - 1] : 0;  // padding: val 0.0, a column the row already touches
+    for (int j = 0; j < len; ++j) {
+        const long long dst = base + (long long)j * 32 + lane;
+        if (a + j < b) {
+            scol[dst] = col[a + j];
+            sval[dst] = val[a + j];
+        } else {
+            scol[dst] = pad_col;
+            sval[dst] = 0.0;
+        }
+    }
+}
+
+static int build_sellp(saena_b200_ctx *ctx, DevOperator &op) {
+    if (op.sellp_ptr) return 0;
+    if (!op.col || !op.val) SB_FAIL("sorted sliced layout: the CSR entries of this operator were released");
+    const int M = op.M;
+    const int n_win = (M + SELLP_WINDOW - 1) / SELLP_WINDOW;
+    const int n_slots = n_win * SELLP_WINDOW;
+    const int ns = n_slots / 32;
+    // row lengths from the row offsets
+    std::vector<int64_t> rp((size_t)M + 1, 0);
+    if (op.wide_offsets) {
+        SB_CUDA(cudaMemcpy(rp.data(), op.rowptr, sizeof(int64_t) * ((size_t)M + 1), cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<int> rp32((size_t)M + 1, 0);
+        SB_CUDA(cudaMemcpy(rp32.data(), op.rowptr, sizeof(int) * ((size_t)M + 1), cudaMemcpyDeviceToHost));
+        for (int i = 0; i <= M; ++i) rp[i] = rp32[i];
+    }
+    std::vector<int> perm((size_t)std::max(n_slots, 1), -1);
+    std::vector<long long> sp((size_t)ns + 1, 0);
+    for (int w = 0; w < n_win; ++w) {
+        const int r0 = w * SELLP_WINDOW, r1 = std::min(M, r0 + SELLP_WINDOW);
+        int *p = perm.data() + (size_t)w * SELLP_WINDOW;
+        for (int r = r0; r < r1; ++r) p[r - r0] = r;
+        std::stable_sort(p, p + (r1 - r0), [&](int x, int y) { return rp[x + 1] - rp[x] > rp[y + 1] - rp[y]; });
+        for (int k = 0; k < SELLP_WINDOW / 32; ++k) {
+            const int first = p[k * 32];                        // the longest row of the slice (or none: -1)
+            const long long len = first >= 0 ? (long long)(rp[first + 1] - rp[first]) : 0;
+            const int sl = w * (SELLP_WINDOW / 32) + k;
+            sp[sl + 1] = sp[sl] + len * 32;
+        }
+    }
+    const int64_t padded = sp[ns];
+    op.sellp_padded = padded;
+    SB_TRY(dev_upload(ctx, &op.sellp_ptr, sp.data(), sp.size()));
+    SB_TRY(dev_upload(ctx, &op.sellp_perm, perm.data(), perm.size()));
+    SB_CUDA(cudaMalloc((void **)&op.sellp_col, sizeof(int) * std::max<int64_t>(padded, 1)));
+    SB_CUDA(cudaMalloc((void **)&op.sellp_val, sizeof(double) * std::max<int64_t>(padded, 1)));
+    if (n_slots) {
+        const int blocks = n_slots / 256;
+        if (op.wide_offsets)
+            sellp_fill_kernel<int64_t><<<blocks, 256, 0, ctx->stream>>>(n_slots, op.sellp_perm, (const int64_t *)op.rowptr,
+                                                                        op.col, op.val, op.sellp_ptr, op.sellp_col, op.sellp_val);
+        else
+            sellp_fill_kernel<int><<<blocks, 256, 0, ctx->stream>>>(n_slots, op.sellp_perm, (const int *)op.rowptr, op.col,
+                                                                    op.val, op.sellp_ptr, op.sellp_col, op.sellp_val);
+    }
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int sb_prepare_operator(saena_b200_ctx *ctx, DevOperator &op) {
     if (!op.present) return 0;
     sb_choose_mapping(ctx, op);
     if (op.use_stream) SB_TRY(build_row_blocks(ctx, op, STREAM_THREADS / op.lanes));
     if (op.use_sell) SB_TRY(build_sell(ctx, op));
+    if (op.use_sellp) SB_TRY(build_sellp(ctx, op));
     return 0;
 }
 
@@ -517,7 +607,12 @@ static void launch_local(saena_b200_ctx *ctx, DevOperator &op, const double *x, 
     const int nrows = hi - lo;
     if (nrows <= 0) return;
     ++ctx->launches;
-    if (op.use_sell) {
+    if (op.use_sellp) {
+        // whole operator (no halo, see sb_choose_mapping): one CTA per 256-row window
+        const int n_slots = (op.M + 255) / 256 * 256;
+        spmv_sellp_kernel<EPI><<<n_slots / 256, 256, 0, s>>>(n_slots, op.sellp_ptr, op.sellp_perm, op.sellp_col,
+                                                             op.sellp_val, x, e);
+    } else if (op.use_sell) {
         const int blocks = (nrows + 255) / 256;
         spmv_sell_kernel<EPI><<<blocks, 256, 0, s>>>(lo, hi, op.sell_ptr, op.sell_col, op.sell_val, x, e, nullptr);
     } else if (op.use_stream) {

@@ -334,6 +334,50 @@ spmv_sell_kernel(int row_begin, int M, const long long *__restrict__ slice_ptr, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// spmv_sellp: the sliced layout over a row permutation (SELL-C-sigma with C = 32, sigma = 256 = one CTA).  Slot t of
+// the grid works on row perm[t]; the rows of a CTA's 256 slots are the 256 consecutive rows of its window, sorted by
+// length, so every slice is nearly rectangular whatever the row-length distribution, and the epilogue's vector
+// streams of a CTA still fall into one contiguous 2 KB range per vector.  Each row is summed by one lane in
+// column order, exactly as in spmv_sell: same result, bit for bit.
+// ---------------------------------------------------------------------------------------------
+template <int EPI, typename XS>
+__device__ __forceinline__ void
+spmv_sellp_body(int vb, int n_slots, const long long *__restrict__ slice_ptr, const int *__restrict__ perm,
+                const int *__restrict__ col, const double *__restrict__ val, const XS xs, const EpiArgs &e) {
+    const int slot = vb * blockDim.x + threadIdx.x;  // n_slots is a multiple of 32
+    if (slot >= n_slots) return;
+    const int lane = threadIdx.x & 31;
+    const int slice = slot >> 5;
+    const long long base = slice_ptr[slice];
+    const int len = (int)((slice_ptr[slice + 1] - base) >> 5);
+    const int *cp = col + base + lane;
+    const double *vp = val + base + lane;
+    double sum = 0.0;
+    int j = 0;
+    for (; j + 4 <= len; j += 4) {
+        int c[4];
+        double a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            c[q] = sb_ld_stream(cp + (j + q) * 32);
+            a[q] = sb_ld_stream(vp + (j + q) * 32);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sum += a[q] * xs.ld(c[q]);
+    }
+    for (; j < len; ++j) sum += sb_ld_stream(vp + j * 32) * xs.ld(sb_ld_stream(cp + j * 32));
+    const int row = perm[slot];
+    if (row >= 0) sb_epilogue<EPI>(row, sum, e);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256)
+spmv_sellp_kernel(int n_slots, const long long *__restrict__ slice_ptr, const int *__restrict__ perm,
+                  const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, EpiArgs e) {
+    spmv_sellp_body<EPI>(blockIdx.x, n_slots, slice_ptr, perm, col, val, XLocal{x}, e);
+}
+
+// ---------------------------------------------------------------------------------------------
 // boundary rows: rows with entries in other ranks' columns.  8 or 32 lanes per row: local segment
 // (recomputed -- these rows are a few percent of the block) + remote segment read from the ghost
 // buffer the halo exchange filled (float when the operator's use_double is false:

@@ -436,8 +436,8 @@ class Context:
 
     def autotune_mapping(self, reps: int = 10, min_gain: float = 0.03):
         """One rank only (setup time, untimed): for every uploaded operator, time the row mappings around the one
-        `sb_choose_mapping` picked from nnz/row (half / double / four times the threads per row; the sliced layout
-        only where the heuristic chose it -- building it costs a second copy of the operator) with the library's own
+        `sb_choose_mapping` picked from nnz/row (half / double / four times the threads per row; the sorted sliced
+        layout, mapping 101, where many short irregular rows run on a sub-warp mapping) with the library's own
         per-launch timer and keep the fastest if it wins by more than `min_gain`.  Composes saena_b200_set_mapping and
         saena_b200_time_matvec; returns [(level, kind, before, after, ms_before, ms_after)].
         Not collective-safe: with several ranks every timed application is an exchange and the candidate lists
@@ -454,6 +454,8 @@ class Context:
                     continue                       # sliced / streaming: measured choices, left alone
                 flush = self.operator_bytes(l, kind) < 300e6
                 cands = sorted({c for c in (cur // 4, cur // 2, cur * 2, cur * 4) if 1 <= c <= 256 and c != cur})
+                if cur < 32 and op.M >= 150_000 and op.nnz_remote == 0:
+                    cands.append(101)              # many short irregular rows: the sorted sliced layout
                 best, t0 = cur, self.time_matvec(l, kind, reps, flush_l2=flush)
                 tb = t0
                 for c in cands:

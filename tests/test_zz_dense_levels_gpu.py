@@ -73,3 +73,30 @@ def test_mapping_autotune_keeps_parity():
         check_vcycle_against_golden(ctx, g)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("name", ["helmholtz2d_p8", "poisson12_cheb", "band8_1500"])
+def test_sorted_sliced_layout_mapping_101(name):
+    """mapping 101 (sliced layout over rows sorted by length inside 256-row windows, csrc/operator.cu:build_sellp):
+    every operator of the hierarchy, plain product and fused epilogues, against the reference's outputs; the
+    mapping sticks (one rank: no halo) and gives the sliced mapping's result bit for bit (one lane sums a row in
+    column order in both)"""
+    g = Golden(name)
+    ctx = Context()
+    try:
+        ctx.upload_hierarchy(g.hier)
+        for l, lv in enumerate(g.hier.levels):
+            for kind, op in ((0, lv.A), (1, lv.P), (2, lv.R)):
+                if op is None:
+                    continue
+                x = g[f"in.L{l}.vc"] if kind == 1 else g[f"in.L{l}.v"]
+                ctx.set_mapping(l, kind, 100)
+                w100 = ctx.matvec(l, kind, x)
+                ctx.set_mapping(l, kind, 101)
+                assert ctx.get_mapping(l, kind) == 101
+                w101 = ctx.matvec(l, kind, x)
+                assert np.array_equal(w100, w101), (l, kind)
+        check_ops_against_golden(ctx, g)          # all A on 101 now: SpMV, residual, Chebyshev, Jacobi; P and R
+        check_vcycle_against_golden(ctx, g)
+    finally:
+        ctx.close()
