@@ -14,6 +14,16 @@ for l in open("gpurun_out/r02_bench.json"):
         print("roofline", d["roofline"]["frac"], "cpu_baseline", d.get("cpu_baseline", {}).get("value"))
         print("mapping_autotune", json.dumps(d.get("mapping_autotune"))[:1500])
 P
+# configs[4]'s shape on one GPU with the same in-run A/B (irregular rows: where mapping 101 should pay)
+SAENA_BENCH_AUTOTUNE_MAP=1 timeout 600 python bench.py --workload unstructured2d --steps 5 --no-cpu-baseline 2> gpurun_out/r02_bench_unstructured.err \
+  | tee gpurun_out/r02_bench_unstructured.json | cut -c1-300
+python - <<'P'
+import json
+for l in open("gpurun_out/r02_bench_unstructured.json"):
+    if l.startswith("{"):
+        d = json.loads(l)
+        print("unstructured ms/solve", d["ms_per_step"], "mapping_autotune", json.dumps(d.get("mapping_autotune"))[:1500])
+P
 # ncu launch list of one bench solve (only after the plain run above exited 0), then the transfer kernels
 K='regex:spmv_|halo_pack|dot_kernel|pcg_|cheb_first|negate_copy|coarsest_kernel|carry_scalar|cg_p_|scale_vector|widen_ghost'
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 2380 -c 800 --csv \
