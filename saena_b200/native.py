@@ -450,12 +450,23 @@ class Context:
                 if op is None or op.M == 0:
                     continue
                 cur = self.get_mapping(l, kind)
-                if cur <= 0 or cur == 100:
-                    continue                       # sliced / streaming: measured choices, left alone
+                if cur <= 0 or cur == 101:
+                    continue                       # streaming (forced by hand) / already the sorted layout
                 flush = self.operator_bytes(l, kind) < 300e6
-                cands = sorted({c for c in (cur // 4, cur // 2, cur * 2, cur * 4) if 1 <= c <= 256 and c != cur})
-                if cur < 32 and op.M >= 150_000 and op.nnz_remote == 0:
-                    cands.append(101)              # many short irregular rows: the sorted sliced layout
+                if cur == 100:
+                    # sliced layout: measured choice; the only candidate is its sorted variant, and only where the
+                    # slices are padded (rows of unequal length) and the operator has no halo
+                    n = np.asarray(op.nnzPerRow_local, np.int64)
+                    pad = np.zeros((len(n) + 31) // 32 * 32, np.int64)
+                    pad[:len(n)] = n
+                    padded = int(pad.reshape(-1, 32).max(axis=1).sum()) * 32
+                    cands = [101] if (op.nnz_remote == 0 and n.sum() > 0 and padded > 1.03 * n.sum()) else []
+                    if not cands:
+                        continue
+                else:
+                    cands = sorted({c for c in (cur // 4, cur // 2, cur * 2, cur * 4) if 1 <= c <= 256 and c != cur})
+                    if cur < 32 and op.M >= 150_000 and op.nnz_remote == 0:
+                        cands.append(101)          # many short irregular rows: the sorted sliced layout
                 best, t0 = cur, self.time_matvec(l, kind, reps, flush_l2=flush)
                 tb = t0
                 for c in cands:
