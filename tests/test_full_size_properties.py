@@ -1,5 +1,5 @@
 """The size-independent property checker (tests/full_size_properties.py) run through the C oracle at a size it
-finishes in seconds; tests/test_zz_full_size_gpu.py runs the same checker through the CUDA path at 256^3."""
+finishes in seconds; tests/test_zy_full_size_gpu.py runs the same checker through the CUDA path at 256^3."""
 import pytest
 
 from oracle.oracle import Oracle

@@ -4,7 +4,7 @@ hold at any size (tests/full_size_properties.py): stencil row sums on every row,
 operator, R = P^T adjointness, linearity of the fused smoother sweeps and of the V-cycle, symmetry and
 positivity of the V-cycle as a preconditioner, and the PCG answer against the residual recomputed from u.
 The same checker runs through the oracle at small sizes (tests/test_full_size_properties.py).
-(Sorted last: ~2 min of GPU time, most of it the untimed setup; first GPU run at round end.)"""
+(Sorted after the core parity tests and before the tests of never-run kernels: ~2 min of GPU time, most of it the untimed setup; first GPU run at round end.)"""
 import os
 
 import pytest
