@@ -251,6 +251,11 @@ int saena_b200_set_mapping(saena_b200_ctx *ctx, int level, int kind, int mapping
 /* The same, taking effect at the next saena_b200_finalize (no layout is built for the mapping that
  * is being replaced: matters for an operator that fills half the HBM). */
 int saena_b200_set_mapping_deferred(saena_b200_ctx *ctx, int level, int kind, int mapping);
+/* Host-only half of mapping 101 (no device needed; what the layout build calls): for row offsets rowptr[M + 1], the
+ * slot -> row permutation perm[ceil(M / 256) * 256] (rows of every 256-row window sorted by length, longest first,
+ * stable; -1 where the last window runs past M) and slice_ptr[ceil(M / 256) * 8 + 1], the element offset of every
+ * 32-slot slice (32 x its longest row). */
+int saena_b200_sellp_layout(int M, const int64_t *rowptr, int32_t *perm, long long *slice_ptr);
 /* the mapping in use (same codes) */
 int saena_b200_get_mapping(const saena_b200_ctx *ctx, int level, int kind);
 /* algorithmic bytes of one application of an operator (SURVEY.md 8d formula), for the roofline */

@@ -845,6 +845,12 @@ int saena_b200_set_graphs(saena_b200_ctx *ctx, int on) {
 
 int64_t saena_b200_graph_replays(const saena_b200_ctx *ctx) { return ctx ? ctx->graph_replays : 0; }
 
+int saena_b200_sellp_layout(int M, const int64_t *rowptr, int32_t *perm, long long *slice_ptr) {
+    if (M < 0 || !rowptr || !perm || !slice_ptr) return 1;
+    sb_sellp_layout(M, rowptr, perm, slice_ptr);
+    return 0;
+}
+
 int saena_b200_get_mapping(const saena_b200_ctx *ctx, int level, int kind) {
     if (!ctx || level < 0 || level >= (int)ctx->levels.size()) return 0;
     const DevLevel &lv = ctx->levels[level];

@@ -310,6 +310,7 @@ int sb_upload_band_operator(saena_b200_ctx *ctx, int level, int n, int half_band
 void sb_free_operator(DevOperator &op);
 void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op);
 int sb_prepare_operator(saena_b200_ctx *ctx, DevOperator &op);
+void sb_sellp_layout(int M, const int64_t *rowptr, int *perm, long long *slice_ptr);
 // w-style application of an operator with a fused epilogue; x is the local input vector.
 int sb_apply(saena_b200_ctx *ctx, DevOperator &op, const double *x, int epi, const EpiArgs &args);
 int64_t sb_operator_bytes(const DevOperator &op);

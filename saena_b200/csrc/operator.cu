@@ -536,6 +536,26 @@ __global__ void sellp_fill_kernel(int n_slots, const int *__restrict__ perm, con
     }
 }
 
+// host only: slot -> row (rows of each SELLP_WINDOW-row window sorted by length, longest first, stable; -1 where the
+// last window runs past M) and the element offset of every 32-slot slice (its longest row's length x 32).
+// perm[ceil(M / 256) * 256], slice_ptr[ceil(M / 256) * 8 + 1].
+void sb_sellp_layout(int M, const int64_t *rp, int *perm, long long *sp) {
+    const int n_win = (M + SELLP_WINDOW - 1) / SELLP_WINDOW;
+    sp[0] = 0;
+    for (int w = 0; w < n_win; ++w) {
+        const int r0 = w * SELLP_WINDOW, r1 = std::min(M, r0 + SELLP_WINDOW);
+        int *p = perm + (size_t)w * SELLP_WINDOW;
+        for (int k = 0; k < SELLP_WINDOW; ++k) p[k] = r0 + k < r1 ? r0 + k : -1;
+        std::stable_sort(p, p + (r1 - r0), [&](int x, int y) { return rp[x + 1] - rp[x] > rp[y + 1] - rp[y]; });
+        for (int k = 0; k < SELLP_WINDOW / 32; ++k) {
+            const int first = p[k * 32];                        // the longest row of the slice (or none: -1)
+            const long long len = first >= 0 ? (long long)(rp[first + 1] - rp[first]) : 0;
+            const int sl = w * (SELLP_WINDOW / 32) + k;
+            sp[sl + 1] = sp[sl] + len * 32;
+        }
+    }
+}
+
 static int build_sellp(saena_b200_ctx *ctx, DevOperator &op) {
     if (op.sellp_ptr) return 0;
     if (!op.col || !op.val) SB_FAIL("sorted sliced layout: the CSR entries of this operator were released");
@@ -554,18 +574,7 @@ static int build_sellp(saena_b200_ctx *ctx, DevOperator &op) {
     }
     std::vector<int> perm((size_t)std::max(n_slots, 1), -1);
     std::vector<long long> sp((size_t)ns + 1, 0);
-    for (int w = 0; w < n_win; ++w) {
-        const int r0 = w * SELLP_WINDOW, r1 = std::min(M, r0 + SELLP_WINDOW);
-        int *p = perm.data() + (size_t)w * SELLP_WINDOW;
-        for (int r = r0; r < r1; ++r) p[r - r0] = r;
-        std::stable_sort(p, p + (r1 - r0), [&](int x, int y) { return rp[x + 1] - rp[x] > rp[y + 1] - rp[y]; });
-        for (int k = 0; k < SELLP_WINDOW / 32; ++k) {
-            const int first = p[k * 32];                        // the longest row of the slice (or none: -1)
-            const long long len = first >= 0 ? (long long)(rp[first + 1] - rp[first]) : 0;
-            const int sl = w * (SELLP_WINDOW / 32) + k;
-            sp[sl + 1] = sp[sl] + len * 32;
-        }
-    }
+    sb_sellp_layout(M, rp.data(), perm.data(), sp.data());
     const int64_t padded = sp[ns];
     op.sellp_padded = padded;
     SB_TRY(dev_upload(ctx, &op.sellp_ptr, sp.data(), sp.size()));

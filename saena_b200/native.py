@@ -67,6 +67,7 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_upload_coarsest.argtypes = [vp, i, ctypes.c_int64, c_i32_p, c_i32_p, dp]
     L.saena_b200_set_coarsest_solver.argtypes = [vp, i]
     L.saena_b200_set_operator_dense.argtypes = [vp, i, i, i]
+    L.saena_b200_sellp_layout.argtypes = [i, vp, vp, vp]
     L.saena_b200_set_graphs.argtypes = [vp, i]
     L.saena_b200_finalize.argtypes = [vp]
     L.saena_b200_p2p_export.argtypes = [vp, vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
@@ -111,7 +112,7 @@ EXPORTED_SYMBOLS = [
     "saena_b200_nccl_unique_id", "saena_b200_init", "saena_b200_init_detached", "saena_b200_time_matvec_compute_only", "saena_b200_destroy", "saena_b200_last_error",
     "saena_b200_upload_operator", "saena_b200_upload_band_operator", "saena_b200_upload_level_aux", "saena_b200_upload_level_scale",
     "saena_b200_upload_coarsest",
-    "saena_b200_set_coarsest_solver", "saena_b200_set_operator_dense", "saena_b200_set_graphs", "saena_b200_finalize",
+    "saena_b200_set_coarsest_solver", "saena_b200_set_operator_dense", "saena_b200_sellp_layout", "saena_b200_set_graphs", "saena_b200_finalize",
     "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_find_eig", "saena_b200_p2p_enable", "saena_b200_autotune_halo", "saena_b200_halo_choice", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
@@ -152,6 +153,19 @@ def smoother_id(name) -> int:
     if name == "jacobi":
         return JACOBI
     raise ValueError(f"unknown smoother {name!r}")  # the reference: "Error: Unknown smoother" then exit
+
+
+def sellp_layout(rowptr: np.ndarray):
+    """host-only half of mapping 101 (saena_b200_sellp_layout): (perm, slice_ptr) for CSR row offsets"""
+    rp = np.ascontiguousarray(rowptr, np.int64)
+    M = len(rp) - 1
+    n_slots = (M + 255) // 256 * 256
+    perm = np.full(max(n_slots, 1), -1, I32)
+    sp = np.zeros(n_slots // 32 + 1, np.int64)
+    L = load_library()
+    if L.saena_b200_sellp_layout(M, _vp(rp), _vp(perm), _vp(sp)):
+        raise RuntimeError("saena_b200_sellp_layout failed")
+    return perm[:n_slots], sp
 
 
 class Context:
