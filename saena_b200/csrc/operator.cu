@@ -618,9 +618,8 @@ static void launch_local(saena_b200_ctx *ctx, DevOperator &op, const double *x, 
     ++ctx->launches;
     if (op.use_sellp) {
         // whole operator (no halo, see sb_choose_mapping): one CTA per 256-row window
-        const int n_slots = (op.M + 255) / 256 * 256;
-        spmv_sellp_kernel<EPI><<<n_slots / 256, 256, 0, s>>>(n_slots, op.sellp_ptr, op.sellp_perm, op.sellp_col,
-                                                             op.sellp_val, x, e);
+        spmv_sellp_kernel<EPI><<<(op.M + 255) / 256, 256, 0, s>>>(op.M, op.sellp_ptr, op.sellp_perm, op.sellp_col,
+                                                                   op.sellp_val, x, e);
     } else if (op.use_sell) {
         const int blocks = (nrows + 255) / 256;
         spmv_sell_kernel<EPI><<<blocks, 256, 0, s>>>(lo, hi, op.sell_ptr, op.sell_col, op.sell_val, x, e, nullptr);

@@ -336,16 +336,17 @@ spmv_sell_kernel(int row_begin, int M, const long long *__restrict__ slice_ptr, 
 // ---------------------------------------------------------------------------------------------
 // spmv_sellp: the sliced layout over a row permutation (SELL-C-sigma with C = 32, sigma = 256 = one CTA).  Slot t of
 // the grid works on row perm[t]; the rows of a CTA's 256 slots are the 256 consecutive rows of its window, sorted by
-// length, so every slice is nearly rectangular whatever the row-length distribution, and the epilogue's vector
-// streams of a CTA still fall into one contiguous 2 KB range per vector.  Each row is summed by one lane in
-// column order, exactly as in spmv_sell: same result, bit for bit.
+// length, so every slice is nearly rectangular whatever the row-length distribution; the row sums go back to row
+// order through shared memory, so the epilogue's vector streams are as coalesced as in spmv_sell.  Each row is
+// summed by one lane in column order, exactly as in spmv_sell: same result, bit for bit.
 // ---------------------------------------------------------------------------------------------
 template <int EPI, typename XS>
 __device__ __forceinline__ void
-spmv_sellp_body(int vb, int n_slots, const long long *__restrict__ slice_ptr, const int *__restrict__ perm,
+spmv_sellp_body(int vb, int M, const long long *__restrict__ slice_ptr, const int *__restrict__ perm,
                 const int *__restrict__ col, const double *__restrict__ val, const XS xs, const EpiArgs &e) {
-    const int slot = vb * blockDim.x + threadIdx.x;  // n_slots is a multiple of 32
-    if (slot >= n_slots) return;
+    // blockDim.x == 256 == the window; the grid holds exactly ceil(M / 256) CTAs, so every slot exists
+    __shared__ double s_sum[256];
+    const int slot = vb * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int slice = slot >> 5;
     const long long base = slice_ptr[slice];
@@ -366,15 +367,21 @@ spmv_sellp_body(int vb, int n_slots, const long long *__restrict__ slice_ptr, co
         for (int q = 0; q < 4; ++q) sum += a[q] * xs.ld(c[q]);
     }
     for (; j < len; ++j) sum += sb_ld_stream(vp + j * 32) * xs.ld(sb_ld_stream(cp + j * 32));
+    // back to row order through shared memory: the window's rows are the 256 consecutive rows from vb * 256, each in
+    // exactly one slot, so thread t finishes row vb * 256 + t and the epilogue's vector streams stay coalesced
+    const int wbase = vb * 256;
     const int row = perm[slot];
-    if (row >= 0) sb_epilogue<EPI>(row, sum, e);
+    if (row >= 0) s_sum[row - wbase] = sum;
+    __syncthreads();
+    const int mine = wbase + threadIdx.x;
+    if (mine < M) sb_epilogue<EPI>(mine, s_sum[threadIdx.x], e);
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(256)
-spmv_sellp_kernel(int n_slots, const long long *__restrict__ slice_ptr, const int *__restrict__ perm,
+spmv_sellp_kernel(int M, const long long *__restrict__ slice_ptr, const int *__restrict__ perm,
                   const int *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x, EpiArgs e) {
-    spmv_sellp_body<EPI>(blockIdx.x, n_slots, slice_ptr, perm, col, val, XLocal{x}, e);
+    spmv_sellp_body<EPI>(blockIdx.x, M, slice_ptr, perm, col, val, XLocal{x}, e);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -27,14 +27,20 @@ def _emulate(rowptr, col, val, x):
             dst = base + j * 32 + lane
             scol[dst], sval[dst] = (col[a + j], val[a + j]) if a + j < b else (pad_col, 0.0)
     y = np.full(M, np.nan)
-    for slot in range(n_slots):                       # spmv_sellp_body
-        sl, lane = slot >> 5, slot & 31
-        base, ln = int(sp[sl]), int(sp[sl + 1] - sp[sl]) >> 5
-        s = 0.0
-        for j in range(ln):
-            s += sval[base + j * 32 + lane] * x[scol[base + j * 32 + lane]]
-        if perm[slot] >= 0:
-            y[perm[slot]] = s
+    for vb in range(n_slots // 256):                  # spmv_sellp_body, one CTA per window
+        s_sum = np.full(256, np.nan)
+        for t in range(256):
+            slot = vb * 256 + t
+            sl, lane = slot >> 5, t & 31
+            base, ln = int(sp[sl]), int(sp[sl + 1] - sp[sl]) >> 5
+            s = 0.0
+            for j in range(ln):
+                s += sval[base + j * 32 + lane] * x[scol[base + j * 32 + lane]]
+            if perm[slot] >= 0:
+                s_sum[perm[slot] - vb * 256] = s      # back to row order through shared memory
+        for t in range(256):
+            if vb * 256 + t < M:
+                y[vb * 256 + t] = s_sum[t]
     return y, perm, sp
 
 
