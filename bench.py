@@ -323,6 +323,8 @@ def main():
         agg_sweep = [int(x) for x in filter(None, os.environ.get("SAENA_BENCH_AGG_SWEEP", "").split(","))] if world > 1 else []
         if not agg_sweep:
             del dh
+    import gc
+    gc.collect()                 # the setup's tensors go back to the driver before the library allocates
     torch.cuda.empty_cache()
     ctx = native.Context(device=local, rank=rank, nranks=world, nccl_id=nccl_id)
     ctx.upload_hierarchy(hier)
