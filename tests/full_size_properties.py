@@ -73,5 +73,5 @@ def check(impl, hier, n, rhs, tol=1e-12, seed=7):
     # the recurrence's residual and the recomputed one drift apart by ~ eps * ||A|| ||u|| / ||b|| per update (2.6e4 * eps at
     # 256^3: 1e-3 of a 1e-8 residual after ten iterations): a few percent is the most that may separate them
     assert true_rel < 1.05e-8 and abs(true_rel - out["rel_residual"]) <= 0.05 * out["rel_residual"], out
-    assert np.all(np.diff(hist) < 0)                     # this problem's history decreases monotonically
+    assert np.all(hist[1:] < hist[0])                    # (CG does not promise a monotone residual 2-norm: only this)
     return out
