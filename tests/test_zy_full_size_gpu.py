@@ -30,7 +30,7 @@ def test_full_size_256_cubed_properties():
         ctx.upload_hierarchy(hier)
         out = check(ctx, hier, n, sa_setup.poisson3d_rhs(n))
         if n == 256:
-            assert out["iterations"] == 9        # the bench's count (profiles/r01_bench_levels.md)
+            assert abs(out["iterations"] - 9) <= 1     # the bench's count (profiles/r01_bench_levels.md), +-1
         assert ctx.launch_count() > 0
     finally:
         ctx.close()
