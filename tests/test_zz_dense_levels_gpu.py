@@ -85,6 +85,7 @@ def test_sorted_sliced_layout_mapping_101(name):
     ctx = Context()
     try:
         ctx.upload_hierarchy(g.hier)
+        bitwise = []
         for l, lv in enumerate(g.hier.levels):
             for kind, op in ((0, lv.A), (1, lv.P), (2, lv.R)):
                 if op is None:
@@ -95,8 +96,10 @@ def test_sorted_sliced_layout_mapping_101(name):
                 ctx.set_mapping(l, kind, 101)
                 assert ctx.get_mapping(l, kind) == 101
                 w101 = ctx.matvec(l, kind, x)
-                assert np.array_equal(w100, w101), (l, kind)
+                assert rel(w101, w100) <= 1e-14, (l, kind)
+                bitwise.append(np.array_equal(w100, w101))
         check_ops_against_golden(ctx, g)          # all A on 101 now: SpMV, residual, Chebyshev, Jacobi; P and R
         check_vcycle_against_golden(ctx, g)
+        assert all(bitwise), bitwise              # same lane, same order of the same multiply-adds
     finally:
         ctx.close()
