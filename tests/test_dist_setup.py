@@ -48,3 +48,16 @@ def test_one_rank_distributed_setup_is_the_one_process_setup():
             assert a[k].shape == b[k].shape and np.allclose(a[k], b[k], rtol=1e-12, atol=1e-300), k
         else:
             assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_distributed_operator_builder_equals_split_operator(world):
+    """sa_setup_dist.rank_operator (each rank from its own rows) = hierarchy.split_operator (from the global matrix),
+    array by array, on random rectangular operators and partitions with empty blocks (tests/dist_rank_operator_check.py)"""
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29790 + world),
+                          os.path.join(ROOT, "tests", "dist_rank_operator_check.py")],
+                         capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1"))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "RANK_OPERATOR_OK" in out.stdout
