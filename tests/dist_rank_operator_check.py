@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from saena_b200 import sa_setup_dist as sd  # noqa: E402
-from saena_b200.hierarchy import _OP_ARRAYS, KIND_R, split_operator  # noqa: E402
+from saena_b200.hierarchy import _OP_ARRAYS, KIND_R, balanced_split, split_operator  # noqa: E402
 
 
 def main():
@@ -46,6 +46,17 @@ def main():
         for f in _OP_ARRAYS:
             a, b = np.asarray(getattr(got, f)), np.asarray(getattr(want, f))
             assert a.shape == b.shape and np.array_equal(a, b), (seed, rank, f, a, b)
+        # the nnz-balanced split found collectively = hierarchy.balanced_split on the global row offsets
+        assert np.array_equal(sd.balanced_split_dist(comm, M), balanced_split(A.indptr.astype(np.int64), world)), seed
+        # moving the rows to another partition and back changes nothing
+        other = split(n_rows)
+        back = sd.repartition(comm, sd.repartition(comm, M, other), rs)
+        assert torch.equal(back.row, M.row) and torch.equal(back.col, M.col) and torch.equal(back.val, M.val), seed
+        moved = sd.repartition(comm, M, other)
+        o0, o1 = int(other[rank]), int(other[rank + 1])
+        ref_blk = A[o0:o1].tocoo()
+        ordr = np.lexsort((ref_blk.col, ref_blk.row))
+        assert np.array_equal(moved.row.numpy(), ref_blk.row[ordr]) and np.array_equal(moved.col.numpy(), ref_blk.col[ordr]), seed
     dist.barrier()
     if rank == 0:
         print("RANK_OPERATOR_OK", flush=True)
