@@ -194,6 +194,45 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def autotune_mapping_collective(ctx, hier, world, reps=10, min_gain=0.03):
+    """The setup-time row-mapping autotuner on several ranks (opt-in A/B, SAENA_BENCH_AUTOTUNE_MAP): every timed
+    application is an exchange, so all ranks walk the same candidates -- rank 0's current mapping of the operator
+    and its neighbours -- and decide on the slowest rank's time (all-reduce MAX): one mapping per operator, the same
+    on every rank.  Returns [(level, kind, before on this rank, after, ms_before, ms_after)]."""
+    import torch
+    import torch.distributed as dist
+
+    def agree(vals, op):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return t.tolist()
+
+    out = []
+    for l, lv in enumerate(hier.levels):
+        for kind, op in ((0, lv.A), (1, lv.P), (2, lv.R)):
+            if op is None:
+                continue
+            mine = ctx.get_mapping(l, kind) if op.M else 0
+            lead = torch.tensor([mine], dtype=torch.int64, device="cuda")
+            dist.broadcast(lead, 0)
+            cur = int(lead.item())
+            rows = int(agree([float(op.M)], dist.ReduceOp.MIN)[0])
+            if cur <= 0 or cur >= 100 or rows == 0:
+                continue            # sliced / streaming choices and levels some rank holds nothing of: left alone
+            cands = [cur] + sorted({c for c in (cur // 4, cur // 2, cur * 2, cur * 4) if 1 <= c <= 256 and c != cur})
+            times = []
+            for c in cands:
+                ctx.set_mapping(l, kind, c)
+                times.append(ctx.time_matvec(l, kind, reps, flush_l2=ctx.operator_bytes(l, kind) < 300e6))
+            times = agree(times, dist.ReduceOp.MAX)
+            k = int(np.argmin(times))
+            if times[k] > (1.0 - min_gain) * times[0]:
+                k = 0
+            ctx.set_mapping(l, kind, cands[k])
+            out.append((l, kind, mine, cands[k], times[0], times[k]))
+    return out
+
+
 def verify_properties(ctx, hier, rank, world):
     """SAENA_BENCH_VERIFY=1 (untimed, collective): size-independent properties of the uploaded, row-partitioned
     hierarchy -- what stands in for the oracle at sizes it cannot run (tests/full_size_properties.py is the one-rank
@@ -388,18 +427,18 @@ def main():
     clk = clocks.summary()
     graph_info = {"vcycles_replayed_from_graph": ctx.graph_replays()}
     map_tune = None
-    if world == 1 and os.environ.get("SAENA_BENCH_AUTOTUNE_MAP"):
+    if os.environ.get("SAENA_BENCH_AUTOTUNE_MAP"):
         # in-run A/B (not the bench value, off by default until measured): per-operator row mapping picked by timing the
         # neighbours of the heuristic's choice, then the same solves again.  SAENA_BENCH_AUTOTUNE_MAP=keep leaves the tuned
         # mappings in place for the per-level tables below; anything else restores the heuristic's.
-        table = ctx.autotune_mapping(10)
+        table = ctx.autotune_mapping(10) if world == 1 else autotune_mapping_collective(ctx, hier, world)
         for _ in range(2):
             ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
         barrier()
         ctx.timer_start()
         for _ in range(args.steps):
             ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
-        tuned_ms = ctx.timer_stop() / args.steps
+        tuned_ms = max_over_ranks(ctx.timer_stop() / args.steps)
         barrier()
         map_tune = {"ms_per_step_heuristic": ms_step, "ms_per_step_autotuned": tuned_ms,
                     "changed": [dict(zip(("level", "kind", "before", "after", "ms_before", "ms_after"), (l, "APR"[k], a, b, t0, t1)))
