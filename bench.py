@@ -132,11 +132,19 @@ def cpu_reference_solve_multirank(reps: int, warmup: int, ranks: int, mx: int):
     sec = max(float(p["sec_per_solve"][0]) for p in parts)   # max over ranks, as Poisson.cpp:216-246 reports
     iters = int(parts[0]["iters"][0])
     n = (mx - 2) ** 3
+    # the other half of BASELINE.json's metric on the CPU: level-0 SpMV as saena_object::profile_matvecs times it
+    # (5 applications, max over ranks), in the algorithmic bytes of SURVEY 8d: 12 nnz + 20 M, nnz = 7 n - 6 (mx-2)^2
+    spmv_gbs = None
+    if all("sec_per_matvec0" in p.files for p in parts):
+        mv = max(float(p["sec_per_matvec0"][0]) for p in parts)
+        if mv > 0:
+            spmv_gbs = (12.0 * (7 * n - 6 * (mx - 2) ** 2) + 20.0 * n) / mv / 1e9
     what = (f"the reference's own solve_pCG (oracle/_ref/libsaena_ref_mp.so = unmodified paralab/Saena sources, -Ofast) "
             f"on {ranks} MPI ranks = {ranks} host cores (multi-process MPI stand-in over Unix sockets, oracle/ref_shim_mp), "
             f"3D Poisson {mx - 2}^3 = {n} unknowns (laplacian3D mx={mx}), same options; {reps} solves, {iters} "
             f"iterations each, max over ranks; setup + warm-up not timed (whole run {wall:.0f} s)")
-    return dict(value=n / sec / 1e6, unit=UNIT, cores=ranks, kind="reference", sample=what), sec, iters, n
+    return dict(value=n / sec / 1e6, unit=UNIT, cores=ranks, kind="reference", sample=what,
+                spmv_level0_GBs=spmv_gbs), sec, iters, n
 
 
 def cpu_reference_solve(reps: int, warmup: int = 0, mx: int = CPU_SAMPLE_MX):

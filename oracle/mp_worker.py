@@ -154,6 +154,8 @@ def main():
             s.time_solve_pcg(1)
         L.sref_barrier()   # MPI_Barrier before the timed region, as experiments/Poisson.cpp:216-246
         res["sec_per_solve"] = np.array([s.time_solve_pcg(reps) / reps])
+        s.time_matvec(0, 2)
+        res["sec_per_matvec0"] = np.array([s.time_matvec(0, 5)])   # the reference's profile_matvecs figure, level 0
     os.makedirs(out, exist_ok=True)
     np.savez(os.path.join(out, f"rank{rank}.npz"), **res)
     s.close()

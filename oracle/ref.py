@@ -377,3 +377,9 @@ class RefSolver:
 
     def time_solve_pcg(self, reps: int) -> float:
         return float(lib().sref_time_solve_pcg(self._h, int(reps)))
+
+    def time_matvec(self, level: int, reps: int = 5) -> float:
+        """seconds per application of A_level, timed as saena_object::profile_matvecs does (collective)"""
+        f = lib().sref_time_matvec
+        f.restype = ctypes.c_double
+        return float(f(self._h, int(level), int(reps)))

@@ -527,6 +527,25 @@ double sref_time_solve_pcg(void *hv, int reps) {
     return MPI_Wtime() - t0;
 }
 
+// Seconds per application of A_level, the way saena_object::profile_matvecs times it (src/saena_object.cpp:618-638:
+// v = 1, a barrier, `reps` timed matvecs with v and w swapped in between) -- returned instead of printed.
+double sref_time_matvec(void *hv, int level, int reps) {
+    Handle *h = (Handle *)hv;
+    if (level < 0 || level > obj(h)->max_level) return -1.0;
+    Grid &g = obj(h)->grids[level];
+    if (!g.active || !g.A || !g.A->active) return 0.0;
+    std::vector<value_t> v(g.A->M, 1), w(g.A->M);
+    MPI_Barrier(g.A->comm);
+    double t = 0;
+    for (int i = 0; i < reps; ++i) {
+        const double t1 = MPI_Wtime();
+        g.A->matvec(&v[0], &w[0]);
+        t += MPI_Wtime() - t1;
+        std::swap(v, w);
+    }
+    return t / (reps > 0 ? reps : 1);
+}
+
 // saena::amg::profile_matvecs through the public API (experiments/Poisson.cpp:262): the reference's host loop in
 // the reference builds, the adaptor's device timings in the drop-in builds.  Prints "matvec level l" lines.
 void sref_profile_matvecs(void *hv) {
