@@ -73,5 +73,8 @@ def check(impl, hier, n, rhs, tol=1e-12, seed=7):
     # the recurrence's residual and the recomputed one drift apart by ~ eps * ||A|| ||u|| / ||b|| per update (2.6e4 * eps at
     # 256^3: 1e-3 of a 1e-8 residual after ten iterations): a few percent is the most that may separate them
     assert true_rel < 1.05e-8 and abs(true_rel - out["rel_residual"]) <= 0.05 * out["rel_residual"], out
-    assert np.all(hist[1:] < hist[0])                    # (CG does not promise a monotone residual 2-norm: only this)
+    # No claim on the shape of the history: CG minimises the energy norm of the error, not ||r||_2, and on this problem
+    # the first step RAISES the residual norm once n is large -- the C oracle gives hist[1]/hist[0] = 0.32, 0.76, 1.34 at
+    # n = 24, 40, 64 (tests/test_zx_midsize_oracle_gpu.py compares the whole history with the oracle at 96^3 / 128^3).
+    out["hist"] = [float(x) for x in hist / hist[0]]
     return out
