@@ -311,7 +311,7 @@ def main():
     import torch
     import torch.distributed as dist
     from saena_b200 import native
-    from saena_b200.distributed import exchange_nccl_id, setup_p2p_halo
+    from saena_b200.distributed import all_ranks_ok, exchange_nccl_id, setup_p2p_halo
     from saena_b200.hierarchy import KIND_A, KIND_P, KIND_R
     from saena_b200.sa_setup import (build_device_hierarchy, poisson3d_coo, poisson3d_rhs, unstructured2d_coo,
                                      unstructured2d_rhs)
@@ -375,18 +375,65 @@ def main():
     torch.cuda.empty_cache()
     ctx = native.Context(device=local, rank=rank, nranks=world, nccl_id=nccl_id)
     ctx.upload_hierarchy(hier)
-    halo_transport = "none"
-    if world > 1:
+    # Halo transport (N > 1).  Default: NVLink peer memory, fused kernel, per-operator choice fused / separate launches
+    # measured at setup.  Every step below is agreed across the ranks: if the peer-memory exchange cannot be set up, or
+    # its autotune / trial solve fails or times out on ANY rank (csrc/halo_sync.cuh bounds every wait), ALL ranks switch
+    # to the NCCL transport together and the line says so ("halo_fallback").
+    halo_transport, halo_fallback = "none", None
+
+    def fall_back_to_nccl(why: str):
+        nonlocal halo_transport, halo_fallback
+        log(f"[rank {rank}] peer-memory halo -> NCCL: {why}")
+        try:
+            ctx.clear_fault()
+            ctx.p2p_enable(0)
+        except native.NativeError as e:
+            log(f"[rank {rank}] could not switch the transport: {e}")
         halo_transport = "nccl"
-        if os.environ.get("SAENA_B200_HALO", "p2p") == "p2p" and setup_p2p_halo(ctx):
+        halo_fallback = why
+
+    p2p_up = world > 1 and os.environ.get("SAENA_B200_HALO", "p2p") == "p2p" and setup_p2p_halo(ctx, log)
+    # every operator's row mapping chosen by measurement at setup (saena_b200_autotune_mapping, collective; untimed like
+    # the rest of the setup -- the adaptor does the same after its upload); SAENA_BENCH_MAPPING_AUTOTUNE=0: nnz/row rule only
+    mapping_tuned = None
+    if os.environ.get("SAENA_BENCH_MAPPING_AUTOTUNE", "1") != "0":
+        before = {(l, k): ctx.get_mapping(l, k) for l in range(len(hier.levels)) for k in (KIND_A, KIND_P, KIND_R)}
+        for attempt in (0, 1):
+            ok, why = True, "on another rank"
+            try:
+                ctx.autotune_mapping_native(10, 0.03)
+            except native.NativeError as e:
+                ok, why = False, f"mapping autotune: {e}"
+            if world == 1 and not ok:
+                raise SystemExit(f"bench.py: {why}")
+            if world == 1 or all_ranks_ok(ok):
+                break
+            if attempt == 1 or not p2p_up:
+                raise SystemExit(f"bench.py: mapping autotune failed over NCCL too ({why})")
+            fall_back_to_nccl(why)   # its timed applications are the first exchanges over peer memory
+            p2p_up = False
+        mapping_tuned = [{"level": l, "kind": "APR"[k], "rule": b, "measured": ctx.get_mapping(l, k)}
+                         for (l, k), b in before.items() if b != 0 and ctx.get_mapping(l, k) != b]
+    if world > 1:
+        if halo_fallback is None:
+            halo_transport = "nccl"
+        if p2p_up:
             if os.environ.get("SAENA_B200_HALO_FUSED", "1") != "0":
                 halo_transport = ("nvlink peer memory, fused: pack + peer stores + interior rows + ghost rows "
                                   "in one kernel per operator application")
                 if os.environ.get("SAENA_B200_HALO_AUTOTUNE", "1") != "0":
-                    ctx.autotune_halo(10)   # per operator: fused kernel or separate launches, whichever measured faster
-                    halo_transport += "; per-operator choice fused / separate launches measured at setup"
+                    ok, why = True, "on another rank"
+                    try:
+                        ctx.autotune_halo(10)   # per operator: fused kernel or separate launches, whichever measured faster
+                    except native.NativeError as e:
+                        ok, why = False, f"autotune: {e}"
+                    if all_ranks_ok(ok):
+                        halo_transport += "; per-operator choice fused / separate launches measured at setup"
+                    else:
+                        fall_back_to_nccl(why)
             else:
-                halo_transport = "nvlink peer memory (pack kernel stores into the neighbour's ghost buffer)"
+                ctx.p2p_enable(1)
+                halo_transport = "nvlink peer memory, separate launches (pack kernel stores into the neighbour's landing area)"
     for spec in filter(None, os.environ.get("SAENA_BENCH_MAP", "").split(",")):   # tuning: "level:kind:mapping"
         lvl, kind, mp = (int(x) for x in spec.split(":"))
         ctx.set_mapping(lvl, kind, mp)
@@ -416,20 +463,45 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if world > 1 and halo_transport != "nccl":
+        # trial solve over the chosen transport before anything is timed
+        ok, why = True, "on another rank"
+        try:
+            ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+        except native.NativeError as e:
+            ok, why = False, f"trial solve: {e}"
+        if not all_ranks_ok(ok):
+            fall_back_to_nccl(why)
+
     # ---- warm-up (the clock sampler starts here: nvidia-smi needs ~0.2 s before its first sample,
     #      longer than a multi-GPU timed region; every sample is taken under the same solve load)
-    iters = hist = None
-    with ClockSampler(local) as clocks:
-        for _ in range(args.warmup):
-            iters, hist = ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
-        # ---- timed: K solves, inputs resident in HBM, CUDA events on the library's compute stream
-        launches0 = ctx.launch_count()
-        barrier()
-        ctx.timer_start()
-        for _ in range(args.steps):
-            iters, hist = ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
-        ms_total = ctx.timer_stop()
-        barrier()
+    def timed_region():
+        it_ = hist_ = None
+        with ClockSampler(local) as clocks_:
+            for _ in range(args.warmup):
+                it_, hist_ = ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+            # ---- timed: K solves, inputs resident in HBM, CUDA events on the library's compute stream
+            l0_ = ctx.launch_count()
+            barrier()
+            ctx.timer_start()
+            for _ in range(args.steps):
+                it_, hist_ = ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
+            ms_ = ctx.timer_stop()
+            barrier()
+        return it_, hist_, ms_, l0_, clocks_
+
+    ok, why = True, "on another rank"
+    try:
+        iters, hist, ms_total, launches0, clocks = timed_region()
+    except native.NativeError as e:
+        if world == 1:
+            raise
+        ok, why = False, f"timed region: {e}"
+    if world > 1 and not all_ranks_ok(ok):
+        if halo_transport == "nccl":
+            raise SystemExit(f"bench.py: the solve failed over the NCCL transport too ({why})")
+        fall_back_to_nccl(why)
+        iters, hist, ms_total, launches0, clocks = timed_region()
     launches = ctx.launch_count() - launches0
     ms_step = max_over_ranks(ms_total / args.steps)
     clk = clocks.summary()
@@ -454,7 +526,8 @@ def main():
         if os.environ["SAENA_BENCH_AUTOTUNE_MAP"] != "keep":
             for l, k, a, b, _, _ in table:
                 ctx.set_mapping(l, k, a)
-    if world > 1 and ctx.graph_replays() > 0 and not os.environ.get("SAENA_BENCH_NO_AB"):
+    # (opt-in since round 2, SAENA_BENCH_AB=1: the default run carries the bench value and the per-level tables only)
+    if world > 1 and ctx.graph_replays() > 0 and os.environ.get("SAENA_BENCH_AB") and not os.environ.get("SAENA_BENCH_NO_AB"):
         # A/B on the same uploaded hierarchy: the same solves with eager launches (not the bench value)
         ctx.set_graphs(False)
         ctx.solve_pcg_dev(rhs_dev.data_ptr(), u_dev.data_ptr(), **OPTS)
@@ -488,15 +561,32 @@ def main():
                 ctx.autotune_halo(10)
 
     # ---- e2e: host buffers through the reference-facing entry point, copies inside the timed region
-    ctx._ck(ctx._L.saena_b200_solve_pcg(ctx._h, rhs_host.data_ptr(), u_host.data_ptr(), OPTS["max_iter"], OPTS["tol"],
-                                        1, OPTS["pre"], OPTS["post"], *_iters_hist_args()))
-    barrier()
-    t = time.perf_counter()
-    for _ in range(args.steps):
-        ctx._ck(ctx._L.saena_b200_solve_pcg(ctx._h, rhs_host.data_ptr(), u_host.data_ptr(), OPTS["max_iter"],
-                                            OPTS["tol"], 1, OPTS["pre"], OPTS["post"], *_iters_hist_args()))
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t) * 1e3 / args.steps)
+    diag_error = None
+    e2e_ms = e2e_pageable_ms = None
+    try:
+        ctx._ck(ctx._L.saena_b200_solve_pcg(ctx._h, rhs_host.data_ptr(), u_host.data_ptr(), OPTS["max_iter"], OPTS["tol"],
+                                            1, OPTS["pre"], OPTS["post"], *_iters_hist_args()))
+        barrier()
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            ctx._ck(ctx._L.saena_b200_solve_pcg(ctx._h, rhs_host.data_ptr(), u_host.data_ptr(), OPTS["max_iter"],
+                                                OPTS["tol"], 1, OPTS["pre"], OPTS["post"], *_iters_hist_args()))
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t) * 1e3 / args.steps)
+        # the same with the caller's PAGEABLE buffers: what the drop-in receives from saena_aligned_alloc'ed vectors
+        # (adaptor/saena_b200_adaptor.cpp:run_solver); not the e2e value, reported beside it
+        rhs_pg, u_pg = np.array(rhs_host.numpy(), copy=True), np.empty(l0.M)
+        barrier()
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            ctx._ck(ctx._L.saena_b200_solve_pcg(ctx._h, rhs_pg.ctypes.data, u_pg.ctypes.data, OPTS["max_iter"],
+                                                OPTS["tol"], 1, OPTS["pre"], OPTS["post"], *_iters_hist_args()))
+        barrier()
+        e2e_pageable_ms = max_over_ranks((time.perf_counter() - t) * 1e3 / args.steps)
+        del rhs_pg, u_pg
+    except native.NativeError as e:
+        diag_error = f"e2e: {e}"
+        log(f"[rank {rank}] {diag_error}")
 
     # ---- check the answer we timed: the recurrence's last <r,r>, and ||rhs - A u|| / ||rhs|| recomputed from the u the
     #      host-buffer solve returned (one more operator application, untimed; collective on several ranks)
@@ -516,26 +606,33 @@ def main():
     # ---- per-level kernel table + roofline of the dominant kernel (CUDA events per launch)
     peak, peak_src = measured_peaks()
     levels_tbl, dominant = [], None
-    for l, lv in enumerate(hier.levels):
-        if lv.A.M == 0:
-            continue
-        a_bytes = ctx.operator_bytes(l, KIND_A)
-        # first Chebyshev sweep: 12 nnz + M*(4 + 8*[u gathered, rhs, inv_diag, d out, u out]) = SpMV + 24 M
-        sweep_bytes = a_bytes + 24 * lv.A.M
-        big = a_bytes > 300e6   # larger than L2: no flush needed; smaller levels are flushed between launches
-        ms_mv = ctx.time_matvec(l, KIND_A, 20, flush_l2=not big)
-        ms_sw = ctx.time_smooth_sweep(l, "chebyshev", 20, flush_l2=not big)
-        ent = {"level": l, "rows": lv.A.M, "nnz": lv.A.nnz, "mapping": ctx.get_mapping(l, KIND_A), "spmv_ms": ms_mv, "spmv_GBs": a_bytes / ms_mv / 1e6,
-               "cheb_sweep_ms": ms_sw, "cheb_sweep_GBs": sweep_bytes / ms_sw / 1e6,
-               "frac_of_peak": sweep_bytes / ms_sw / 1e6 / peak}
-        if lv.P is not None and lv.P.M:
-            ent["P_ms"] = ctx.time_matvec(l, KIND_P, 20, flush_l2=not big)
-            ent["R_ms"] = ctx.time_matvec(l, KIND_R, 20, flush_l2=not big)
-            ent["P_mapping"], ent["R_mapping"] = ctx.get_mapping(l, KIND_P), ctx.get_mapping(l, KIND_R)
-        levels_tbl.append(ent)
-        # share of a V-cycle: 5 fused sweeps + residual ~ 6 passes
-        if dominant is None or ms_sw * 5 > dominant[0]:
-            dominant = (ms_sw * 5, l, sweep_bytes, ms_sw)
+    try:
+        for l, lv in enumerate(hier.levels):
+            if lv.A.M == 0:
+                continue
+            a_bytes = ctx.operator_bytes(l, KIND_A)
+            # first Chebyshev sweep: 12 nnz + M*(4 + 8*[u gathered, rhs, inv_diag, d out, u out]) = SpMV + 24 M
+            sweep_bytes = a_bytes + 24 * lv.A.M
+            big = a_bytes > 300e6   # larger than L2: no flush needed; smaller levels are flushed between launches
+            ms_mv = ctx.time_matvec(l, KIND_A, 20, flush_l2=not big)
+            ms_sw = ctx.time_smooth_sweep(l, "chebyshev", 20, flush_l2=not big)
+            ent = {"level": l, "rows": lv.A.M, "nnz": lv.A.nnz, "mapping": ctx.get_mapping(l, KIND_A), "spmv_ms": ms_mv, "spmv_GBs": a_bytes / ms_mv / 1e6,
+                   "cheb_sweep_ms": ms_sw, "cheb_sweep_GBs": sweep_bytes / ms_sw / 1e6,
+                   "frac_of_peak": sweep_bytes / ms_sw / 1e6 / peak}
+            if lv.P is not None and lv.P.M:
+                ent["P_ms"] = ctx.time_matvec(l, KIND_P, 20, flush_l2=not big)
+                ent["R_ms"] = ctx.time_matvec(l, KIND_R, 20, flush_l2=not big)
+                ent["P_mapping"], ent["R_mapping"] = ctx.get_mapping(l, KIND_P), ctx.get_mapping(l, KIND_R)
+            levels_tbl.append(ent)
+            # share of a V-cycle: 5 fused sweeps + residual ~ 6 passes
+            if dominant is None or ms_sw * 5 > dominant[0]:
+                dominant = (ms_sw * 5, l, sweep_bytes, ms_sw)
+    except native.NativeError as e:
+        diag_error = diag_error or f"per-level table: {e}"
+        log(f"[rank {rank}] per-level table: {e}")
+    have_dominant = dominant is not None
+    if not have_dominant:   # nothing could be timed: the roofline object says so
+        dominant = (0.0, 0, 0, 1.0)
     _, dl, dbytes, dms = dominant
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
@@ -545,6 +642,8 @@ def main():
                 "frac": dbytes / dms / 1e6 / peak, "traffic": traffic,
                 "kernel": f"fused Chebyshev sweep (SpMV + update epilogue) on level {dl}", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dbytes, "launch_ms": dms}
+    if not have_dominant:
+        roofline.update(achieved=None, frac=None, launch_ms=None, kernel="not measured: " + str(diag_error))
 
     # whole-solve algorithmic bytes (SURVEY 8d formulas on the uploaded sizes) -> effective bandwidth
     pre, post = OPTS["pre"], OPTS["post"]
@@ -563,21 +662,25 @@ def main():
     solve_gbs = solve_bytes / ms_step / 1e6
 
     # ---- what each level costs inside a solve: V-cycles entered at level l, consecutive differences
-    vc = [max_over_ranks(ctx.time_vcycle(l, OPTS["smoother"], OPTS["pre"], OPTS["post"], 10))
-          for l in range(len(hier.levels))]
-    vcycle_levels = {"unit": "ms per V-cycle, eager launches, max over ranks",
-                     "entered_at_level": vc,
-                     "level_share": [vc[l] - (vc[l + 1] if l + 1 < len(vc) else 0.0) for l in range(len(vc))]}
-
-    halo = None
-    if world > 1:
-        full_ms, local_ms, halo_ms = ctx.time_matvec_parts(0, KIND_A, 20)
-        full_ms, local_ms, halo_ms = max_over_ranks(full_ms), max_over_ranks(local_ms), max_over_ranks(halo_ms)
-        halo = {"level": 0, "spmv_full_ms": full_ms, "spmv_local_only_ms": local_ms, "pack_exchange_only_ms": halo_ms,
-                "hidden_frac": max(0.0, min(1.0, 1.0 - (full_ms - local_ms) / halo_ms)) if halo_ms > 0 else None,
-                "transport": halo_transport,
-                "ghost_values_per_rank": int(hier.levels[0].A.col_remote_size),
-                "ghost_dtype": "f64" if hier.levels[0].A.use_double else "f32 (float_level 0)"}
+    vcycle_levels, halo = None, None
+    try:
+        if diag_error is None:
+            vc = [max_over_ranks(ctx.time_vcycle(l, OPTS["smoother"], OPTS["pre"], OPTS["post"], 10))
+                  for l in range(len(hier.levels))]
+            vcycle_levels = {"unit": "ms per V-cycle, eager launches, max over ranks",
+                             "entered_at_level": vc,
+                             "level_share": [vc[l] - (vc[l + 1] if l + 1 < len(vc) else 0.0) for l in range(len(vc))]}
+        if world > 1 and diag_error is None:
+            full_ms, local_ms, halo_ms = ctx.time_matvec_parts(0, KIND_A, 20)
+            full_ms, local_ms, halo_ms = max_over_ranks(full_ms), max_over_ranks(local_ms), max_over_ranks(halo_ms)
+            halo = {"level": 0, "spmv_full_ms": full_ms, "spmv_local_only_ms": local_ms, "pack_exchange_only_ms": halo_ms,
+                    "hidden_frac": max(0.0, min(1.0, 1.0 - (full_ms - local_ms) / halo_ms)) if halo_ms > 0 else None,
+                    "transport": halo_transport,
+                    "ghost_values_per_rank": int(hier.levels[0].A.col_remote_size),
+                    "ghost_dtype": "f64" if hier.levels[0].A.use_double else "f32 (float_level 0)"}
+    except native.NativeError as e:
+        diag_error = diag_error or f"per-level V-cycle / halo timing: {e}"
+        log(f"[rank {rank}] per-level V-cycle / halo timing: {e}")
 
     total_unknowns = int(N)
     if args.workload == "poisson3d":
@@ -605,13 +708,20 @@ def main():
             "solve_s": ms_step / 1e3, "iterations": iters, "rel_residual": rel_res, "true_rel_residual": true_rel_res,
             "solve_algorithmic_GB": solve_bytes / 1e9, "solve_effective_GBs": solve_gbs,
             "solve_frac_of_hbm_peak": solve_gbs / peak,
-            "e2e": {"value": total_unknowns / (e2e_ms / 1e3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+            "e2e": {"value": total_unknowns / (e2e_ms / 1e3) / 1e6 if e2e_ms else None, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 8 * total_unknowns, "d2h_bytes_per_step": 8 * total_unknowns,
-                    "timer": "wall clock between device synchronisations (host copies included)"},
+                    "timer": "wall clock between device synchronisations (host copies included)",
+                    "buffers": "pinned host memory",
+                    "pageable_ms_per_step": e2e_pageable_ms,
+                    "pageable_value": total_unknowns / (e2e_pageable_ms / 1e3) / 1e6 if e2e_pageable_ms else None},
             "gpu_launches": int(launches), "vcycle_graph": graph_info, "vcycle_levels": vcycle_levels, "clocks": clk, "roofline": roofline,
             "levels": levels_tbl}
     if halo is not None:
         line["halo_overlap"] = halo
+    line["row_mappings_changed_by_setup_autotune"] = mapping_tuned
+    if world > 1:
+        line["halo_transport"] = halo_transport
+        line["halo_fallback"] = halo_fallback
     if map_tune is not None:
         line["mapping_autotune"] = map_tune
     if os.environ.get("SAENA_BENCH_VERIFY"):
@@ -631,7 +741,8 @@ def main():
         barrier()
         ctx.upload_hierarchy(hier2)
         if halo_transport != "nccl":
-            setup_p2p_halo(ctx)
+            if not setup_p2p_halo(ctx, log):
+                raise SystemExit("bench.py: agglomeration sweep: the peer-memory halo could not be set up again")
             if "per-operator" in halo_transport:
                 ctx.autotune_halo(10)
         for _ in range(3):
@@ -643,11 +754,20 @@ def main():
         ms2 = max_over_ranks(ctx.timer_stop() / args.steps)
         barrier()
         line.setdefault("agglomerate_sweep", []).append({"agglomerate_below": thr, "ms_per_step": ms2, "iterations": it2})
+    if diag_error is not None:
+        # a diagnostic after the timed region failed on this rank: the ranks may no longer be in step, so the line goes
+        # out first and nobody waits for anybody (a clean shutdown would synchronise with a stream that may never drain)
+        line["diagnostics_error"] = diag_error
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()   # nobody unmaps a peer's arena while that peer may still write into it
     ctx.close()
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -158,18 +158,36 @@ int saena_b200_finalize(saena_b200_ctx *ctx);
  * After finalize every rank exports a small blob (IPC handle of its halo arena + where each
  * sender's values land), the host all-gathers the blobs over whatever channel it has
  * (MPI_Allgather in the adaptor, torch.distributed in bench.py) and every rank imports the
- * concatenation (rank order, `blob_bytes` each).  From then on the ghost values of the distributed
+ * concatenation (rank order, `blob_bytes` each); no rank applies an operator before all have
+ * returned from the import (barrier).  From then on the ghost values of the distributed
  * SpMV are stored by the sender straight into the receiver's memory over NVLink, and the whole
  * distributed operator application -- pack + peer stores, interior rows, rows that wait for the
  * ghost values, fused epilogue -- is ONE kernel (csrc/fused_halo.cu; what matvec_sparse,
  * src/saena_matrix_matvec.cpp:9-113, does with MPI_Isend/Irecv/Waitany around two loops).
  * saena_b200_p2p_enable selects the transport: 2 = that fused kernel (default after the import),
- * 1 = peer stores with separate launches (pack kernel, stream memory-op flags, boundary kernel),
- * 0 = ncclSend/ncclRecv (what runs without the import).  Collective: every rank passes the same
- * value.  p2p_export with buf == NULL only reports the size. */
+ * 1 = peer stores with separate launches (pack kernel on a comm stream, interior kernel, wait
+ * kernel, boundary kernel, release kernel), 0 = ncclSend/ncclRecv (what runs without the import).
+ * 1 and 2 are two forms of ONE hand-shake (csrc/halo_sync.cuh: monotonic counters, two landing
+ * buffers per operator), so they may be mixed freely per operator, per rank and per application;
+ * only the switch between 0 and non-zero is collective.  p2p_export with buf == NULL only reports
+ * the size.
+ *
+ * Failure detection.  Every device-side wait of the exchange is bounded (SAENA_B200_HALO_TIMEOUT_MS,
+ * default 5000): a wait that runs out records what it was waiting for, every later wait of the
+ * context drains at once, and the ABI call in which it happened returns non-zero with the operator,
+ * counter and values in saena_b200_last_error -- each rank on its own clock, never a hang.  Every
+ * blocking host wait is bounded too (SAENA_B200_SYNC_TIMEOUT_S, default 180: a peer process that
+ * died inside a collective).  The reference's convention for a failed rank is print + MPI_Abort
+ * (src/saena_object_solve.cpp:1012-1013); the adaptor maps the status to that.  After a timed-out
+ * exchange the counters of the ranks are out of step: saena_b200_clear_fault (every rank) followed
+ * by saena_b200_p2p_enable(ctx, 0) continues over NCCL, a new export/import re-arms peer memory. */
 int saena_b200_p2p_export(saena_b200_ctx *ctx, void *buf, int64_t cap, int64_t *size_out);
 int saena_b200_p2p_import(saena_b200_ctx *ctx, const void *blobs, int64_t blob_bytes);
 int saena_b200_p2p_enable(saena_b200_ctx *ctx, int on);
+int saena_b200_fault_status(saena_b200_ctx *ctx);  /* 0: no wait of this context has timed out */
+int saena_b200_clear_fault(saena_b200_ctx *ctx);
+/* deadlines: device-side halo waits in ms (< 0: unchanged), blocking host waits in s (<= 0: unbounded) */
+int saena_b200_set_timeouts(saena_b200_ctx *ctx, double halo_timeout_ms, double sync_timeout_s);
 /* Measures both peer-memory paths on every operator of the uploaded hierarchy (reps back-to-back
  * applications each, times summed over the ranks) and keeps the faster one per operator.
  * Collective; call after p2p_import.  saena_b200_halo_choice reports the outcome for one operator
@@ -200,6 +218,11 @@ int saena_b200_solve_vcycle(saena_b200_ctx *ctx, const double *rhs, double *u, i
                             int *hist_len);                                   /* saena_object::solve */
 int saena_b200_solve_cg(saena_b200_ctx *ctx, const double *rhs, double *u, int max_iter, double tol, int *iters,
                         double *hist, int hist_cap, int *hist_len);           /* saena_object::solve_CG */
+/* saena_object::solve_smoother (src/saena_object_solve.cpp:2017-2117): `pre` smoother sweeps per iteration on
+ * level 0, nothing else; `post` is unused, as in the reference */
+int saena_b200_solve_smoother(saena_b200_ctx *ctx, const double *rhs, double *u, int max_iter, double tol,
+                              int smoother, int pre, int post, int *iters, double *hist, int hist_cap,
+                              int *hist_len);
 
 /* Same solve with rhs / u already resident in device memory (no host copies). */
 int saena_b200_solve_pcg_dev(saena_b200_ctx *ctx, const double *rhs_dev, double *u_dev, int max_iter, double tol,
@@ -256,6 +279,12 @@ int saena_b200_set_mapping_deferred(saena_b200_ctx *ctx, int level, int kind, in
  * stable; -1 where the last window runs past M) and slice_ptr[ceil(M / 256) * 8 + 1], the element offset of every
  * 32-slot slice (32 x its longest row). */
 int saena_b200_sellp_layout(int M, const int64_t *rowptr, int32_t *perm, long long *slice_ptr);
+/* Setup-time choice of every operator's row mapping by measurement: starting from the nnz/row rule, times the
+ * neighbouring mappings (1/8 .. 8x the threads per row; the sorted sliced layout where it applies) with `reps`
+ * applications each and keeps the fastest where it wins by more than min_gain (e.g. 0.03).  Collective on several
+ * ranks (same candidates everywhere, decision on the slowest rank's time, one mapping per operator on all ranks);
+ * call after finalize -- and after p2p_import, so that the exchange timed is the one the solve will use. */
+int saena_b200_autotune_mapping(saena_b200_ctx *ctx, int reps, double min_gain, int *changed_out);
 /* the mapping in use (same codes) */
 int saena_b200_get_mapping(const saena_b200_ctx *ctx, int level, int kind);
 /* algorithmic bytes of one application of an operator (SURVEY.md 8d formula), for the roofline */

@@ -159,8 +159,11 @@ int saena_b200_solve_pcg(saena_b200_ctx *ctx, const double *, double *u, int, do
                          int hist_cap, int *hist_len) { return fake_solve(ctx, u, iters, hist, hist_cap, hist_len); }
 int saena_b200_solve_vcycle(saena_b200_ctx *ctx, const double *, double *u, int, double, int, int, int, int *iters,
                             double *hist, int hist_cap, int *hist_len) { return fake_solve(ctx, u, iters, hist, hist_cap, hist_len); }
+int saena_b200_solve_smoother(saena_b200_ctx *ctx, const double *, double *u, int, double, int, int, int, int *iters,
+                            double *hist, int hist_cap, int *hist_len) { return fake_solve(ctx, u, iters, hist, hist_cap, hist_len); }
 int saena_b200_solve_cg(saena_b200_ctx *ctx, const double *, double *u, int, double, int *iters, double *hist, int hist_cap,
                         int *hist_len) { return fake_solve(ctx, u, iters, hist, hist_cap, hist_len); }
+int saena_b200_autotune_mapping(saena_b200_ctx *, int, double, int *changed) { if (changed) *changed = 0; return 0; }
 int saena_b200_matvec(saena_b200_ctx *ctx, int, int, const double *, double *w) {
     const int n = ctx->levels.empty() ? 0 : ctx->levels[0].op[0].d.M;
     for (int i = 0; i < n; ++i) w[i] = 0.0;

@@ -303,3 +303,7 @@ class Oracle:
 
     def solve_vcycle(self, rhs, max_iter=50, tol=1e-8, smoother="chebyshev", pre=3, post=3):
         return self._solve(lib().so_solve_vcycle, rhs, max_iter, tol, smoother, pre, post)
+
+    def solve_smoother(self, rhs, max_iter=50, tol=1e-8, smoother="chebyshev", pre=3, post=3):
+        """saena_object::solve_smoother: `pre` sweeps of the smoother per iteration, nothing else"""
+        return self._solve(lib().so_solve_smoother, rhs, max_iter, tol, smoother, pre, post)

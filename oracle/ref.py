@@ -375,6 +375,25 @@ class RefSolver:
         # reference reports i+1 (saena_object_solve.cpp:2678-2682)
         return u, len(hist) - 1, hist
 
+    def _solve_stationary(self, which, max_iter, tol, smoother, pre, post):
+        u = np.zeros(self._info(0, KIND_A).M, F64)
+        hist = np.zeros(max_iter + 2, F64)
+        n = ctypes.c_int(0)
+        f = lib().sref_solve_stationary
+        f.restype = ctypes.c_int
+        f(self._h, int(which), int(max_iter), ctypes.c_double(tol), int(smoother == "chebyshev"), int(pre), int(post),
+          _p(u), _p(hist), len(hist), ctypes.byref(n))
+        hist = hist[:n.value]
+        return u, len(hist) - 1, hist
+
+    def solve_vcycle(self, max_iter=50, tol=1e-8, smoother="chebyshev", pre=3, post=3):
+        """saena_object::solve on the compiled reference -> (u, reported iterations, history)"""
+        return self._solve_stationary(1, max_iter, tol, smoother, pre, post)
+
+    def solve_smoother(self, max_iter=50, tol=1e-8, smoother="chebyshev", pre=3, post=3):
+        """saena_object::solve_smoother on the compiled reference"""
+        return self._solve_stationary(2, max_iter, tol, smoother, pre, post)
+
     def time_solve_pcg(self, reps: int) -> float:
         return float(lib().sref_time_solve_pcg(self._h, int(reps)))
 

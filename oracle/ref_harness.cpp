@@ -513,6 +513,33 @@ int sref_solve_pcg(void *hv, int max_iter, double tol, int smoother, int pre, in
     return n - 1;  // one <r,r> before the loop, one per executed iteration
 }
 
+// saena_object::solve (which = 1: stationary V-cycles, src/saena_object_solve.cpp:1883-2014) and
+// saena_object::solve_smoother (which = 2: the smoother alone, :2017-2117), called on the saena_object itself -- the
+// public forwarders (src/saena.cpp:751-768) only add return_vec, a permutation back to the caller's rhs ordering.
+// Same outputs as sref_solve_pcg: u in the matrix's row partition, history of sqrt(<r,r>), iteration count.
+int sref_solve_stationary(void *hv, int which, int max_iter, double tol, int smoother, int pre, int post, double *u_out,
+                          double *hist, int hist_cap, int *hist_len) {
+    Handle *h = (Handle *)hv;
+    if (h->vcycle_mem) { obj(h)->free_vcycle_memory(); h->vcycle_mem = false; }
+    obj(h)->set_solve_params(max_iter, tol, smoother ? "chebyshev" : "jacobi", pre, post);
+    g_rr.clear();
+    g_rr_len = obj(h)->grids[0].A->M;
+    value_t *u = nullptr;
+    {
+        QuietStdout q(true);
+        if (which == 1) obj(h)->solve(u);   // both allocate u when it is null and start from zero (:1920-1924, :2047-2051)
+        else obj(h)->solve_smoother(u);
+    }
+    g_rr_len = -1;
+    const int M = obj(h)->grids[0].A->M;
+    if (u_out) memcpy(u_out, u, sizeof(double) * (size_t)M);
+    saena_free(u);
+    int n = (int)g_rr.size();
+    *hist_len = n;
+    for (int i = 0; i < n && i < hist_cap; ++i) hist[i] = sqrt(g_rr[i]);
+    return n - 1;
+}
+
 // Wall-clock seconds of `reps` reference solve_pCG calls (cpu_baseline).
 double sref_time_solve_pcg(void *hv, int reps) {
     Handle *h = (Handle *)hv;

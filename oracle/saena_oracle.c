@@ -532,3 +532,47 @@ int so_solve_vcycle(const so_hierarchy *h, const double *const *rhs, double *con
     free(r); free(M); free(A);
     return i + 1;
 }
+
+/* src/saena_object_solve.cpp:2017-2117 -- saena_object::solve_smoother: the smoother alone as a stationary iteration,
+ * `pre` sweeps per iteration (:2074), residual and <r,r> after each (:2075-2076), same stop rule (:2080) */
+int so_solve_smoother(const so_hierarchy *h, const double *const *rhs, double *const *u, int max_iter, double tol,
+                      int smoother, int pre, int post, double *hist, int hist_cap, int *hist_len) {
+    (void)post;
+    const int n = h->nranks;
+    const so_operator **A = (const so_operator **)calloc((size_t)n, sizeof(void *));
+    const so_level **lv = (const so_level **)calloc((size_t)n, sizeof(void *));
+    int *M = (int *)calloc((size_t)n, sizeof(int));
+    double **r = (double **)calloc((size_t)n, sizeof(double *));
+    for (int k = 0; k < n; ++k) {
+        lv[k] = &h->level[k];
+        A[k] = &h->level[k].A;
+        M[k] = A[k]->M;
+        r[k] = dalloc(M[k]);
+        for (int i = 0; i < M[k]; ++i) u[k][i] = 0.0;                                        /* :2051 */
+    }
+    int nh = 0;
+    so_residual(A, n, (const double *const *)u, rhs, r);                                    /* :2061 */
+    const double init_dot = so_dot(n, M, (const double *const *)r, (const double *const *)r);
+    double current_dot = init_dot;
+    if (nh < hist_cap) hist[nh] = sqrt(init_dot);
+    ++nh;
+    const double THRSHLD = init_dot * tol * tol;                                            /* :2069 */
+    int i = 0;
+    for (; i < max_iter; ++i) {
+        if (smoother) so_chebyshev(lv, n, pre, u, rhs);                                     /* :2074, saena_object.tpp:85-96 */
+        else so_jacobi(lv, n, pre, u, rhs);
+        so_residual(A, n, (const double *const *)u, rhs, r);
+        current_dot = so_dot(n, M, (const double *const *)r, (const double *const *)r);
+        if (nh < hist_cap) hist[nh] = sqrt(current_dot);
+        ++nh;
+        if (current_dot < THRSHLD) break;                                                   /* :2080 */
+    }
+    if (i == max_iter) --i;                                                                 /* :2086-2087 */
+    if (h->scale)                                                                           /* :2100-2102 */
+        for (int k = 0; k < n; ++k)
+            for (int j = 0; j < M[k]; ++j) u[k][j] *= h->level[k].inv_sq_diag[j];
+    *hist_len = nh;
+    for (int k = 0; k < n; ++k) free(r[k]);
+    free(r); free(M); free(A); free(lv);
+    return i + 1;
+}

@@ -118,6 +118,10 @@ int so_solve_pcg(const so_hierarchy *h, const double *const *rhs, double *const 
 int so_solve_vcycle(const so_hierarchy *h, const double *const *rhs, double *const *u, int max_iter, double tol,
                     int smoother, int pre, int post, double *hist, int hist_cap, int *hist_len);
 
+/* saena_object_solve.cpp:2017-2117: the smoother alone as a stationary iteration (`pre` sweeps per iteration; post unused) */
+int so_solve_smoother(const so_hierarchy *h, const double *const *rhs, double *const *u, int max_iter, double tol,
+                      int smoother, int pre, int post, double *hist, int hist_cap, int *hist_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -308,8 +308,14 @@ DeviceSide &device_side(saena_object *obj) {
         MPI_Allgather(mine.data(), (int)n, MPI_BYTE, all.data(), (int)n, MPI_BYTE, A0->comm);
         CK(ds.ctx, saena_b200_p2p_import(ds.ctx, all.data(), n), "p2p import");
         MPI_Barrier(A0->comm);
-        // per operator: the fused halo kernel or the separate launches, whichever measures faster here
-        CK(ds.ctx, saena_b200_autotune_halo(ds.ctx, 10), "halo autotune");
+    }
+    if (!std::getenv("SAENA_B200_NO_AUTOTUNE")) {
+        // setup-time choices by measurement (collective, untimed by the drivers: experiments/Poisson.cpp:191-214 times
+        // the solves only): every operator's row mapping, then -- several ranks -- per operator the fused halo kernel
+        // or the separate launches, whichever is faster here
+        CK(ds.ctx, saena_b200_autotune_mapping(ds.ctx, 10, 0.03, nullptr), "mapping autotune");
+        if (ds.nprocs > 1 && !std::getenv("SAENA_B200_HALO_NCCL"))
+            CK(ds.ctx, saena_b200_autotune_halo(ds.ctx, 10), "halo autotune");
     }
     if (g_verbose && ds.rank == 0) std::printf("saena_b200: hierarchy of %d levels uploaded\n", L + 1);
     return g_solvers[obj] = ds;
@@ -322,7 +328,7 @@ int smoother_id(const std::string &s) {
     std::exit(EXIT_FAILURE);
 }
 
-enum Which { PCG, VCYCLE, CG };
+enum Which { PCG, VCYCLE, CG, SMOOTHER };
 
 int run_solver(saena_object *obj, Which which, value_t *&u, saena::options *opts, bool print_info) {
     obj->set_solve_params(opts->get_max_iter(), opts->get_tol(), opts->get_smoother(), opts->get_preSmooth(),
@@ -347,6 +353,9 @@ int run_solver(saena_object *obj, Which which, value_t *&u, saena::options *opts
     else if (which == VCYCLE)
         rc = saena_b200_solve_vcycle(ds.ctx, obj->grids[0].rhs, u, obj->solver_max_iter, obj->solver_tol, sm,
                                      obj->preSmooth, obj->postSmooth, &iters, g_last_history.data(), cap, &nh);
+    else if (which == SMOOTHER)
+        rc = saena_b200_solve_smoother(ds.ctx, obj->grids[0].rhs, u, obj->solver_max_iter, obj->solver_tol, sm,
+                                       obj->preSmooth, obj->postSmooth, &iters, g_last_history.data(), cap, &nh);
     else
         rc = saena_b200_solve_cg(ds.ctx, obj->grids[0].rhs, u, obj->solver_max_iter, obj->solver_tol, &iters,
                                  g_last_history.data(), cap, &nh);
@@ -386,12 +395,10 @@ int saena::amg::solve_CG(value_t *&u, saena::options *opts) {
 }
 
 int saena::amg::solve_smoother(value_t *&u, saena::options *opts) {
-    // saena_object::solve_smoother is a driver around the smoother alone and is not on the
-    // BASELINE hot path; it keeps running the reference's host code.
-    m_pImpl->set_solve_params(opts->get_max_iter(), opts->get_tol(), opts->get_smoother(), opts->get_preSmooth(),
-                              opts->get_postSmooth());
-    m_pImpl->solve_smoother(u);
-    m_pImpl->grids[0].rhs_orig->return_vec(u);
+    // src/saena.cpp:751-758 -> saena_object::solve_smoother (src/saena_object_solve.cpp:2017-2117): the smoother
+    // alone as a stationary iteration, on the device like the other solvers
+    run_solver(m_pImpl, SMOOTHER, u, opts, true);
+    m_pImpl->grids[0].rhs_orig->return_vec(u);  // host post-step kept (saena.cpp:755-756)
     return 0;
 }
 

@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include <stdlib.h>
+#include <time.h>
 
 #include "common.h"
 
@@ -28,8 +29,12 @@ static int init_body(saena_b200_ctx *ctx, const void *nccl_id) {
     cudaDeviceProp prop;
     SB_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->sm_count = prop.multiProcessorCount;
-    SB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    SB_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    // the comm stream carries the pack kernels of the separate-launch halo: highest priority, so that its few CTAs are
+    // placed as soon as an SM has room while the interior-row kernel of the same application fills the chip
+    int prio_lo = 0, prio_hi = 0;
+    SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    SB_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo));
+    SB_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi));
     SB_CUDA(cudaEventCreateWithFlags(&ctx->ev_packed, cudaEventDisableTiming));
     SB_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
     SB_CUDA(cudaEventCreate(&ctx->ev_t0));
@@ -37,9 +42,13 @@ static int init_body(saena_b200_ctx *ctx, const void *nccl_id) {
     SB_CUDA(cudaMalloc((void **)&ctx->red_partials, sizeof(double) * RED_MAX_BLOCKS * 4));
     SB_CUDA(cudaMalloc((void **)&ctx->red_counter, sizeof(unsigned int)));
     SB_CUDA(cudaMemset(ctx->red_counter, 0, sizeof(unsigned int)));
-    SB_CUDA(cudaMalloc((void **)&ctx->scalars, sizeof(double) * S_COUNT));
-    SB_CUDA(cudaMemset(ctx->scalars, 0, sizeof(double) * S_COUNT));
-    SB_CUDA(cudaMallocHost((void **)&ctx->scalars_host, sizeof(double) * S_COUNT));
+    // Krylov scalars followed by the halo fault record: one device-to-host copy per iteration brings both
+    static_assert(sizeof(double) == sizeof(unsigned long long), "fault words share the scalar buffer");
+    SB_CUDA(cudaMalloc((void **)&ctx->scalars, sizeof(double) * (S_COUNT + S_FAULT_WORDS)));
+    SB_CUDA(cudaMemset(ctx->scalars, 0, sizeof(double) * (S_COUNT + S_FAULT_WORDS)));
+    SB_CUDA(cudaMallocHost((void **)&ctx->scalars_host, sizeof(double) * (S_COUNT + S_FAULT_WORDS)));
+    memset(ctx->scalars_host, 0, sizeof(double) * (S_COUNT + S_FAULT_WORDS));
+    ctx->fault_dev = (unsigned long long *)(ctx->scalars + S_COUNT);
     if (!ctx->detached) SB_TRY(sb_nccl_init(ctx, nccl_id));
     return 0;
 }
@@ -73,6 +82,8 @@ static int init_common(saena_b200_ctx **ctx_out, int device_id, int rank, int nr
     if (const char *gm = getenv("SAENA_B200_GRAPH_MULTI")) ctx->use_graphs_multi = atoi(gm) != 0;
     if (const char *hf = getenv("SAENA_B200_HALO_FUSED")) ctx->fused_default = atoi(hf) != 0;
     if (const char *nv = getenv("SAENA_B200_NVTX")) ctx->nvtx = atoi(nv) != 0;
+    if (const char *t = getenv("SAENA_B200_HALO_TIMEOUT_MS")) ctx->halo_timeout_ns = (unsigned long long)(atof(t) * 1e6);
+    if (const char *t = getenv("SAENA_B200_SYNC_TIMEOUT_S")) ctx->sync_timeout_s = atof(t);
     if (init_body(ctx, nccl_id)) {
         g_sb_init_error = ctx->error;
         delete ctx;
@@ -91,8 +102,8 @@ static void free_level_work(DevLevel &lv, bool owns_rhs) {
 int saena_b200_destroy(saena_b200_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->comm_stream);
+    sb_sync_stream(ctx, ctx->stream);
+    sb_sync_stream(ctx, ctx->comm_stream);
     sb_invalidate_graphs(ctx);
     sb_arena_free(ctx);
     for (size_t l = 0; l < ctx->levels.size(); ++l) {
@@ -109,6 +120,7 @@ int saena_b200_destroy(saena_b200_ctx *ctx) {
     cudaFree(ctx->pcg_r); cudaFree(ctx->pcg_p); cudaFree(ctx->pcg_h); cudaFree(ctx->pcg_u); cudaFree(ctx->pcg_rhs);
     for (int i = 0; i < 4; ++i) cudaFree(ctx->stage[i]);
     cudaFree(ctx->flush_buf);
+    cudaFree(ctx->tune_dev);
     sb_nccl_destroy(ctx);
     cudaEventDestroy(ctx->ev_packed); cudaEventDestroy(ctx->ev_halo);
     cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
@@ -179,11 +191,15 @@ int saena_b200_upload_coarsest(saena_b200_ctx *ctx, int n, int64_t nnz, const in
                                const double *val) {
     if (!ctx) return 1;
     SB_CUDA(cudaSetDevice(ctx->device));
+    sb_invalidate_graphs(ctx);  // a captured V-cycle's coarsest_kernel node points at the buffers released below
+    ctx->finalized = false;
     cudaFree(ctx->coarse_A); cudaFree(ctx->coarse_Ainv); cudaFree(ctx->coarse_tmp);
     ctx->coarse_A = ctx->coarse_Ainv = ctx->coarse_tmp = nullptr;
-    ctx->coarse_n = n;
+    ctx->coarse_n = 0;
     if (n == 0) return 0;
+    // coarsest_kernel keeps one n-vector in dynamic shared memory: 4096 doubles = 32 KB, inside the 48 KB default
     if (n < 0 || n > 4096) SB_FAIL("upload_coarsest: coarsest level must have 1..4096 rows");
+    ctx->coarse_n = n;
     std::vector<double> A((size_t)n * n, 0.0);
     for (int64_t k = 0; k < nnz; ++k) {
         if (row[k] < 0 || row[k] >= n || col[k] < 0 || col[k] >= n) SB_FAIL("upload_coarsest: index out of range");
@@ -289,10 +305,125 @@ int saena_b200_finalize(saena_b200_ctx *ctx) {
     return 0;
 }
 
+}  // extern "C"
+
+// cudaStreamSynchronize with a watchdog: the host polls the stream and gives up after sync_timeout_s -- a peer process
+// that died inside a collective, or any other stall the device-side deadlines do not cover, becomes an error status
+// instead of a process that never returns (the reference: print + MPI_Abort, src/saena_object_solve.cpp:1012-1013).
+int sb_sync_stream(saena_b200_ctx *ctx, cudaStream_t s) {
+    if (ctx->nranks == 1 || ctx->sync_timeout_s <= 0.0) {
+        SB_CUDA(cudaStreamSynchronize(s));
+        return 0;
+    }
+    struct timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (unsigned int n = 0;; ++n) {
+        const cudaError_t q = cudaStreamQuery(s);
+        if (q == cudaSuccess) return 0;
+        if (q != cudaErrorNotReady) {
+            ctx->error = std::string("cudaStreamQuery: ") + cudaGetErrorString(q);
+            return 1;
+        }
+        if ((n & 1023u) == 1023u) {
+            struct timespec t1;
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            const double el = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+            if (el > ctx->sync_timeout_s) {
+                ctx->faulted = true;
+                ctx->error = "rank " + std::to_string(ctx->rank) + ": the device did not finish within " +
+                             std::to_string((int)ctx->sync_timeout_s) +
+                             " s (a peer that left a collective? SAENA_B200_SYNC_TIMEOUT_S); the context is unusable";
+                return 1;
+            }
+        }
+    }
+}
+
+// The fault words arrive with every sb_read_scalars; entry points that do not read scalars fetch them here.
+int sb_check_fault(saena_b200_ctx *ctx) {
+    if (ctx->nranks == 1) return 0;
+    const unsigned long long *f = (const unsigned long long *)(ctx->scalars_host + S_COUNT);
+    if (!ctx->faulted && f[0] == 0ull) {
+        SB_CUDA(cudaMemcpyAsync(ctx->scalars_host + S_COUNT, ctx->scalars + S_COUNT, sizeof(double) * S_FAULT_WORDS,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+        SB_TRY(sb_sync_stream(ctx, ctx->stream));
+    }
+    if (f[0] != 0ull) {
+        const int what = (int)(f[0] & 0xffull), op_id = (int)((f[0] >> 8) & 0xffffffull), slot = (int)(f[0] >> 32);
+        ctx->faulted = true;
+        ctx->error = "rank " + std::to_string(ctx->rank) + ": halo exchange timed out after " +
+                     std::to_string(ctx->halo_timeout_ns / 1000000ull) + " ms on level " + std::to_string(op_id / 3) +
+                     " operator " + "APR"[op_id % 3] + ": waited for the '" +
+                     (what == 1 ? "consumed" : "arrived") + "' counter of neighbour slot " + std::to_string(slot) +
+                     " to reach " + std::to_string(f[1]) + ", saw " + std::to_string(f[2]) +
+                     " (SAENA_B200_HALO_TIMEOUT_MS; results of this call are invalid)";
+        return 1;
+    }
+    if (ctx->faulted) {
+        if (ctx->error.empty()) ctx->error = "an earlier call of this context timed out (saena_b200_clear_fault)";
+        return 1;
+    }
+    return 0;
+}
+
+static __global__ void fault_flag_kernel(const unsigned long long *fault, double *out) { *out = fault[0] != 0ull ? 1.0 : 0.0; }
+
+int sb_agree_fault(saena_b200_ctx *ctx) {
+    if (ctx->nranks == 1 || ctx->detached) return 0;
+    fault_flag_kernel<<<1, 1, 0, ctx->stream>>>(ctx->fault_dev, ctx->scalars + S_AGREE);
+    SB_CUDA(cudaGetLastError());
+    SB_TRY(sb_allreduce_sum(ctx, ctx->scalars + S_AGREE, 1, ctx->stream));
+    SB_TRY(sb_read_scalars(ctx));
+    SB_TRY(sb_check_fault(ctx));
+    if (ctx->scalars_host[S_AGREE] > 0.0) {
+        ctx->faulted = true;
+        ctx->error = "rank " + std::to_string(ctx->rank) + ": the halo exchange of " +
+                     std::to_string((int)ctx->scalars_host[S_AGREE]) +
+                     " peer rank(s) timed out during this call (results are invalid on every rank)";
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" {
+
+// After a timed-out exchange every rank's counters are out of step: the peer-memory transport stays off until the
+// next saena_b200_p2p_import.  Clears the fault so that the context can go on over NCCL (collective by contract: all
+// ranks call it, then saena_b200_p2p_enable(ctx, 0)).
+int saena_b200_clear_fault(saena_b200_ctx *ctx) {
+    if (!ctx) return 1;
+    SB_CUDA(cudaSetDevice(ctx->device));
+    SB_TRY(sb_sync_stream(ctx, ctx->stream));
+    SB_TRY(sb_sync_stream(ctx, ctx->comm_stream));
+    SB_CUDA(cudaMemset(ctx->fault_dev, 0, sizeof(unsigned long long) * S_FAULT_WORDS));
+    memset(ctx->scalars_host + S_COUNT, 0, sizeof(double) * S_FAULT_WORDS);
+    ctx->faulted = false;
+    ctx->error.clear();
+    sb_invalidate_graphs(ctx);
+    return 0;
+}
+
+// halo_timeout_ms: deadline of every device-side wait of the exchange; sync_timeout_s: watchdog of the blocking host
+// waits (<= 0: none).  Negative halo_timeout_ms leaves that value as it is.
+int saena_b200_set_timeouts(saena_b200_ctx *ctx, double halo_timeout_ms, double sync_timeout_s) {
+    if (!ctx) return 1;
+    if (halo_timeout_ms >= 0.0) ctx->halo_timeout_ns = (unsigned long long)(halo_timeout_ms * 1e6);
+    ctx->sync_timeout_s = sync_timeout_s;
+    sb_invalidate_graphs(ctx);   // captured kernel nodes carry the old deadline in their arguments
+    return 0;
+}
+
+int saena_b200_fault_status(saena_b200_ctx *ctx) {
+    if (!ctx) return 1;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return 1;
+    return sb_check_fault(ctx);
+}
+
 #define SB_ENTER()                                                        \
     if (!ctx) return 1;                                                   \
     SB_CUDA(cudaSetDevice(ctx->device));                                  \
-    if (!ctx->finalized) SB_FAIL("call saena_b200_finalize first")
+    if (!ctx->finalized) SB_FAIL("call saena_b200_finalize first");       \
+    if (ctx->faulted) return sb_check_fault(ctx)
 
 static int stage_buf(saena_b200_ctx *ctx, int i, size_t n) {
     if (ctx->stage_cap[i] < n) {
@@ -310,8 +441,8 @@ static int h2d(saena_b200_ctx *ctx, double *dst, const double *src, size_t n) {
 }
 static int d2h(saena_b200_ctx *ctx, double *dst, const double *src, size_t n) {
     if (n) SB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SB_CUDA(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    SB_TRY(sb_sync_stream(ctx, ctx->stream));
+    return sb_check_fault(ctx);   // every host-buffer entry point ends here: a timed-out exchange is an error status
 }
 
 static DevOperator *get_op(saena_b200_ctx *ctx, int level, int kind) {
@@ -396,8 +527,8 @@ int saena_b200_solve_pcg_dev(saena_b200_ctx *ctx, const double *rhs_dev, double 
                              int *hist_len) {
     SB_ENTER();
     SB_TRY(pcg_device(ctx, rhs_dev, u_dev, max_iter, tol, smoother, pre, post, iters, hist, hist_cap, hist_len));
-    SB_CUDA(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    SB_TRY(sb_sync_stream(ctx, ctx->stream));
+    return sb_agree_fault(ctx);
 }
 
 int saena_b200_solve_pcg(saena_b200_ctx *ctx, const double *rhs, double *u, int max_iter, double tol, int smoother,
@@ -407,6 +538,7 @@ int saena_b200_solve_pcg(saena_b200_ctx *ctx, const double *rhs, double *u, int 
     SB_TRY(h2d(ctx, ctx->pcg_rhs, rhs, n));
     SB_TRY(pcg_device(ctx, ctx->pcg_rhs, ctx->pcg_u, max_iter, tol, smoother, pre, post, iters, hist, hist_cap,
                       hist_len));
+    SB_TRY(sb_agree_fault(ctx));
     SB_TRY(d2h(ctx, u, ctx->pcg_u, n));
     return 0;
 }
@@ -445,6 +577,50 @@ int saena_b200_solve_vcycle(saena_b200_ctx *ctx, const double *rhs, double *u, i
     if (ctx->scale) SB_TRY(sb_scale_vector(ctx, n, l0.u[l0.cur], l0.inv_sq_diag));  // :2000-2002
     *iters = i + 1;
     *hist_len = nh;
+    SB_TRY(sb_agree_fault(ctx));
+    SB_TRY(d2h(ctx, u, l0.u[l0.cur], n));
+    return 0;
+}
+
+// saena_object::solve_smoother (src/saena_object_solve.cpp:2017-2117; reached from saena::amg::solve_smoother,
+// src/saena.cpp:751-758): the smoother alone as a stationary iteration -- `pre` sweeps (:2074), residual and <r,r>
+// (:2075-2076), the solvers' stop rule (:2080) -- on level 0.  Every sweep is the fused one-pass kernel of the V-cycle.
+int saena_b200_solve_smoother(saena_b200_ctx *ctx, const double *rhs, double *u, int max_iter, double tol,
+                              int smoother, int pre, int post, int *iters, double *hist, int hist_cap,
+                              int *hist_len) {
+    SB_ENTER();
+    (void)post;
+    DevLevel &l0 = ctx->levels[0];
+    const int n = l0.M;
+    double *r = ctx->pcg_r;
+    int nh = 0;
+    SB_TRY(h2d(ctx, ctx->pcg_rhs, rhs, n));
+    const double *b = ctx->pcg_rhs;
+    l0.cur = 0;
+    SB_TRY(sb_fill_zero(ctx, l0.u[0], n));      // :2051
+    SB_TRY(sb_negate_copy(ctx, n, b, r));       // :2061 with u = 0
+    SB_TRY(sb_dot(ctx, r, r, n, S_RR));
+    SB_TRY(sb_read_scalars(ctx));
+    const double init_dot = ctx->scalars_host[S_RR];
+    push_hist(init_dot, hist, hist_cap, nh);
+    const double THRSHLD = init_dot * tol * tol;  // :2069
+    int i = 0;
+    for (; i < max_iter; ++i) {
+        SB_TRY(sb_smooth(ctx, 0, smoother, pre, b, i == 0));  // the first sweep starts from the zero iterate
+        EpiArgs e{};
+        e.rhs = b;
+        e.out = r;
+        SB_TRY(sb_apply(ctx, l0.A, l0.u[l0.cur], EPI_RESIDUAL, e));
+        SB_TRY(sb_dot(ctx, r, r, n, S_RR));
+        SB_TRY(sb_read_scalars(ctx));
+        push_hist(ctx->scalars_host[S_RR], hist, hist_cap, nh);
+        if (!(ctx->scalars_host[S_RR] >= THRSHLD)) break;     // :2080
+    }
+    if (i == max_iter) --i;                                   // :2086-2087
+    if (ctx->scale) SB_TRY(sb_scale_vector(ctx, n, l0.u[l0.cur], l0.inv_sq_diag));  // :2100-2102
+    *iters = i + 1;
+    *hist_len = nh;
+    SB_TRY(sb_agree_fault(ctx));
     SB_TRY(d2h(ctx, u, l0.u[l0.cur], n));
     return 0;
 }
@@ -484,6 +660,7 @@ int saena_b200_solve_cg(saena_b200_ctx *ctx, const double *rhs, double *u, int m
     if (i == max_iter) --i;
     *iters = i + 1;
     *hist_len = nh;
+    SB_TRY(sb_agree_fault(ctx));
     SB_TRY(d2h(ctx, u, x, n));
     return 0;
 }
@@ -567,7 +744,7 @@ int saena_b200_dot(saena_b200_ctx *ctx, const double *a, const double *b, int n,
     SB_TRY(sb_dot(ctx, ctx->stage[0], ctx->stage[1], n, S_TMP));
     SB_TRY(sb_read_scalars(ctx));
     *out = ctx->scalars_host[S_TMP];
-    return 0;
+    return sb_check_fault(ctx);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -606,31 +783,37 @@ int saena_b200_time_matvec(saena_b200_ctx *ctx, int level, int kind, int reps, i
         SB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
         SB_TRY(sb_apply(ctx, *op, ctx->stage[0], EPI_PLAIN, e));
         SB_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
-        SB_CUDA(cudaEventSynchronize(ctx->ev_t1));
+        SB_TRY(sb_sync_stream(ctx, ctx->stream));
         float ms = 0.f;
         SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
         t.push_back(ms);
     }
     *ms_out = median_of(t);
-    return 0;
+    return sb_check_fault(ctx);
 }
 
-// Picks, per operator, the faster of the two peer-memory halo paths by measuring both on the
+// Picks, per operator, the faster of the two forms of the peer-memory exchange by measuring both on the
 // uploaded hierarchy: the fused kernel (fused_halo.cu) wins where an application is latency-bound
 // (coarse levels, many ranks), the separate launches (p2p_halo.cu: pack on the comm stream
 // overlapping a plain interior kernel) can win on the big fine levels.  Collective: every rank
 // times `reps` back-to-back applications of each operator both ways, the times are summed over
 // the ranks (ncclAllReduce) and every rank takes the same decision from the same sums.
+// Safety does not rest on that agreement: the two forms speak one hand-shake on the same counters and landing
+// buffers (halo_sync.cuh), so a rank whose operator cannot take the fused kernel (64-bit row offsets, a forced
+// streaming mapping) simply runs the separate launches in both timing loops while its neighbours run what they like.
+// Every rank holds every level (empty where it owns no row), so all ranks walk the same (level, operator) list and
+// join the same all-reduces.
 int saena_b200_autotune_halo(saena_b200_ctx *ctx, int reps) {
     SB_ENTER();
     if (ctx->nranks == 1 || !ctx->p2p_ready) return 0;
     if (reps < 1) reps = 10;
     sb_invalidate_graphs(ctx);
-    for (size_t l = 0; l < ctx->levels.size(); ++l) {
+    const size_t n_walk = ctx->levels.size();
+    for (size_t l = 0; l < n_walk; ++l) {
         DevOperator *ops[3] = {&ctx->levels[l].A, &ctx->levels[l].P, &ctx->levels[l].R};
         for (DevOperator *op : ops) {
             double ms2[2] = {0.0, 0.0};
-            const bool mine = op->present && op->p2p && op->p2p_segs && (!op->sends.empty() || !op->recvs.empty());
+            const bool mine = op->present && op->p2p && op->hs.epoch && (!op->sends.empty() || !op->recvs.empty());
             if (mine) {
                 SB_TRY(stage_buf(ctx, 0, op->n_local_cols));
                 SB_TRY(stage_buf(ctx, 1, op->M));
@@ -638,15 +821,14 @@ int saena_b200_autotune_halo(saena_b200_ctx *ctx, int reps) {
                 EpiArgs e{};
                 e.out = ctx->stage[1];
                 for (int mode = 0; mode < 2; ++mode) {
-                    op->fused = mode == 0;
-                    if (op->fused && !sb_fused_eligible(*op)) { ms2[0] = 1e30; continue; }
+                    op->fused = mode == 0;   // not eligible: sb_apply takes the separate launches, same protocol
                     for (int it = -2; it < reps; ++it) {
                         if (it == 0) SB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
                         SB_TRY(sb_apply(ctx, *op, ctx->stage[0], EPI_PLAIN, e));
                     }
                     SB_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
-                    SB_CUDA(cudaEventSynchronize(ctx->ev_t1));
-                    SB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+                    SB_TRY(sb_sync_stream(ctx, ctx->stream));
+                    SB_TRY(sb_sync_stream(ctx, ctx->comm_stream));
                     float ms = 0.f;
                     SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
                     ms2[mode] = ms / reps;
@@ -658,10 +840,115 @@ int saena_b200_autotune_halo(saena_b200_ctx *ctx, int reps) {
             SB_TRY(sb_allreduce_sum(ctx, ctx->scalars + S_TMP, 2, ctx->stream));
             SB_TRY(sb_read_scalars(ctx));
             const double f = ctx->scalars_host[S_TMP], u = ctx->scalars_host[S_TMP + 1];
-            if (op->present && op->p2p && op->p2p_segs) op->fused = f <= u;
+            if (op->present && op->p2p && op->hs.epoch) op->fused = f <= u;
         }
     }
+    return sb_agree_fault(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Setup-time choice of every operator's row mapping BY MEASUREMENT (north_star: "warp-per-row or row-block mapping
+// chosen per level by nnz/row"): sb_choose_mapping's nnz/row rule gives the starting point, this walks the
+// neighbouring mappings -- 1/8 .. 8x the threads per row, and the sorted sliced layout (101) where short irregular
+// rows run on a sub-warp mapping -- times `reps` applications of each with the library's own launcher and keeps the
+// fastest when it wins by more than min_gain.  Round 2 measurement behind it (profiles/r02_mapping_autotune.md): the
+// rule was up to 27 % off on the transfer operators of level 2 and 12 % on level 3's A (256 -> 64 threads per row).
+// Collective on several ranks: every rank walks the same operators and the same candidates (derived from the
+// all-reduced maximum of the ranks' starting points), every timed application of an operator with a halo is an
+// exchange all ranks take part in, and the decision is taken on the slowest rank's median time (all-reduce MAX) --
+// one mapping per operator on all ranks.  Sliced operators (mapping 100) stay: where the rule picks the sliced
+// layout it measured fastest on every shape tried (profiles/r01_mapping_sweep.md).
+// changed_out (optional): number of operators whose mapping changed on this rank.
+// ---------------------------------------------------------------------------------------------
+static int time_apply_median(saena_b200_ctx *ctx, DevOperator *op, int reps, bool flush, float *ms_out) {
+    EpiArgs e{};
+    e.out = ctx->stage[1];
+    std::vector<float> t;
+    for (int it = -2; it < reps; ++it) {
+        if (flush) SB_TRY(flush_l2(ctx));
+        SB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+        SB_TRY(sb_apply(ctx, *op, ctx->stage[0], EPI_PLAIN, e));
+        SB_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
+        SB_TRY(sb_sync_stream(ctx, ctx->stream));
+        float ms = 0.f;
+        SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+        if (it >= 0) t.push_back(ms);
+    }
+    *ms_out = median_of(t);
     return 0;
+}
+
+int saena_b200_autotune_mapping(saena_b200_ctx *ctx, int reps, double min_gain, int *changed_out) {
+    SB_ENTER();
+    if (reps < 3) reps = 10;
+    if (!(min_gain >= 0.0)) min_gain = 0.03;
+    if (!ctx->tune_dev) SB_CUDA(cudaMalloc((void **)&ctx->tune_dev, sizeof(double) * 32));
+    sb_invalidate_graphs(ctx);
+    int changed = 0;
+    const bool multi = ctx->nranks > 1 && !ctx->detached;
+    for (size_t l = 0; l < ctx->levels.size(); ++l) {
+        DevOperator *ops[3] = {&ctx->levels[l].A, &ctx->levels[l].P, &ctx->levels[l].R};
+        for (int kind = 0; kind < 3; ++kind) {
+            DevOperator *op = ops[kind];
+            // ---- what this rank holds
+            const bool mine = op->present && op->M > 0 && op->nnz_local + op->nnz_remote > 0;
+            const int cur = !mine ? 0 : (op->use_sell ? SB_MAPPING_SELL : (op->use_sellp ? SB_MAPPING_SELLP : (op->use_stream ? -op->lanes : op->lanes)));
+            const bool has_halo = mine && (!op->sends.empty() || !op->recvs.empty() || op->nnz_remote > 0 || op->merged);
+            // ---- agree: [largest threads-per-row starting point, somebody is sliced / streaming / pinned]
+            double agree[2] = {(cur >= 1 && cur <= 256) ? (double)cur : 0.0,
+                               (mine && (cur <= 0 || cur >= SB_MAPPING_SELL || op->sell_only)) ? 1.0 : 0.0};
+            if (multi) {
+                SB_CUDA(cudaMemcpyAsync(ctx->tune_dev, agree, sizeof(agree), cudaMemcpyHostToDevice, ctx->stream));
+                SB_TRY(sb_allreduce_max(ctx, ctx->tune_dev, 2, ctx->stream));
+                SB_CUDA(cudaMemcpyAsync(agree, ctx->tune_dev, sizeof(agree), cudaMemcpyDeviceToHost, ctx->stream));
+                SB_TRY(sb_sync_stream(ctx, ctx->stream));
+            }
+            const int start = (int)agree[0];
+            if (start == 0 || agree[1] != 0.0) continue;   // nobody holds it, or a mapping this walk leaves alone
+            // ---- candidates, the same list on every rank
+            std::vector<int> cands;
+            for (int c = 1; c <= 256; c *= 2)
+                if (c * 8 >= start && c <= start * 8) cands.push_back(c);
+            if (!multi && mine && !has_halo && start < 32 && op->M >= 150000) cands.push_back(SB_MAPPING_SELLP);
+            std::vector<double> ms(32, 0.0);
+            if (mine) {
+                SB_TRY(stage_buf(ctx, 0, op->n_local_cols));
+                SB_TRY(stage_buf(ctx, 1, op->M));
+                SB_CUDA(cudaMemsetAsync(ctx->stage[0], 0, sizeof(double) * op->n_local_cols, ctx->stream));
+            }
+            const bool flush = mine && sb_operator_bytes(*op) < (int64_t)300e6;
+            for (size_t k = 0; k < cands.size(); ++k) {
+                if (!mine) continue;   // no row, no halo: nothing of this operator to run, only the agreement below
+                op->forced_mapping = cands[k];
+                SB_TRY(sb_prepare_operator(ctx, *op));
+                float t = 0.f;
+                SB_TRY(time_apply_median(ctx, op, reps, flush, &t));
+                ms[k] = t;
+            }
+            if (multi) {
+                SB_CUDA(cudaMemcpyAsync(ctx->tune_dev, ms.data(), sizeof(double) * 32, cudaMemcpyHostToDevice, ctx->stream));
+                SB_TRY(sb_allreduce_max(ctx, ctx->tune_dev, 32, ctx->stream));
+                SB_CUDA(cudaMemcpyAsync(ms.data(), ctx->tune_dev, sizeof(double) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+                SB_TRY(sb_sync_stream(ctx, ctx->stream));
+            }
+            // ---- decision: the fastest; the starting point unless it is beaten by more than min_gain
+            size_t best = 0, base = 0;
+            for (size_t k = 0; k < cands.size(); ++k) {
+                if (cands[k] == start) base = k;
+                if (ms[k] < ms[best]) best = k;
+            }
+            if (!(ms[best] < (1.0 - min_gain) * ms[base])) best = base;
+            if (mine) {
+                op->forced_mapping = cands[best];
+                SB_TRY(sb_prepare_operator(ctx, *op));
+                SB_CUDA(cudaStreamSynchronize(ctx->stream));
+                sb_drop_unused_layouts(*op);
+                if (cands[best] != cur) ++changed;
+            }
+        }
+    }
+    if (changed_out) *changed_out = changed;
+    return multi ? sb_agree_fault(ctx) : 0;
 }
 
 // 1: fused kernel, 0: separate launches / NCCL, -1: no such operator; ms[2] = this rank's autotune timings
@@ -705,13 +992,15 @@ int saena_b200_time_matvec_compute_only(saena_b200_ctx *ctx, int level, int kind
     SB_ENTER();
     DevOperator *op = get_op(ctx, level, kind);
     if (!op) SB_FAIL("time_matvec_compute_only: no such operator");
-    const bool was = op->fused;
+    const bool was = op->fused, was_p2p = op->p2p;
     op->fused = fused != 0;
+    if (fused && ctx->detached) op->p2p = true;   // compute roles only: the hand-shake state is never touched
     ctx->apply_mode = 1;
     int rc = saena_b200_time_matvec(ctx, level, kind, 3, 0, ms_out);
     if (!rc) rc = saena_b200_time_matvec(ctx, level, kind, reps, do_flush, ms_out);
     ctx->apply_mode = 0;
     op->fused = was;
+    op->p2p = was_p2p;
     return rc;
 }
 
@@ -743,7 +1032,7 @@ int saena_b200_time_smooth_sweep(saena_b200_ctx *ctx, int level, int smoother, i
         SB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
         SB_TRY(sb_smooth(ctx, level, smoother, 1, ctx->stage[1], false));
         SB_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
-        SB_CUDA(cudaEventSynchronize(ctx->ev_t1));
+        SB_TRY(sb_sync_stream(ctx, ctx->stream));
         float ms = 0.f;
         SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
         t.push_back(ms);
@@ -766,8 +1055,8 @@ int saena_b200_time_vcycle(saena_b200_ctx *ctx, int level, int smoother, int pre
         SB_TRY(sb_vcycle(ctx, level, smoother, pre, post, rhs, true));
     }
     SB_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
-    SB_CUDA(cudaEventSynchronize(ctx->ev_t1));
-    SB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+    SB_TRY(sb_sync_stream(ctx, ctx->stream));
+    SB_TRY(sb_sync_stream(ctx, ctx->comm_stream));
     float ms = 0.f;
     SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
     *ms_out = ms / reps;
@@ -777,7 +1066,7 @@ int saena_b200_time_vcycle(saena_b200_ctx *ctx, int level, int smoother, int pre
 int saena_b200_timer_start(saena_b200_ctx *ctx) {
     if (!ctx) return 1;
     SB_CUDA(cudaSetDevice(ctx->device));
-    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SB_TRY(sb_sync_stream(ctx, ctx->stream));
     SB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
     return 0;
 }
@@ -786,7 +1075,7 @@ int saena_b200_timer_stop(saena_b200_ctx *ctx, float *ms_out) {
     if (!ctx) return 1;
     SB_CUDA(cudaSetDevice(ctx->device));
     SB_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
-    SB_CUDA(cudaEventSynchronize(ctx->ev_t1));
+    SB_TRY(sb_sync_stream(ctx, ctx->stream));
     SB_CUDA(cudaEventElapsedTime(ms_out, ctx->ev_t0, ctx->ev_t1));
     return 0;
 }
@@ -831,8 +1120,10 @@ int saena_b200_set_operator_dense(saena_b200_ctx *ctx, int level, int kind, int 
 
 int saena_b200_set_coarsest_solver(saena_b200_ctx *ctx, int use_cg) {
     if (!ctx) return 1;
-    ctx->coarsest_cg = use_cg != 0;
-    sb_invalidate_graphs(ctx);
+    if (ctx->coarsest_cg != (use_cg != 0)) {
+        ctx->coarsest_cg = use_cg != 0;
+        sb_invalidate_graphs(ctx);
+    }
     return 0;
 }
 

@@ -70,30 +70,25 @@ struct HaloPeer {
     int count;
 };
 
-// Peer-memory halo (csrc/p2p_halo.cu): one segment of the packed send order and where it lands
-// in the receiving rank's ghost buffer (IPC-mapped), plus the flag the sender raises there.
-struct P2PSegment {
+// Peer-memory halo (csrc/halo_sync.cuh, fused_halo.cu, p2p_halo.cu): one slice of the packed send order, where it
+// lands in the receiving rank's landing area (IPC-mapped, doubles, TWO buffers selected by the parity of the
+// application count) and the counter the last pack CTA raises there.
+struct HaloSeg {
     long long start;              // first packed element of this receiver's slice
     long long count;
-    void *dst;                    // peer ghost slice (double* or float*)
-    unsigned long long *arrived;  // flag in the PEER's arena: "this operator's ghost values have landed"
+    double *dst;                  // slice of buffer 0 in the receiver's landing area
+    long long dst_stride;         // elements between the receiver's two buffers (= its recvSize)
+    unsigned long long *arrived;  // flag in the RECEIVER's arena: "values of application k have landed" (= k + 1)
 };
 
-// Fused halo kernel (csrc/fused_halo.cu): one slice of the packed send order, where it lands in
-// the receiver's landing area (doubles) and the epoch counter the last pack CTA raises there.
-struct FusedSeg {
-    long long start;
-    long long count;
-    double *dst;
-    unsigned long long *arrived;
-};
-
-struct FusedHaloDev {
-    unsigned long long *epoch = nullptr;  // applications completed (device memory: graph-replayable)
-    unsigned int *tickets = nullptr;      // [2] last-CTA detection: pack CTAs / all hand-shake CTAs
-    FusedSeg *segs = nullptr;                      // [sends.size()]
-    unsigned long long **wait_consumed = nullptr;  // [sends.size()] my arena: receiver r consumed epoch e
-    unsigned long long **wait_arrived = nullptr;   // [recvs.size()] my arena: sender s's epoch e has landed
+// Device-side state of one operator's hand-shake.  All counters are monotonic (application counts), nothing is ever
+// reset, so a launch carries no host-side state and replays from a CUDA graph.
+struct HaloSyncDev {
+    unsigned long long *epoch = nullptr;  // [2] applications completed by the pack role / by the receiving role
+    unsigned int *tickets = nullptr;      // [2] last-CTA detection of the two roles
+    HaloSeg *segs = nullptr;                         // [sends.size()]
+    unsigned long long **wait_consumed = nullptr;    // [sends.size()] my arena: receiver r has consumed application k
+    unsigned long long **wait_arrived = nullptr;     // [recvs.size()] my arena: sender s's application k has landed
     unsigned long long **signal_consumed = nullptr;  // [recvs.size()] the senders' arenas
 };
 
@@ -164,21 +159,19 @@ struct DevOperator {
     void *ghost_buf = nullptr; // double[recvSize] or float[recvSize]
     std::vector<HaloPeer> sends, recvs;
 
-    // peer-memory path (set by saena_b200_p2p_import; the NCCL path stays as the fallback)
+    // peer-memory path (set by saena_b200_p2p_import; the NCCL path stays as the fallback).  p2p: ghost values are
+    // stored by the senders into ghost_d over NVLink.  fused: the whole application is ONE kernel (fused_halo.cu);
+    // otherwise separate launches (p2p_halo.cu: pack kernel on the comm stream, interior kernel, wait, boundary
+    // kernel, release).  Both speak the same hand-shake on the same flags and landing buffers, so the choice is free
+    // per operator, per rank and per application.
     bool p2p = false;
-    P2PSegment *p2p_segs = nullptr;               // device copy, [sends.size()]
-    unsigned int *p2p_ticket = nullptr;           // last-block detection of the pack kernel
-    std::vector<unsigned long long *> p2p_wait_arrived;    // my arena: one flag per sender
-    std::vector<unsigned long long *> p2p_wait_consumed;   // my arena: one flag per receiver of mine
-    unsigned long long **p2p_signal_consumed = nullptr;    // device array of peers' flags, [recvs.size()]
-    size_t ghost_arena_off = 0;                   // where this operator's ghost area starts in the arena
-
-    // fused path (fused_halo.cu): exchange + SpMV in one kernel; default once the peers are imported
     bool fused = false;
     float tune_ms[2] = {0.f, 0.f};                // saena_b200_autotune_halo: fused / separate launches
-    double *ghost_d = nullptr;                    // landing area in the arena, recvSize doubles
+    double *ghost_d = nullptr;                    // landing area in the arena, 2 x recvSize doubles (double-buffered)
+    size_t ghost_arena_off = 0;                   // NCCL path: where this operator's typed ghost area / x_ext starts
     size_t ghost_d_off = 0;
-    FusedHaloDev fh;
+    int op_id = 0;                                // level * 3 + kind (fault reports)
+    HaloSyncDev hs;
 
     // kernel mapping
     int lanes = 0;            // lanes per row (vec) / lanes per row in the reduce phase (stream)
@@ -275,7 +268,16 @@ struct saena_b200_ctx {
     size_t arena_bytes = 0;
     std::vector<void *> peer_arena;  // [nranks] IPC mappings of the peers' arenas (nullptr: not opened)
     bool p2p_ready = false;
+    // bounded waits (halo_sync.cuh): a spin that outlives halo_timeout_ns records what it waited for in fault_dev and
+    // every later wait drains at once; the ABI call that ran into it returns non-zero (the reference's convention is
+    // print + MPI_Abort, src/saena_object_solve.cpp:1012-1013; the adaptor maps the status to that).
+    unsigned long long *fault_dev = nullptr;   // = (unsigned long long *)(scalars + S_COUNT): code, wanted, seen, spare
+    unsigned long long halo_timeout_ns = 5000000000ull;   // SAENA_B200_HALO_TIMEOUT_MS
+    double sync_timeout_s = 180.0;             // host-side watchdog of every blocking wait (SAENA_B200_SYNC_TIMEOUT_S)
+    bool faulted = false;                      // sticky until saena_b200_clear_fault
     bool fused_default = true;  // p2p_import switches eligible operators to the fused kernel (SAENA_B200_HALO_FUSED=0: no)
+
+    double *tune_dev = nullptr;   // [32] scratch of the collective mapping autotune (all-reduce MAX of candidate times)
 
     // L2 flush buffer for the timing loops
     void *flush_buf = nullptr;
@@ -285,7 +287,9 @@ struct saena_b200_ctx {
 // scalar slots
 enum { S_RHO_RES = 0, S_PDOTH = 1, S_RR = 2, S_BETA_NUM = 3, S_TMP = 4,
        S_C_RR = 8, S_C_DEN = 9, S_C_RRNEW = 10,  // coarsest-level CG (must not clobber the outer loop's)
-       S_COUNT = 16 };
+       S_AGREE = 11,                             // number of ranks whose halo exchange timed out (sb_agree_fault)
+       S_COUNT = 16,
+       S_FAULT_WORDS = 4 };  // the halo fault record follows the scalars: one copy brings both to the host
 
 static const int SB_MAPPING_SELL = 100;   // forced_mapping / set_mapping code of the sliced layout
 static const int SB_MAPPING_SELLP = 101;  // ... of the sliced layout with rows sorted by length inside 256-row windows
@@ -310,6 +314,7 @@ int sb_upload_band_operator(saena_b200_ctx *ctx, int level, int n, int half_band
 void sb_free_operator(DevOperator &op);
 void sb_choose_mapping(saena_b200_ctx *ctx, DevOperator &op);
 int sb_prepare_operator(saena_b200_ctx *ctx, DevOperator &op);
+void sb_drop_unused_layouts(DevOperator &op);
 void sb_sellp_layout(int M, const int64_t *rowptr, int *perm, long long *slice_ptr);
 // w-style application of an operator with a fused epilogue; x is the local input vector.
 int sb_apply(saena_b200_ctx *ctx, DevOperator &op, const double *x, int epi, const EpiArgs &args);
@@ -321,6 +326,7 @@ int sb_nccl_init(saena_b200_ctx *ctx, const void *id);
 void sb_nccl_destroy(saena_b200_ctx *ctx);
 int sb_halo_exchange(saena_b200_ctx *ctx, DevOperator &op, cudaStream_t s);
 int sb_allreduce_sum(saena_b200_ctx *ctx, double *dev_vals, int count, cudaStream_t s);
+int sb_allreduce_max(saena_b200_ctx *ctx, double *dev_vals, int count, cudaStream_t s);
 // moves blocks of `src` to the peers' `dst`; forward: send plan -> recv plan, backward: reversed
 int sb_repart(saena_b200_ctx *ctx, const RepartPlan &plan, bool backward, const double *src, double *dst,
               cudaStream_t s);
@@ -328,13 +334,22 @@ int sb_repart(saena_b200_ctx *ctx, const RepartPlan &plan, bool backward, const 
 // ---- p2p_halo.cu
 int sb_arena_build(saena_b200_ctx *ctx);     // at finalize: allocate the arena, point ghost buffers into it
 void sb_arena_free(saena_b200_ctx *ctx);
-int sb_p2p_pack_and_signal(saena_b200_ctx *ctx, DevOperator &op, const double *x, cudaStream_t s);
-int sb_p2p_wait_arrived(saena_b200_ctx *ctx, DevOperator &op, cudaStream_t s);
-int sb_p2p_signal_consumed(saena_b200_ctx *ctx, DevOperator &op, cudaStream_t s);
+// separate-launch form of the peer-memory exchange (same hand-shake as the fused kernel)
+int sb_p2p_pack(saena_b200_ctx *ctx, DevOperator &op, const double *x, cudaStream_t s);   // wait consumed, pack, raise arrived
+int sb_p2p_wait_arrived(saena_b200_ctx *ctx, DevOperator &op, cudaStream_t s);            // 1 CTA spins (bounded)
+int sb_p2p_gather_ghosts(saena_b200_ctx *ctx, DevOperator &op, double *dst, cudaStream_t s);  // current buffer -> dst
+int sb_p2p_release(saena_b200_ctx *ctx, DevOperator &op, cudaStream_t s);                 // raise consumed, advance epoch
 
 // ---- fused_halo.cu
 bool sb_fused_eligible(const DevOperator &op);
 int sb_apply_fused(saena_b200_ctx *ctx, DevOperator &op, const double *x, int epi, const EpiArgs &args);
+
+// ---- api.cu
+int sb_sync_stream(saena_b200_ctx *ctx, cudaStream_t s);   // cudaStreamSynchronize with a watchdog
+int sb_check_fault(saena_b200_ctx *ctx);                   // non-zero (and ctx->error set) once a halo wait has timed out
+// collective end of a solver call: all ranks return the same status (one all-reduce of the fault flags), so no rank
+// leaves the sequence of collective calls while the others go on
+int sb_agree_fault(saena_b200_ctx *ctx);
 
 // ---- vector_ops.cu
 int sb_dot(saena_b200_ctx *ctx, const double *a, const double *b, int n, int slot);           // scalars[slot] = <a,b> (global)

@@ -14,8 +14,7 @@
 // not remove it, so it is device-side dependency latency, not launch cost).  Here a CTA's role
 // follows from its index:
 //
-//   [0, n_pack)                  pack: wait until the receivers have consumed my previous values,
-//                                gather x[vIndex[i]] (rounded through float when the operator's
+//   [0, n_pack)                  pack: gather x[vIndex[i]] (rounded through float when the operator's
 //                                use_double is false -- the same value matvec_sparse_float widens
 //                                on the receiving side) and store it straight into the receiving
 //                                rank's landing area; the last pack CTA raises `arrived` there
@@ -27,15 +26,20 @@
 //                                merged operators (every row couples to ghosts) run the ordinary
 //                                mapping over [local | ghost] columns, the gather choosing the
 //                                source by column index -- no x_ext copy, no widen pass.
-//   last CTA of the hand-shake   tells every sender its values are consumed, advances the epoch
+//   last CTA of each role        raises the flags of the hand-shake and advances the role's counter
 //
-// The epoch lives in device memory (read by the CTAs, advanced by the last one), flags are
-// monotonic counters, so a launch carries no host-side state: the kernel replays from a CUDA graph.
-// Progress: CTAs are dispatched in index order, so the pack CTAs of a launch are resident before
-// any CTA of the same launch spins; they wait only on `consumed`, which the peers raised at the
-// end of THEIR previous launch of this operator.  No cycle.
+// The hand-shake (halo_sync.cuh) is shared with the separate-launch form (p2p_halo.cu): monotonic
+// counters in device memory, two landing buffers selected by the application's parity, every wait
+// bounded by a globaltimer deadline.  A launch carries no host-side state: the kernel replays from
+// a CUDA graph.  Progress: CTAs are dispatched in index order, so the pack CTAs of a launch are
+// resident before any CTA of the same launch spins; with two buffers they wait only for a
+// `consumed` signal the peers sent a whole application earlier.  A waiting CTA's producer is always a
+// pack CTA of ANOTHER rank's launch of the same operator, and nothing of this rank stands between
+// that launch and the GPU: every earlier launch of this rank has completed (stream order; the
+// separate-launch form joins its comm stream before its boundary kernel).  No cycle.
 #include <algorithm>
 
+#include "halo_sync.cuh"
 #include "spmv_kernels.cuh"
 
 struct FusedArgs {
@@ -54,7 +58,8 @@ struct FusedArgs {
     const int *bcol;
     const double *bval;
     const double *x;
-    const double *ghost;  // this rank's landing area (doubles)
+    const double *ghost;  // this rank's landing area: 2 x recvSize doubles
+    int recvSize;
     EpiArgs e;
     // CTA roles: pack | interior rows | rows that wait for ghosts.  The waiting CTAs are at most a
     // chip-full (resident all at once) and stride over n_wait_blocks virtual blocks, so the
@@ -62,16 +67,9 @@ struct FusedArgs {
     int n_pack, n_int, n_wait, n_wait_blocks;
     int do_sync, do_compute;
     // pack
-    int vIndexSize, n_segs, round_float;
+    int vIndexSize, round_float;
     const int *vIndex;
-    const FusedSeg *segs;
-    // hand-shake
-    unsigned long long *epoch;
-    unsigned int *tickets;  // [0] pack CTAs done, [1] pack + waiting CTAs done
-    unsigned long long *const *wait_consumed;    // [n_segs]  my arena
-    unsigned long long *const *wait_arrived;     // [n_recv]  my arena
-    unsigned long long *const *signal_consumed;  // [n_recv]  the senders' arenas
-    int n_recv;
+    HaloSync h;
 };
 
 template <int MAP, int EPI, typename XS>
@@ -100,75 +98,35 @@ fused_halo_spmv_kernel(const __grid_constant__ FusedArgs a) {
         fused_rows<MAP, EPI>(b - a.n_pack, a.int_lo, a.int_hi, a, XLocal{a.x});
         return;
     }
+    const bool packer = b < a.n_pack;
     if (a.do_sync) {
-        if (tid == 0) s_epoch = *(volatile unsigned long long *)a.epoch;
+        if (tid == 0) s_epoch = *(volatile unsigned long long *)&a.h.epoch[packer ? 0 : 1];
         __syncthreads();
     }
-    const unsigned long long done = a.do_sync ? s_epoch : 0ull;  // applications completed before this one
-    if (b < a.n_pack) {
-        // ---- pack + peer stores
-        if (tid < a.n_segs) {
-            const volatile unsigned long long *f = a.wait_consumed[tid];
-            while (*f < done) __nanosleep(40);
-        }
-        __syncthreads();
-        const int i = b * 256 + tid;
-        if (i < a.vIndexSize) {
-            int s = 0;
-            while (s + 1 < a.n_segs && i >= a.segs[s + 1].start) ++s;  // a handful of receivers
-            double v = a.x[a.vIndex[i]];
-            if (a.round_float) v = (double)(float)v;  // matvec_sparse_float: the value the receiver would widen
-            a.segs[s].dst[i - a.segs[s].start] = v;
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned int t = atomicAdd(&a.tickets[0], 1u);
-            if (t == (unsigned int)a.n_pack - 1u) {
-                __threadfence_system();
-                for (int s = 0; s < a.n_segs; ++s) *(volatile unsigned long long *)a.segs[s].arrived = done + 1ull;
-                a.tickets[0] = 0u;
-            }
-        }
-    } else {
-        // ---- rows that read ghost values
-        if (a.do_sync) {
-            if (tid < a.n_recv) {
-                const volatile unsigned long long *f = a.wait_arrived[tid];
-                while (*f < done + 1ull) __nanosleep(40);
-            }
-            __threadfence();
-            __syncthreads();
-        }
-        if (a.do_compute) {
-            for (int vb = b - a.n_pack - a.n_int; vb < a.n_wait_blocks; vb += a.n_wait) {
-                if constexpr (MERGED) {
-                    fused_rows<MAP, EPI>(vb, 0, a.M, a, XGhost{a.x, a.ghost, a.n_local});
-                    if constexpr (MAP >= 64 && MAP != SB_MAPPING_SELL) __syncthreads();  // s_part is reused
-                } else {
-                    if (a.bnd_wide)
-                        spmv_boundary_body<32, EPI, int, double>(vb, a.n_brows, a.brow, a.rowptr, a.col, a.val,
-                                                                 a.brow_ptr, a.bcol, a.bval, a.x, a.ghost, a.e);
-                    else
-                        spmv_boundary_body<8, EPI, int, double>(vb, a.n_brows, a.brow, a.rowptr, a.col, a.val,
-                                                                a.brow_ptr, a.bcol, a.bval, a.x, a.ghost, a.e);
-                }
+    const unsigned long long done = a.do_sync ? s_epoch : 0ull;  // applications this role completed before this one
+    if (packer) {
+        sb_halo_pack_cta(a.h, b, a.n_pack, done, a.x, a.vIndex, a.vIndexSize, a.round_float != 0);
+        return;
+    }
+    // ---- rows that read ghost values
+    if (a.do_sync) sb_halo_wait_cta(a.h, done);
+    if (a.do_compute) {
+        const double *ghost = a.ghost + (size_t)(done & 1ull) * (size_t)a.recvSize;
+        for (int vb = b - a.n_pack - a.n_int; vb < a.n_wait_blocks; vb += a.n_wait) {
+            if constexpr (MERGED) {
+                fused_rows<MAP, EPI>(vb, 0, a.M, a, XGhost{a.x, ghost, a.n_local});
+                if constexpr (MAP >= 64 && MAP != SB_MAPPING_SELL) __syncthreads();  // s_part is reused
+            } else {
+                if (a.bnd_wide)
+                    spmv_boundary_body<32, EPI, int, double>(vb, a.n_brows, a.brow, a.rowptr, a.col, a.val,
+                                                             a.brow_ptr, a.bcol, a.bval, a.x, ghost, a.e);
+                else
+                    spmv_boundary_body<8, EPI, int, double>(vb, a.n_brows, a.brow, a.rowptr, a.col, a.val,
+                                                            a.brow_ptr, a.bcol, a.bval, a.x, ghost, a.e);
             }
         }
     }
-    if (!a.do_sync) return;
-    // ---- the last CTA of the hand-shake releases the senders and advances the epoch
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        const unsigned int t = atomicAdd(&a.tickets[1], 1u);
-        if (t == (unsigned int)(a.n_pack + a.n_wait) - 1u) {
-            for (int r = 0; r < a.n_recv; ++r) *(volatile unsigned long long *)a.signal_consumed[r] = done + 1ull;
-            *(volatile unsigned long long *)a.epoch = done + 1ull;
-            a.tickets[1] = 0u;
-            __threadfence_system();
-        }
-    }
+    if (a.do_sync) sb_halo_release_cta(a.h, a.n_wait, done);
 }
 
 static int main_blocks(const DevOperator &op, int nrows) {
@@ -178,8 +136,11 @@ static int main_blocks(const DevOperator &op, int nrows) {
     return (nrows + rows_per_block - 1) / rows_per_block;
 }
 
+// The fused kernel covers the 32-bit-offset CSR / sliced mappings; anything else (64-bit row offsets, the
+// streaming mapping) takes the separate launches, which speak the same hand-shake -- the choice is local.
 bool sb_fused_eligible(const DevOperator &op) {
-    return op.fused && !op.wide_offsets && !op.use_stream && (!op.sends.empty() || !op.recvs.empty());
+    return op.p2p && op.fused && !op.wide_offsets && !op.use_stream && !op.use_sellp &&
+           (!op.sends.empty() || !op.recvs.empty());
 }
 
 template <int EPI, bool MERGED>
@@ -207,14 +168,12 @@ static int apply_fused_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x
     a.M = op.M; a.int_lo = op.int_lo; a.int_hi = op.int_hi; a.n_local = op.n_local_cols;
     a.n_brows = op.n_brows; a.bnd_wide = op.avg_nnz_row() >= 48.0;
     a.brow = op.brow; a.brow_ptr = op.brow_ptr; a.bcol = op.bcol; a.bval = op.bval;
-    a.x = x; a.ghost = op.ghost_d; a.e = e;
+    a.x = x; a.ghost = op.ghost_d; a.recvSize = op.recvSize; a.e = e;
     a.do_sync = mode != 1;
     a.do_compute = mode != 2;
-    a.vIndexSize = op.vIndexSize; a.vIndex = op.vIndex; a.segs = op.fh.segs; a.n_segs = (int)op.sends.size();
+    a.vIndexSize = op.vIndexSize; a.vIndex = op.vIndex;
     a.round_float = !op.use_double;
-    a.epoch = op.fh.epoch; a.tickets = op.fh.tickets;
-    a.wait_consumed = op.fh.wait_consumed; a.wait_arrived = op.fh.wait_arrived;
-    a.signal_consumed = op.fh.signal_consumed; a.n_recv = (int)op.recvs.size();
+    a.h = sb_halo_sync_args(ctx, op);
     a.n_pack = mode == 1 ? 0 : (op.vIndexSize + 255) / 256;
     if (op.merged) {
         a.n_int = 0;
@@ -233,7 +192,7 @@ static int apply_fused_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x
     // a pack CTA of another rank, never a CTA behind it in this grid)
     a.n_wait = std::min(a.n_wait_blocks, 8 * ctx->sm_count);
     if (mode != 1 && a.n_wait == 0 && !op.recvs.empty()) SB_FAIL("fused apply: receives but no row reads them");
-    if (a.n_segs > 256 || a.n_recv > 256) SB_FAIL("fused apply: more than 256 neighbours (one spinning thread each)");
+    if (a.h.n_segs > 256 || a.h.n_recv > 256) SB_FAIL("fused apply: more than 256 neighbours (one spinning thread each)");
     const int grid = a.n_pack + a.n_int + a.n_wait;
     if (grid == 0) return 0;
     ++ctx->launches;

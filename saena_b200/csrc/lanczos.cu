@@ -168,9 +168,10 @@ int sb_find_eig(saena_b200_ctx *ctx, int level, int max_iter, const double *star
         pev = ev;
     }
 #undef LZ_TRY
-    cudaError_t ce = cudaStreamSynchronize(s);
+    const int sync_rc = sb_sync_stream(ctx, s);
     release();
-    if (ce != cudaSuccess) SB_FAIL("find_eig: a kernel failed");
+    if (sync_rc) return sync_rc;
+    SB_TRY(sb_check_fault(ctx));
     *eig_out = 1.0001 * ev;  // lamlan_saena.h:59
     if (iters_out) *iters_out = itern;
     ctx->launches += 4 * itern;

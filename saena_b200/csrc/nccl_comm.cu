@@ -13,6 +13,7 @@
 // in a torchrun process this resolves to the libnccl.so.2 torch already loaded.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 
 #include "common.h"
 
@@ -34,11 +35,12 @@ NcclApi g_nccl;
 
 bool load_nccl(std::string &err) {
     if (g_nccl.handle) return true;
-    const char *names[] = {"libnccl.so.2", "libnccl.so",
-                           "/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib/libnccl.so.2",
-                           "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    // SAENA_B200_NCCL_LIB names the library explicitly; otherwise the loader's search path decides (in a torchrun
+    // process libnccl.so.2 resolves to the copy torch already mapped)
+    const char *names[] = {getenv("SAENA_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     void *h = nullptr;
     for (const char *n : names) {
+        if (!n || !*n) continue;
         h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         if (h) break;
     }
@@ -127,6 +129,14 @@ int sb_allreduce_sum(saena_b200_ctx *ctx, double *dev_vals, int count, cudaStrea
     if (!ctx->nccl_comm) SB_FAIL("all-reduce without a communicator (a detached context has no peers)");
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     SB_NCCL(g_nccl.AllReduce(dev_vals, dev_vals, (size_t)count, ncclDouble, ncclSum, comm, s));
+    return 0;
+}
+
+int sb_allreduce_max(saena_b200_ctx *ctx, double *dev_vals, int count, cudaStream_t s) {
+    if (ctx->nranks == 1) return 0;
+    if (!ctx->nccl_comm) SB_FAIL("all-reduce without a communicator (a detached context has no peers)");
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    SB_NCCL(g_nccl.AllReduce(dev_vals, dev_vals, (size_t)count, ncclDouble, ncclMax, comm, s));
     return 0;
 }
 

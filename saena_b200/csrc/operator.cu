@@ -34,7 +34,8 @@ void sb_free_operator(DevOperator &op) {
     cudaFree(op.rowptr); cudaFree(op.col); cudaFree(op.val); cudaFree(op.blk_row);
     cudaFree(op.brow); cudaFree(op.brow_ptr); cudaFree(op.bcol); cudaFree(op.bval); cudaFree(op.brow_mask);
     cudaFree(op.vIndex); cudaFree(op.send_buf);
-    cudaFree(op.p2p_segs); cudaFree(op.p2p_ticket); cudaFree(op.p2p_signal_consumed);
+    cudaFree(op.hs.epoch); cudaFree(op.hs.tickets); cudaFree(op.hs.segs);
+    cudaFree(op.hs.wait_consumed); cudaFree(op.hs.wait_arrived); cudaFree(op.hs.signal_consumed);
     // ghost_buf / x_ext belong to the context's halo arena
     cudaFree(op.sell_ptr); cudaFree(op.sell_col); cudaFree(op.sell_val);
     cudaFree(op.sellp_ptr); cudaFree(op.sellp_perm); cudaFree(op.sellp_col); cudaFree(op.sellp_val);
@@ -76,10 +77,12 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
     // name and ~all rows would take the boundary kernel.  (For slab partitions the rows outside the
     // longest clean run ARE the rows with remote entries, and the first rule alone decides, as before.)
     int n_rows_with_remote = 0, n_outside_clean_run = 0;
+    for (int64_t k = 0; k < d->nnz_remote; ++k)
+        if (d->row_remote[k] < 0 || d->row_remote[k] >= M) SB_FAIL("upload_operator: row_remote out of range");
     if (d->nnz_remote > 0) {
         std::vector<char> has(M, 0);
         for (int64_t k = 0; k < d->nnz_remote; ++k)
-            if (d->row_remote[k] >= 0 && d->row_remote[k] < M && !has[d->row_remote[k]]) { has[d->row_remote[k]] = 1; ++n_rows_with_remote; }
+            if (!has[d->row_remote[k]]) { has[d->row_remote[k]] = 1; ++n_rows_with_remote; }
         int best = 0;
         for (int i = 0; i < M;) {
             if (has[i]) { ++i; continue; }
@@ -595,6 +598,20 @@ static int build_sellp(saena_b200_ctx *ctx, DevOperator &op) {
     return 0;
 }
 
+// copies of the entries in layouts the operator no longer uses (a mapping walk builds them to time them)
+void sb_drop_unused_layouts(DevOperator &op) {
+    if (!op.use_sellp && op.sellp_ptr) {
+        cudaFree(op.sellp_ptr); cudaFree(op.sellp_perm); cudaFree(op.sellp_col); cudaFree(op.sellp_val);
+        op.sellp_ptr = nullptr; op.sellp_perm = nullptr; op.sellp_col = nullptr; op.sellp_val = nullptr;
+        op.sellp_padded = 0;
+    }
+    if (!op.use_sell && !op.sell_only && op.sell_ptr) {
+        cudaFree(op.sell_ptr); cudaFree(op.sell_col); cudaFree(op.sell_val);
+        op.sell_ptr = nullptr; op.sell_col = nullptr; op.sell_val = nullptr;
+        op.sell_padded = 0;
+    }
+}
+
 int sb_prepare_operator(saena_b200_ctx *ctx, DevOperator &op) {
     if (!op.present) return 0;
     sb_choose_mapping(ctx, op);
@@ -667,19 +684,26 @@ static void launch_boundary(saena_b200_ctx *ctx, DevOperator &op, const double *
     const bool wide = op.avg_nnz_row() >= 48.0;
     const int threads = 256, rows_per_block = threads / (wide ? 32 : 8);
     const int blocks = (op.n_brows + rows_per_block - 1) / rows_per_block;
-#define SB_BND(L, G)                                                                               \
+#define SB_BND(L, G, GHOST, EPOCH)                                                                 \
     spmv_boundary_kernel<L, EPI, OffT, G><<<blocks, threads, 0, ctx->stream>>>(                    \
         op.n_brows, op.brow, rp, op.col, op.val, op.brow_ptr, op.bcol, op.bval, x,                 \
-        (const G *)op.ghost_buf, e)
-    if (op.use_double) { if (wide) SB_BND(32, double); else SB_BND(8, double); }
-    else { if (wide) SB_BND(32, float); else SB_BND(8, float); }
+        (const G *)(GHOST), EPOCH, op.recvSize, e)
+    if (op.p2p) {
+        // peer-memory exchange: doubles (the sender rounded through float when use_double is false), two buffers
+        if (wide) SB_BND(32, double, op.ghost_d, op.hs.epoch); else SB_BND(8, double, op.ghost_d, op.hs.epoch);
+    } else if (op.use_double) {
+        if (wide) SB_BND(32, double, op.ghost_buf, nullptr); else SB_BND(8, double, op.ghost_buf, nullptr);
+    } else {
+        if (wide) SB_BND(32, float, op.ghost_buf, nullptr); else SB_BND(8, float, op.ghost_buf, nullptr);
+    }
 #undef SB_BND
 }
 
-// the compute stream may not touch the ghost values before they have landed
+// The compute stream joins the comm stream (its own pack / exchange is done: x may be overwritten by the caller, and
+// nothing of this application is still waiting for an SM), then waits for the ghost values.
 static int wait_halo(saena_b200_ctx *ctx, DevOperator &op) {
-    if (op.p2p) return sb_p2p_wait_arrived(ctx, op, ctx->stream);
     SB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+    if (op.p2p) return sb_p2p_wait_arrived(ctx, op, ctx->stream);
     return 0;
 }
 
@@ -690,6 +714,7 @@ static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, cons
     const bool has_halo = !op.sends.empty() || !op.recvs.empty();
     const bool halo = has_halo && ctx->apply_mode != 1;
     const bool compute = ctx->apply_mode != 2;
+    if (halo && ctx->detached) SB_FAIL("apply: a detached context has no peer to exchange ghost values with");
     if (halo) {
         // pack + exchange on the comm stream, both overlapped with the interior rows: the comm
         // stream only waits for x to be ready (ev_packed marks that point of the compute stream),
@@ -697,9 +722,9 @@ static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, cons
         SB_CUDA(cudaEventRecord(ctx->ev_packed, ctx->stream));
         SB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_packed, 0));
         if (op.p2p) {
-            // peer-memory path: the pack kernel stores straight into the neighbours' ghost buffers
-            // over NVLink and raises their "arrived" flags; no send buffer, no NCCL rendezvous
-            SB_TRY(sb_p2p_pack_and_signal(ctx, op, x, ctx->comm_stream));
+            // peer-memory path: the pack kernel stores straight into the neighbours' landing areas
+            // over NVLink and raises their "arrived" counters; no send buffer, no NCCL rendezvous
+            SB_TRY(sb_p2p_pack(ctx, op, x, ctx->comm_stream));
         } else {
             if (op.vIndexSize) {
                 ++ctx->launches;
@@ -712,8 +737,8 @@ static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, cons
                                                                                   (float *)op.send_buf);
             }
             SB_TRY(sb_halo_exchange(ctx, op, ctx->comm_stream));
-            SB_CUDA(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
         }
+        SB_CUDA(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
     }
     if (op.merged) {
         // x_ext = [x | ghosts], then one ordinary SpMV over the extended columns
@@ -721,7 +746,9 @@ static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, cons
             SB_CUDA(cudaMemcpyAsync(op.x_ext, x, sizeof(double) * op.n_local_cols, cudaMemcpyDeviceToDevice, ctx->stream));
         if (halo) SB_TRY(wait_halo(ctx, op));
         if (compute) {
-            if (!op.use_double && op.recvSize) {
+            if (op.p2p) {
+                SB_TRY(sb_p2p_gather_ghosts(ctx, op, op.x_ext + op.n_local_cols, ctx->stream));
+            } else if (!op.use_double && op.recvSize) {
                 ++ctx->launches;
                 widen_ghost_kernel<<<(op.recvSize + 255) / 256, 256, 0, ctx->stream>>>(
                     op.recvSize, (const float *)op.ghost_buf, op.x_ext + op.n_local_cols);
@@ -729,7 +756,7 @@ static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, cons
             if (op.wide_offsets) launch_local<EPI, int64_t>(ctx, op, op.x_ext, e);
             else launch_local<EPI, int>(ctx, op, op.x_ext, e);
         }
-        if (halo && op.p2p) SB_TRY(sb_p2p_signal_consumed(ctx, op, ctx->stream));
+        if (halo && op.p2p) SB_TRY(sb_p2p_release(ctx, op, ctx->stream));
         SB_CUDA(cudaGetLastError());
         return 0;
     }
@@ -742,7 +769,7 @@ static int apply_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x, cons
         if (op.wide_offsets) launch_boundary<EPI, int64_t>(ctx, op, x, e);
         else launch_boundary<EPI, int>(ctx, op, x, e);
     }
-    if (halo && op.p2p) SB_TRY(sb_p2p_signal_consumed(ctx, op, ctx->stream));
+    if (halo && op.p2p) SB_TRY(sb_p2p_release(ctx, op, ctx->stream));
     SB_CUDA(cudaGetLastError());
     return 0;
 }

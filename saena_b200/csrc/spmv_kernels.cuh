@@ -431,7 +431,11 @@ spmv_boundary_kernel(int n_brows, const int *__restrict__ brow, const OffT *__re
                      const int *__restrict__ col, const double *__restrict__ val,
                      const int *__restrict__ brow_ptr, const int *__restrict__ bcol,
                      const double *__restrict__ bval, const double *__restrict__ x,
-                     const GhostT *__restrict__ ghost, EpiArgs e) {
+                     const GhostT *__restrict__ ghost, const unsigned long long *__restrict__ epoch, int ghost_stride,
+                     EpiArgs e) {
+    // peer-memory exchange with separate launches (p2p_halo.cu): two landing buffers, the current one follows from
+    // the receiving role's application counter; NCCL path: epoch == nullptr, one typed buffer
+    if (epoch) ghost += (size_t)(epoch[1] & 1ull) * (size_t)ghost_stride;
     spmv_boundary_body<LANES, EPI, OffT, GhostT>(blockIdx.x, n_brows, brow, rowptr, col, val, brow_ptr, bcol, bval, x,
                                                  ghost, e);
 }

@@ -313,10 +313,10 @@ int sb_coarsest_cg(saena_b200_ctx *ctx, const double *rhs, double *u) {
 }
 
 int sb_read_scalars(saena_b200_ctx *ctx) {
-    SB_CUDA(cudaMemcpyAsync(ctx->scalars_host, ctx->scalars, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost,
-                            ctx->stream));
-    SB_CUDA(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    // the halo fault words follow the scalars (common.h): the host learns of a timed-out exchange with the same copy
+    SB_CUDA(cudaMemcpyAsync(ctx->scalars_host, ctx->scalars, (S_COUNT + S_FAULT_WORDS) * sizeof(double),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    return sb_sync_stream(ctx, ctx->stream);
 }
 
 // ---------------------------------------------------------------------------------------------

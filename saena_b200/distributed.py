@@ -56,16 +56,47 @@ def halo_exchange_host(op: Operator, v: np.ndarray) -> np.ndarray:
     return ghost.astype(np.float64)
 
 
-def setup_p2p_halo(ctx) -> bool:
-    """Switch a multi-rank context's halo exchange to NVLink peer memory: all-gather every rank's
-    export blob and import them (collective).  Returns False (and leaves the NCCL path in place)
-    when the context has a single rank."""
+def all_ranks_ok(ok: bool) -> bool:
+    """True when `ok` holds on EVERY rank (one all-reduce): the way a per-rank failure becomes a decision all ranks
+    take together, instead of one rank leaving a collective sequence the others are still in."""
+    import torch
     import torch.distributed as dist
+
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([0 if ok else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item()) == 0
+
+
+def setup_p2p_halo(ctx, log=None) -> bool:
+    """Switch a multi-rank context's halo exchange to NVLink peer memory: all-gather every rank's
+    export blob and import them (collective).  Returns False -- on every rank, with the NCCL path left in
+    place on every rank -- when the context has a single rank or when the export / import failed anywhere."""
+    import torch.distributed as dist
+
+    from .native import NativeError
 
     if ctx.nranks == 1:
         return False
+    err = None
+    try:
+        mine = ctx.p2p_export()
+    except NativeError as e:
+        mine, err = b"", e
     blobs = [None] * ctx.nranks
-    dist.all_gather_object(blobs, ctx.p2p_export())
-    ctx.p2p_import(blobs)
-    dist.barrier()
+    dist.all_gather_object(blobs, mine)
+    ok = err is None and len(mine) > 0 and all(len(b) == len(mine) for b in blobs)
+    if ok:
+        try:
+            ctx.p2p_import(blobs)
+        except NativeError as e:
+            ok, err = False, e
+    if err is not None and log is not None:
+        log(f"[rank {ctx.rank}] peer-memory halo unavailable: {err}")
+    if not all_ranks_ok(ok):     # also the barrier after the import: nobody applies an operator before all are wired
+        try:
+            ctx.p2p_enable(0)
+        except NativeError:
+            pass
+        return False
     return True

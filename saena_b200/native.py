@@ -75,12 +75,16 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_find_eig.argtypes = [vp, i, i, vp, ctypes.c_uint64, i, ctypes.POINTER(ctypes.c_double),
                                       ctypes.POINTER(ctypes.c_int)]
     L.saena_b200_p2p_enable.argtypes = [vp, i]
+    L.saena_b200_fault_status.argtypes = [vp]
+    L.saena_b200_clear_fault.argtypes = [vp]
+    L.saena_b200_set_timeouts.argtypes = [vp, ctypes.c_double, ctypes.c_double]
     L.saena_b200_autotune_halo.argtypes = [vp, i]
     L.saena_b200_halo_choice.argtypes = [vp, i, i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
     solve_args = [vp, vp, vp, i, d, i, i, i, ip, dp, i, ip]
     L.saena_b200_solve_pcg.argtypes = solve_args
     L.saena_b200_solve_pcg_dev.argtypes = solve_args
     L.saena_b200_solve_vcycle.argtypes = solve_args
+    L.saena_b200_solve_smoother.argtypes = solve_args
     L.saena_b200_solve_cg.argtypes = [vp, vp, vp, i, d, ip, dp, i, ip]
     L.saena_b200_matvec.argtypes = [vp, i, i, vp, vp]
     L.saena_b200_residual.argtypes = [vp, i, vp, vp, vp]
@@ -100,6 +104,7 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_graph_replays.restype = ctypes.c_int64
     L.saena_b200_graph_replays.argtypes = [vp]
     L.saena_b200_set_mapping.argtypes = [vp, i, i, i]
+    L.saena_b200_autotune_mapping.argtypes = [vp, i, ctypes.c_double, ip]
     L.saena_b200_set_mapping_deferred.argtypes = [vp, i, i, i]
     L.saena_b200_get_mapping.argtypes = [vp, i, i]
     L.saena_b200_operator_bytes.restype = ctypes.c_int64
@@ -113,10 +118,10 @@ EXPORTED_SYMBOLS = [
     "saena_b200_upload_operator", "saena_b200_upload_band_operator", "saena_b200_upload_level_aux", "saena_b200_upload_level_scale",
     "saena_b200_upload_coarsest",
     "saena_b200_set_coarsest_solver", "saena_b200_set_operator_dense", "saena_b200_sellp_layout", "saena_b200_set_graphs", "saena_b200_finalize",
-    "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_find_eig", "saena_b200_p2p_enable", "saena_b200_autotune_halo", "saena_b200_halo_choice", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_cg",
+    "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_find_eig", "saena_b200_p2p_enable", "saena_b200_fault_status", "saena_b200_clear_fault", "saena_b200_set_timeouts", "saena_b200_autotune_halo", "saena_b200_halo_choice", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_smoother", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
-    "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_time_vcycle", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_graph_replays", "saena_b200_set_mapping", "saena_b200_set_mapping_deferred", "saena_b200_get_mapping",
+    "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_time_vcycle", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_graph_replays", "saena_b200_set_mapping", "saena_b200_autotune_mapping", "saena_b200_set_mapping_deferred", "saena_b200_get_mapping",
     "saena_b200_operator_bytes",
 ]
 
@@ -298,6 +303,17 @@ class Context:
         """2: fused halo kernel (default after p2p_import), 1: peer stores with separate launches, 0: NCCL"""
         self._ck(self._L.saena_b200_p2p_enable(self._h, int(on)))
 
+    def fault_status(self) -> bool:
+        """True once a device-side wait of the halo exchange (or a host wait) of this context has timed out"""
+        return bool(self._L.saena_b200_fault_status(self._h))
+
+    def set_timeouts(self, halo_timeout_ms: float = -1.0, sync_timeout_s: float = 180.0):
+        self._ck(self._L.saena_b200_set_timeouts(self._h, float(halo_timeout_ms), float(sync_timeout_s)))
+
+    def clear_fault(self):
+        """after a timed-out exchange: every rank calls this, then p2p_enable(0) (NCCL) or a new p2p export/import"""
+        self._ck(self._L.saena_b200_clear_fault(self._h))
+
     def autotune_halo(self, reps: int = 10):
         """collective: keep, per operator, the faster of the fused kernel and the separate launches"""
         self._ck(self._L.saena_b200_autotune_halo(self._h, reps))
@@ -341,6 +357,13 @@ class Context:
         rhs = np.ascontiguousarray(rhs, F64)
         u = np.zeros(self.level_rows[0], F64)
         it, hist = self._solve(self._L.saena_b200_solve_vcycle, rhs, u, max_iter, tol, smoother, pre, post)
+        return u, it, hist
+
+    def solve_smoother(self, rhs, max_iter=50, tol=1e-8, smoother="chebyshev", pre=3, post=3):
+        """saena_object::solve_smoother: the smoother alone as a stationary iteration on level 0"""
+        rhs = np.ascontiguousarray(rhs, F64)
+        u = np.zeros(self.level_rows[0], F64)
+        it, hist = self._solve(self._L.saena_b200_solve_smoother, rhs, u, max_iter, tol, smoother, pre, post)
         return u, it, hist
 
     def solve_cg(self, rhs, max_iter=500, tol=1e-8):
@@ -447,6 +470,13 @@ class Context:
 
     def get_mapping(self, level, kind) -> int:
         return int(self._L.saena_b200_get_mapping(self._h, level, kind))
+
+    def autotune_mapping_native(self, reps: int = 10, min_gain: float = 0.03) -> int:
+        """saena_b200_autotune_mapping: the library's own setup-time choice of every operator's row mapping by
+        measurement (collective on several ranks); returns how many operators changed on this rank"""
+        n = ctypes.c_int(0)
+        self._ck(self._L.saena_b200_autotune_mapping(self._h, int(reps), float(min_gain), ctypes.byref(n)))
+        return n.value
 
     def autotune_mapping(self, reps: int = 10, min_gain: float = 0.03):
         """One rank only (setup time, untimed): for every uploaded operator, time the row mappings around the one

@@ -69,15 +69,17 @@ def main():
         dist.barrier()   # no peer is still writing into the arena this upload is about to replace
         ctx.upload_hierarchy(mine)
         # halo transport: the fused kernel (exchange + SpMV in one launch over NVLink peer memory) on
-        # three cases, peer stores with separate launches on two, ncclSend/ncclRecv on one
-        transport = ("fused", "fused", "nccl", "p2p", "fused", "p2p")[case_no % 6]
+        # three cases, peer stores with separate launches on one, ncclSend/ncclRecv on one, and one case where the
+        # even ranks run the fused kernel and the odd ranks the separate launches on the SAME operators (the two
+        # forms speak one hand-shake, csrc/halo_sync.cuh: any mix must work)
+        transport = ("fused", "fused", "nccl", "p2p", "fused", "mixed")[case_no % 6]
         if os.environ.get("SAENA_B200_HALO", "p2p") != "p2p":
             transport = "nccl"
         case_no += 1
         use_p2p = transport != "nccl"
         if use_p2p:
-            setup_p2p_halo(ctx)
-            ctx.p2p_enable(2 if transport == "fused" else 1)
+            assert setup_p2p_halo(ctx), "peer-memory halo could not be set up"
+            ctx.p2p_enable({"fused": 2, "p2p": 1, "mixed": 2 if rank % 2 == 0 else 1}[transport])
             if case_no == 5:
                 # per operator: whichever of the two peer-memory paths measures faster (a mix of both)
                 ctx.autotune_halo(3)
@@ -109,11 +111,13 @@ def main():
                 want = o.matvec(l, KIND_R, v_parts)
                 got = ctx.matvec(l, KIND_R, v_parts[rank])
                 worst[f"{tag}.L{l}.R"] = rel(np.concatenate(gather(got, csz, rank, world)), np.concatenate(want))
-            if transport.startswith("fused") and l <= 1:
-                # every row mapping of the fused kernel (sliced, sub-warp, row-group), A and P; then the
-                # measurement modes (compute only / exchange only) must leave the hand-shake consistent
+            if use_p2p and l <= 1:
+                # every row mapping of the fused kernel (sliced, sub-warp, row-group), A and P -- and of the
+                # separate launches, the streaming mapping included (never fused: it takes the separate launches
+                # whatever the mode); then the measurement modes (compute only / exchange only) must leave the
+                # hand-shake consistent
                 want_a = np.concatenate(o.matvec(l, KIND_A, v_parts))
-                for mp in (100, 1, 4, 16, 32, 256, 0):
+                for mp in (100, 1, 4, 16, 32, 256, -4, 0):
                     ctx.set_mapping(l, KIND_A, mp)
                     got = ctx.matvec(l, KIND_A, v_parts[rank])
                     worst[f"{tag}.L{l}.A.map{mp}"] = rel(np.concatenate(gather(got, sizes, rank, world)), want_a)
@@ -154,6 +158,36 @@ def main():
         if rank == 0:
             print(f"{tag}: pcg iters {it} (oracle {it_o}), history err {herr:.2e}, u err {uerr:.2e}, "
                   f"{replays} V-cycles replayed from a graph", flush=True)
+    # ---- failure detection (the counterpart of the reference's print + MPI_Abort, src/saena_object_solve.cpp:1012-1013):
+    #      rank 0 applies a distributed operator ALONE.  Its wait for the neighbours' ghost values must run into the
+    #      deadline, the call must return an error that names the operator, and after clear_fault + a new import on
+    #      every rank the exchange must give the right answer again.
+    if os.environ.get("SAENA_B200_HALO", "p2p") == "p2p":
+        import time
+        sizes = [h.levels[0].A.M for h in hs]
+        off = np.concatenate(([0], np.cumsum(sizes)))
+        full_v = np.random.default_rng(5).standard_normal(off[-1])
+        v_parts = [full_v[off[i]:off[i + 1]] for i in range(world)]
+        want = np.concatenate(o.matvec(0, KIND_A, v_parts))
+        dist.barrier()
+        ctx.set_timeouts(300.0, 60.0)
+        if rank == 0:
+            t0, msg = time.time(), None
+            try:
+                ctx.matvec(0, KIND_A, v_parts[0])
+            except native.NativeError as e:
+                msg = str(e)
+            assert msg is not None and "timed out" in msg and "level 0 operator A" in msg, msg
+            assert time.time() - t0 < 20.0, "the bounded wait took too long"
+            assert ctx.fault_status()
+            print(f"bounded wait: a lone application returned after {time.time() - t0:.2f} s with: {msg}", flush=True)
+        dist.barrier()
+        ctx.clear_fault()
+        assert setup_p2p_halo(ctx), "peer-memory halo could not be re-armed after a fault"
+        ctx.set_timeouts(5000.0, 180.0)
+        assert not ctx.fault_status()
+        got = ctx.matvec(0, KIND_A, v_parts[rank])
+        worst["after_fault.L0.A"] = rel(np.concatenate(gather(got, sizes, rank, world)), want)
     # ---- the reference's OWN multi-rank layout (tests/golden/*_np{2,4}.npz: per-rank hierarchies exactly as the
     #      reference on `world` MPI ranks laid them out -- shrunk coarse levels, Grid::repart_u plans, float halo --
     #      and its own outputs).  What the drop-in adaptor uploads in a multi-rank run.  Opt-in until its first run
@@ -164,7 +198,7 @@ def main():
         mine = g.hiers[rank]
         dist.barrier()
         ctx.upload_hierarchy(mine)
-        setup_p2p_halo(ctx)
+        assert setup_p2p_halo(ctx), "peer-memory halo could not be set up on the reference's layout"
         ctx.autotune_halo(3)
 
         def apply(name, l, *a):

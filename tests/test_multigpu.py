@@ -29,8 +29,6 @@ def test_distributed_path_matches_multirank_oracle(world):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs on one box (gpurun --gpus 2)")
-@pytest.mark.xfail(strict=False, reason="first GPU run of the reference's own multi-rank layouts (written after the "
-                                        "round's GPU budget was spent); CPU side is green: test_multirank_reference.py")
 @pytest.mark.parametrize("world", [2, 4])
 def test_reference_multirank_layout_on_gpus(world):
     """the per-rank hierarchies exactly as the reference on `world` MPI ranks laid them out (shrunk coarse
@@ -48,8 +46,6 @@ def test_reference_multirank_layout_on_gpus(world):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs on one box (gpurun --gpus 2)")
-@pytest.mark.xfail(strict=False, reason="first NCCL run of the distributed setup (written after the round's GPU budget was "
-                                        "spent); CPU side (gloo) is green: tests/test_dist_setup.py")
 @pytest.mark.parametrize("world,args", [(2, ["poisson", "40", "double"]), (2, ["poisson", "48"]), (4, ["unstructured", "300", "double"])])
 def test_distributed_setup_on_gpus_feeds_the_library(world, args):
     """saena_b200/sa_setup_dist.py over NCCL (what bench.py --n 512 uses on 8 GPUs) = the one-process setup, and the

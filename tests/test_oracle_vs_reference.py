@@ -48,6 +48,26 @@ def test_pcg_iterations_and_history(poisson16):
     check_pcg(it, hist, u, it_ref, hist_ref, u_ref, TOL_HIST)
 
 
+def test_stationary_solvers_match_the_reference(poisson16):
+    """saena_object::solve (stationary V-cycles, :1883-2014) and saena_object::solve_smoother (the smoother alone,
+    :2017-2117): iteration counts equal, histories within 1e-9 while the residual is far from cancellation (both
+    recompute r = A u - rhs every iteration: near convergence that difference loses ~8 digits, so the tail is
+    compared at 1e-6), solutions equal"""
+    s, h = poisson16
+    o = Oracle(h)
+    for name, kw in (("solve_vcycle", dict(max_iter=50, tol=1e-8, smoother="chebyshev", pre=3, post=3)),
+                     ("solve_smoother", dict(max_iter=12, tol=1e-8, smoother="chebyshev", pre=3, post=3)),
+                     ("solve_smoother", dict(max_iter=7, tol=1e-8, smoother="jacobi", pre=2, post=0))):
+        u_ref, it_ref, hist_ref = getattr(s, name)(**kw)
+        u, it, hist = getattr(o, name)(s.rhs(), **kw)
+        assert it == it_ref, (name, it, it_ref)
+        assert len(hist) == len(hist_ref)
+        err = np.abs(hist - hist_ref) / hist_ref
+        head = hist_ref > 1e-5 * hist_ref[0]
+        assert err[head].max() <= TOL_HIST and err.max() <= 1e-6, (name, err)
+        assert rel(u, u_ref) <= 1e-9, (name, rel(u, u_ref))
+
+
 def test_coarsest_cg_direct_solver_option(poisson16):
     s, h = poisson16
     o = Oracle(h, coarsest_cg=True)

@@ -46,9 +46,6 @@ LIB_MP = os.path.join(os.path.dirname(LIB), "libsaena_dropin_mp.so")
 
 
 @pytest.mark.skipif(not os.path.exists(LIB_MP) or _ngpu() < 2, reason="needs libsaena_dropin_mp.so and >= 2 GPUs")
-@pytest.mark.xfail(strict=False, reason="first run of the drop-in on several MPI ranks with GPUs behind it (written after "
-                                        "the round's GPU budget was spent); its upload walk is green on CPU: "
-                                        "tests/test_adaptor_multirank.py")
 @pytest.mark.parametrize("ranks,mx", [(2, 18), (4, 26)])
 def test_public_api_on_several_mpi_ranks_matches_the_multirank_reference(ranks, mx):
     """the reference's driver on `ranks` MPI ranks (multi-process MPI stand-in), one GPU per rank: GPU solve through
@@ -68,8 +65,6 @@ EXE_CPU = os.path.join(os.path.dirname(LIB), "poisson_mp")
 
 
 @pytest.mark.skipif(not (os.path.exists(EXE_B200) and os.path.exists(EXE_CPU)), reason="driver executables not built")
-@pytest.mark.xfail(strict=False, reason="first GPU run of the reference's unmodified driver with the drop-in linked "
-                                        "(written after the round's GPU budget was spent)")
 @pytest.mark.parametrize("ranks", [1, 2])
 def test_the_reference_driver_itself_with_the_dropin_linked(ranks, tmp_path):
     """experiments/Poisson.cpp, unmodified, linked per INTEGRATION.md: its solve_pCG calls run on the GPU(s), its

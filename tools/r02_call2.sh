@@ -1,0 +1,26 @@
+# Round 2, the 2-GPU call (gpurun --gpus 2 --timeout 1500 -- 'bash tools/r02_call2.sh'): the unified halo hand-shake
+# (fused / separate launches / mixed / NCCL, bounded waits with a fault injection), the reference's own 2-rank layout,
+# the distributed setup over NCCL, the drop-in on 2 MPI ranks, then bench at N=2 and the 512^3 rehearsal at 256^3.
+mkdir -p gpurun_out
+set -x
+nvidia-smi -L
+nvidia-smi topo -m | head -6
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29556 tests/multigpu_check.py > gpurun_out/r02_mg2.log 2>&1; echo "multigpu_check exit $?"
+grep -E "MULTIGPU_OK|FAILED|bounded wait|Error|error" gpurun_out/r02_mg2.log | head -12; tail -4 gpurun_out/r02_mg2.log | cut -c1-300
+timeout 900 python -m pytest tests/test_multigpu.py tests/test_public_api_dropin.py -q -m gpu -k "not distributed_path" > gpurun_out/r02_pytest_2gpu.log 2>&1; tail -15 gpurun_out/r02_pytest_2gpu.log | cut -c1-400
+SAENA_BENCH_AB=1 SAENA_BENCH_VERBOSE=1 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 5 --no-cpu-baseline 2> gpurun_out/r02_bench_n2.err | tee gpurun_out/r02_bench_n2.json | cut -c1-300
+echo "bench exit $?"; grep -E "rank|Error|error|FAILED|fallback" gpurun_out/r02_bench_n2.err | tail -8
+python - <<'P'
+import json
+for l in open("gpurun_out/r02_bench_n2.json"):
+    if l.startswith('{'):
+        d=json.loads(l); print(d['n_gpus'], d['ms_per_step'], d['iterations'], d.get('halo_transport'), d.get('halo_fallback')); print(d['vcycle_graph']); print(d['vcycle_levels']); print(d.get('halo_overlap')); print(d.get('row_mappings_changed_by_setup_autotune'))
+P
+SAENA_BENCH_VERBOSE=1 SAENA_BENCH_VERIFY=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 2 --n 256 --steps 5 --no-cpu-baseline --dist-setup on 2> gpurun_out/r02_bench_256_dist_n2.err | tee gpurun_out/r02_bench_256_dist_n2.json | cut -c1-300
+echo "dist-setup bench exit $?"; grep -E "level |setup|Error|error" gpurun_out/r02_bench_256_dist_n2.err | tail -30
+python - <<'P'
+import json
+for l in open("gpurun_out/r02_bench_256_dist_n2.json"):
+    if l.startswith('{'):
+        d=json.loads(l); print(d['n_gpus'], d['ms_per_step'], d['iterations'], d['rel_residual'], d['true_rel_residual'], d.get('verify'))
+P
