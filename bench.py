@@ -131,9 +131,11 @@ def cpu_reference_solve_multirank(reps: int, warmup: int, ranks: int, mx: int):
         shutil.rmtree(out, ignore_errors=True)
     sec = max(float(p["sec_per_solve"][0]) for p in parts)   # max over ranks, as Poisson.cpp:216-246 reports
     iters = int(parts[0]["iters"][0])
+    setup_s = max(float(p["setup_s"][0]) for p in parts) if all("setup_s" in p.files for p in parts) else None
     n = (mx - 2) ** 3
     # the other half of BASELINE.json's metric on the CPU: level-0 SpMV as saena_object::profile_matvecs times it
-    # (5 applications, max over ranks), in the algorithmic bytes of SURVEY 8d: 12 nnz + 20 M, nnz = 7 n - 6 (mx-2)^2
+    # (20 applications after a warm-up, max over ranks), in the algorithmic bytes of SURVEY 8d: 12 nnz + 20 M,
+    # nnz = 7 n - 6 (mx-2)^2; at 96^3 / 128^3 the operator (130 / 310 MB with its vectors) is beyond the host's caches
     spmv_gbs = None
     if all("sec_per_matvec0" in p.files for p in parts):
         mv = max(float(p["sec_per_matvec0"][0]) for p in parts)
@@ -142,19 +144,34 @@ def cpu_reference_solve_multirank(reps: int, warmup: int, ranks: int, mx: int):
     what = (f"the reference's own solve_pCG (oracle/_ref/libsaena_ref_mp.so = unmodified paralab/Saena sources, -Ofast) "
             f"on {ranks} MPI ranks = {ranks} host cores (multi-process MPI stand-in over Unix sockets, oracle/ref_shim_mp), "
             f"3D Poisson {mx - 2}^3 = {n} unknowns (laplacian3D mx={mx}), same options; {reps} solves, {iters} "
-            f"iterations each, max over ranks; setup + warm-up not timed (whole run {wall:.0f} s)")
+            f"iterations each, max over ranks; the reference's own setup ({setup_s if setup_s is None else round(setup_s, 1)} s) "
+            f"and the warm-up are not timed (whole run {wall:.0f} s)")
     return dict(value=n / sec / 1e6, unit=UNIT, cores=ranks, kind="reference", sample=what,
-                spmv_level0_GBs=spmv_gbs), sec, iters, n
+                spmv_level0_GBs=spmv_gbs, unknowns=n, setup_s=setup_s, ms_per_solve=sec * 1e3), sec, iters, n
 
 
-def cpu_reference_solve(reps: int, warmup: int = 0, mx: int = CPU_SAMPLE_MX):
+def cpu_sample_mx(ranks: int, arm: bool) -> int:
+    """laplacian3D(mx) size of the CPU sample: what the reference's own HOST SETUP lets a bounded run afford (the setup
+    is what costs: 40 s for 96^3 on 8 ranks in this image, the solves are 0.9 s each).  The reference arm
+    (--impl reference) takes the larger sample; the in-run cpu_baseline of the default bench run the smaller one."""
+    if os.environ.get("SAENA_BENCH_CPU_MX_MP"):
+        return int(os.environ["SAENA_BENCH_CPU_MX_MP"])
+    if ranks >= 16:
+        return 130 if arm else 98     # 128^3 = 2.1 M unknowns / 96^3 = 0.88 M
+    if ranks >= 8:
+        return 98 if arm else 66
+    return 66
+
+
+def cpu_reference_solve(reps: int, warmup: int = 0, mx: int = CPU_SAMPLE_MX, arm: bool = False):
     from oracle import ref
     n = (mx - 2) ** 3
     ranks = min(host_cores(), int(os.environ.get("SAENA_BENCH_CPU_RANKS", 32)))
     if ref.mp_available() and ranks > 1:
         try:
-            # a larger sample than the one-rank arm: 64^3 unknowns keep >= 8 k rows per rank at 32 ranks
-            return cpu_reference_solve_multirank(reps, warmup, ranks, int(os.environ.get("SAENA_BENCH_CPU_MX_MP", 66)))
+            # far larger samples than the one-rank arm can set up: 96^3 / 128^3 unknowns -- every rank's share of every
+            # fine level is beyond its core's caches, as at the bench's own 256^3
+            return cpu_reference_solve_multirank(reps, warmup, ranks, cpu_sample_mx(ranks, arm))
         except Exception as e:   # fall back to the one-rank build below
             log(f"[reference arm] multi-rank run failed ({e!r}); falling back to one rank")
     if ref.available():
@@ -189,12 +206,25 @@ def cpu_reference_solve(reps: int, warmup: int = 0, mx: int = CPU_SAMPLE_MX):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    base, sec, iters, n = cpu_reference_solve(max(args.steps, 1), args.warmup)
+    base, sec, iters, n = cpu_reference_solve(max(args.steps, 1), args.warmup, arm=True)
+    # the trend with the problem size (one more, smaller sample; SAENA_BENCH_CPU_SWEEP=0 skips it): the CPU's
+    # unknowns/s is nearly flat in n, so the sample stands for the 256^3 workload it cannot set up in a bounded run
+    sweep = [{"unknowns": n, "value": base["value"], "ms_per_solve": sec * 1e3, "iterations": iters}]
+    if base.get("cores", 1) > 1 and os.environ.get("SAENA_BENCH_CPU_SWEEP", "1") != "0" and n > 64 ** 3:
+        try:
+            b2, s2, i2, n2 = cpu_reference_solve_multirank(3, 1, base["cores"], 66)
+            sweep.insert(0, {"unknowns": n2, "value": b2["value"], "ms_per_solve": s2 * 1e3, "iterations": i2})
+        except Exception as e:
+            log(f"[reference arm] size sweep point failed: {e!r}")
+    base["size_sweep"] = sweep
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"3D 7-point Poisson AMG-PCG, bounded sample {round(n ** (1 / 3))}^3 unknowns of the "
                                    f"256^3 workload, {base['cores']} host core(s)",
+                       "same_config_as_gpu_arm": False,
+                       "why_a_sample": "the reference's own host setup for 256^3 takes the better part of an hour; "
+                                       "throughput in unknowns/s is compared, see cpu_baseline.size_sweep for its trend in n",
                        "options": "data/options006_poisson.xml values"},
             "iterations": iters, "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -279,8 +309,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("SAENA_BENCH_N", 256)),
-                    help="unknowns per dimension (256 = BASELINE.json configs[1])")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=int(os.environ.get("SAENA_BENCH_N", 256)),
+                    help="unknowns per dimension (256 = BASELINE.json configs[1]); under torchrun write --size (its own "
+                         "parser reads a bare --n as an abbreviation of --nnodes / --nproc-per-node)")
     ap.add_argument("--workload", default="poisson3d", choices=["poisson3d", "unstructured2d"],
                     help="poisson3d = BASELINE.json configs[1] (the bench line); unstructured2d = configs[4]'s synthetic "
                          "2-D Helmholtz-like matrix with irregular rows (same solve, same JSON keys, its own metric name)")

@@ -105,6 +105,8 @@ def main():
     # SAENA_MP_FLOAT_LEVEL: the options file's float_level (0 = the drivers' value: ghost values travel as float on
     # every level; >= the level count: every halo in double)
     opts = ref.RefOptions(float_level=int(os.environ.get("SAENA_MP_FLOAT_LEVEL", "0")))
+    import time
+    t_setup = time.perf_counter()
     if what == "poisson":
         s = ref.RefSolver.poisson(mx, opts)
     elif what == "unstructured":
@@ -117,6 +119,7 @@ def main():
         s = ref.RefSolver.from_coo(n, row[keep], col[keep], val[keep], unstructured2d_rhs(n)[lo:hi], opts, rhs_offset=lo)
     else:
         raise SystemExit(f"unknown workload {what}")
+    setup_s = time.perf_counter() - t_setup   # matrix generation + the reference's AMG setup on this rank
     if os.environ.get("SAENA_MP_ADAPTOR_CHECK"):
         check_adaptor_upload(L, s, rank, size, out)
         before = L.rec_destroys()
@@ -154,8 +157,11 @@ def main():
             s.time_solve_pcg(1)
         L.sref_barrier()   # MPI_Barrier before the timed region, as experiments/Poisson.cpp:216-246
         res["sec_per_solve"] = np.array([s.time_solve_pcg(reps) / reps])
-        s.time_matvec(0, 2)
-        res["sec_per_matvec0"] = np.array([s.time_matvec(0, 5)])   # the reference's profile_matvecs figure, level 0
+        s.time_matvec(0, 3)
+        # the reference's profile_matvecs figure for level 0 (src/saena_object.cpp:618-638 times 5 applications; 20 here,
+        # after a warm-up, so that the figure is a bandwidth and not the first touches of a cache-resident vector)
+        res["sec_per_matvec0"] = np.array([s.time_matvec(0, 20)])
+        res["setup_s"] = np.array([setup_s])
     os.makedirs(out, exist_ok=True)
     np.savez(os.path.join(out, f"rank{rank}.npz"), **res)
     s.close()

@@ -631,40 +631,68 @@ int MPI_Op_free(MPI_Op *op) { *op = MPI_OP_NULL; return MPI_SUCCESS; }
 /* ------------------------------------------------------------------ collectives */
 enum { T_BARRIER = -10, T_BCAST = -11, T_REDUCE = -12, T_GATHER = -13, T_SCATTER = -14, T_ALLTOALL = -15, T_SCAN = -16 };
 
+/* Barrier / Bcast / Reduce walk a binomial tree (log2(size) message latencies instead of size): the CPU arm of the
+ * bench runs the reference on 16-32 ranks, where a root that talks to every rank in turn would tax each of the four
+ * dot products per PCG iteration.  Reductions stay deterministic: a node combines contiguous rank ranges in rank
+ * order (lower ranks' partial on the left), only the association differs from a left-to-right sum. */
+static void tree_up(MPI_Comm comm, int tag, char *acc, char *tmp, size_t n, int count, MPI_Datatype dt, MPI_Op op) {
+    /* partial of ranks [rank, rank + span) ends in `acc` on the lowest rank of the range; rank 0 ends with everything */
+    Comm *c = C(comm);
+    const int size = c->size, rank = c->rank;
+    for (int mask = 1; mask < size; mask <<= 1) {
+        if (rank & mask) { csend(c, rank - mask, tag, acc, n); return; }
+        if (rank + mask < size) {
+            crecv(comm, rank + mask, tag, tmp, n);
+            c = C(comm);
+            if (n && op != MPI_OP_NULL) { reduce_local(acc, tmp, count, dt, op); memcpy(acc, tmp, n); }
+        }
+    }
+}
+static void tree_down(MPI_Comm comm, int tag, void *buf, size_t n) {   /* from rank 0 to everybody */
+    Comm *c = C(comm);
+    const int size = c->size, rank = c->rank;
+    int mask = 1;
+    while (mask < size) {
+        if (rank & mask) { crecv(comm, rank - mask, tag, buf, n); c = C(comm); break; }
+        mask <<= 1;
+    }
+    for (mask >>= 1; mask > 0; mask >>= 1)
+        if (rank + mask < size) csend(c, rank + mask, tag, buf, n);
+}
 int MPI_Barrier(MPI_Comm comm) {
     Comm *c = C(comm);
-    char z = 0;
+    char z = 0, t = 0;
     if (c->size == 1) return MPI_SUCCESS;
-    if (c->rank == 0) {
-        for (int i = 1; i < c->size; ++i) { crecv(comm, i, T_BARRIER, &z, 1); c = C(comm); }
-        for (int i = 1; i < c->size; ++i) csend(c, i, T_BARRIER, &z, 1);
-    } else {
-        csend(c, 0, T_BARRIER, &z, 1);
-        crecv(comm, 0, T_BARRIER, &z, 1);
-    }
+    tree_up(comm, T_BARRIER, &z, &t, 1, 1, MPI_BYTE, MPI_OP_NULL);
+    tree_down(comm, T_BARRIER, &z, 1);
     return MPI_SUCCESS;
 }
 int MPI_Bcast(void *buf, int count, MPI_Datatype dt, int root, MPI_Comm comm) {
     Comm *c = C(comm);
     const size_t n = (size_t)count * dt_size(dt);
     if (c->size == 1) return MPI_SUCCESS;
-    if (c->rank == root) { for (int i = 0; i < c->size; ++i) if (i != root) csend(c, i, T_BCAST, buf, n); }
-    else crecv(comm, root, T_BCAST, buf, n);
+    if (root != 0) {   /* hand the payload to rank 0 first, then the tree */
+        if (c->rank == root) csend(c, 0, T_BCAST, buf, n);
+        else if (c->rank == 0) crecv(comm, root, T_BCAST, buf, n);
+    }
+    tree_down(comm, T_BCAST, buf, n);
     return MPI_SUCCESS;
 }
 int MPI_Reduce(const void *s, void *r, int count, MPI_Datatype dt, MPI_Op op, int root, MPI_Comm comm) {
     Comm *c = C(comm);
     const size_t n = (size_t)count * dt_size(dt);
     const void *mine = s == MPI_IN_PLACE ? r : s;
-    if (c->rank != root) { csend(c, root, T_REDUCE, mine, n); return MPI_SUCCESS; }
-    /* combine in rank order: acc = c_0 op c_1 op ... (deterministic; `in` = lower ranks' partial) */
     char *acc = (char *)malloc(n ? n : 1), *tmp = (char *)malloc(n ? n : 1);
-    for (int i = 0; i < c->size; ++i) {
-        if (i == root) memcpy(tmp, mine, n); else { crecv(comm, i, T_REDUCE, tmp, n); c = C(comm); }
-        if (i == 0) memcpy(acc, tmp, n);
-        else { reduce_local(acc, tmp, count, dt, op); memcpy(acc, tmp, n); }
+    memcpy(acc, mine, n);
+    if (c->size > 1) tree_up(comm, T_REDUCE, acc, tmp, n, count, dt, op);
+    c = C(comm);
+    if (root == 0) {
+        if (c->rank == 0) memcpy(r, acc, n);
+    } else if (c->rank == 0) {
+        csend(c, root, T_REDUCE, acc, n);
+    } else if (c->rank == root) {
+        crecv(comm, 0, T_REDUCE, r, n);
     }
-    memcpy(r, acc, n);
     free(acc); free(tmp);
     return MPI_SUCCESS;
 }

@@ -5,7 +5,7 @@
 N=${1:-8}; n=${2:-512}; shift; shift
 set -x
 SAENA_BENCH_VERBOSE=1 SAENA_BENCH_NO_AB=1 SAENA_BENCH_VERIFY=1 timeout 1400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
-  --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus $N --n $n --steps 5 --no-cpu-baseline "$@" \
+  --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus $N --size $n --steps 5 --no-cpu-baseline "$@" \
   2> gpurun_out/bench_${n}_n${N}.err | tee gpurun_out/bench_${n}_n${N}.json | cut -c1-400
 echo "bench exit $?"
 grep -E "level |aggregation|RAP|setup|Error|error" gpurun_out/bench_${n}_n${N}.err | tail -40
