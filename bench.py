@@ -302,6 +302,19 @@ def verify_properties(ctx, hier, rank, world):
     return out
 
 
+def nvlink_counters(device: int):
+    """cumulative NVLink data counters of one GPU, summed over its links, in KiB: (tx, rx); None if unavailable"""
+    import re
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(device)], capture_output=True, text=True,
+                             timeout=20).stdout
+        tx = sum(int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
+        rx = sum(int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
+        return (tx, rx) if ("Data Tx" in out) else None
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -709,6 +722,22 @@ def main():
                     "transport": halo_transport,
                     "ghost_values_per_rank": int(hier.levels[0].A.col_remote_size),
                     "ghost_dtype": "f64" if hier.levels[0].A.use_double else "f32 (float_level 0)"}
+        if world > 1 and diag_error is None and os.environ.get("SAENA_BENCH_NVLINK"):
+            # NVLink evidence for the fused compute + exchange kernel: the GPU's own link counters around 500
+            # applications of the level-0 operator (every application is one exchange); expected = what the plan sends
+            apps = 500
+            barrier()
+            c0 = nvlink_counters(local)
+            ctx.time_matvec(0, KIND_A, apps)
+            barrier()
+            c1 = nvlink_counters(local)
+            sent = int(hier.levels[0].A.vIndexSize) * 8   # doubles on the wire (rounded through float by the sender)
+            if c0 and c1:
+                halo["nvlink_rank0"] = {"applications": apps, "tx_KiB": c1[0] - c0[0], "rx_KiB": c1[1] - c0[1],
+                                        "tx_bytes_per_application": (c1[0] - c0[0]) * 1024 / apps,
+                                        "rx_bytes_per_application": (c1[1] - c0[1]) * 1024 / apps,
+                                        "payload_bytes_sent_per_application_by_plan": sent,
+                                        "source": "nvidia-smi nvlink -gt d, summed over the links of this rank's GPU"}
     except native.NativeError as e:
         diag_error = diag_error or f"per-level V-cycle / halo timing: {e}"
         log(f"[rank {rank}] per-level V-cycle / halo timing: {e}")

@@ -257,6 +257,12 @@ int saena_b200_time_matvec_parts(saena_b200_ctx *ctx, int level, int kind, int r
  * as they lie): fused != 0 through the fused halo kernel, else the separate interior + boundary kernels */
 int saena_b200_time_matvec_compute_only(saena_b200_ctx *ctx, int level, int kind, int fused, int reps, int do_flush,
                                         float *ms_out);
+/* Measurement behind a design decision (one rank): the V-cycle's residual + restriction on `level` as the solve
+ * path's two kernels (res = A u - rhs written, then R res) against ONE kernel that scatters every fine residual
+ * through its row of P with FP64 atomics and never writes res (csrc/fused_restrict.cu).  Median ms of `reps`
+ * launches each and the relative 2-norm difference of the two coarse vectors. */
+int saena_b200_time_residual_restrict(saena_b200_ctx *ctx, int level, const double *u, const double *rhs, int reps,
+                                      float *ms_two_kernels, float *ms_fused, double *rel_diff);
 int saena_b200_timer_start(saena_b200_ctx *ctx);
 /* ms per V-cycle entered at `level` from a zero iterate (reps back-to-back, eager, collective over
  * the ranks); the difference between consecutive levels is one level's cost inside a solve */

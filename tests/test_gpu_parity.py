@@ -409,3 +409,22 @@ def test_cuda_vs_compiled_reference_same_process_same_hierarchy(mx):
     finally:
         ctx.close()
         s.close()
+
+
+def test_fused_residual_restrict_measurement_kernel_matches_the_two_kernels():
+    """csrc/fused_restrict.cu (the measurement behind 'restriction fused with the residual'): the scatter form with
+    FP64 atomics gives the solve path's res_coarse = R (A u - rhs) within the per-operator tolerance"""
+    g = Golden(GOLDEN[1])
+    ctx = Context()
+    rng = np.random.default_rng(21)
+    try:
+        ctx.upload_hierarchy(g.hier)
+        for l, lv in enumerate(g.hier.levels[:-1]):
+            ctx.set_mapping(l, KIND_A, 100)
+            u, b = rng.uniform(-1, 1, lv.A.M), rng.uniform(-1, 1, lv.A.M)
+            t2, t1, diff = ctx.time_residual_restrict(l, u, b, 3)
+            assert diff <= TOL_OP and t1 > 0 and t2 > 0, (l, diff)
+            want = Oracle(g.hier).matvec(l, KIND_R, Oracle(g.hier).residual(l, u, b))
+            assert rel(ctx.matvec(l, KIND_R, ctx.residual(l, u, b)), want) <= TOL_OP
+    finally:
+        ctx.close()

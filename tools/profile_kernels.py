@@ -1,5 +1,7 @@
-"""Small driver for `ncu --set full`: builds the bench hierarchy (256^3 by default), uploads it and
-runs two one-iteration PCG solves (= 2 x 2 V-cycles), nothing else.  See tools/profile_full.sh."""
+"""Small driver for `ncu --set full`: builds the bench hierarchy (256^3 by default), uploads it, lets the library pick
+the row mappings by measurement as bench.py does, then -- between cudaProfilerStart/Stop, so that
+`ncu --profile-from-start off` sees nothing else -- runs ONE one-iteration PCG solve: 2 V-cycles (the first eager or
+captured, every kernel of every level), the level-0 SpMV, the dots and the Krylov updates.  See tools/r02_call5.sh."""
 import sys
 
 sys.path.insert(0, ".")
@@ -15,9 +17,16 @@ del dh
 torch.cuda.empty_cache()
 ctx = native.Context()
 ctx.upload_hierarchy(h)
+if "--no-autotune" not in sys.argv:
+    ctx.autotune_mapping_native(10, 0.03)
+ctx.set_graphs(False)   # eager launches: every kernel is its own ncu result, in V-cycle order
 rhs = torch.from_numpy(poisson3d_rhs(n)).cuda()
 u = torch.zeros_like(rhs)
-for _ in range(2):
-    it, hist = ctx.solve_pcg_dev(rhs.data_ptr(), u.data_ptr(), max_iter=1, tol=1e-8)
-print("ok", it, hist)
+it, hist = ctx.solve_pcg_dev(rhs.data_ptr(), u.data_ptr(), max_iter=1, tol=1e-8)   # warm
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+it, hist = ctx.solve_pcg_dev(rhs.data_ptr(), u.data_ptr(), max_iter=1, tol=1e-8)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("ok", it, hist, [(l, ctx.get_mapping(l, 0), ctx.get_mapping(l, 1), ctx.get_mapping(l, 2)) for l in range(len(h.levels))])
 ctx.close()
