@@ -206,6 +206,20 @@ int saena_b200_halo_choice(const saena_b200_ctx *ctx, int level, int kind, float
 int saena_b200_find_eig(saena_b200_ctx *ctx, int level, int max_iter, const double *start, uint64_t seed, int store,
                         double *eig_out, int *iters_out);
 
+/* ---- next to the solve path: the Galerkin product's SpGEMM on the device ----------
+ * C = A B for CSR operands (64-bit row offsets, int32 columns, FP64 values), all pointers DEVICE pointers, work on
+ * the default stream.  What saena_object::triple_mat_mult (src/saena_object_setup2.cpp:361) computes as R (A P)
+ * through the matmat machinery of src/saena_object_setup_matmat.cpp:27-1160 (innermost product: MKL's
+ * mkl_dcsrmultcsr, :214-218).  Two calls: symbolic fills c_rowptr[M + 1] and returns nnz(C); the caller allocates
+ * c_col / c_val of that size and calls numeric, which writes every row with ascending columns.  A is M x K, B is
+ * K x N.  Row-wise Gustavson with per-row accumulators chosen by row size (csrc/spgemm.cu).  No context is needed;
+ * errors are reported through saena_b200_last_error(NULL). */
+int saena_b200_spgemm_symbolic(int M, int K, int N, const int64_t *a_rowptr, const int32_t *a_col,
+                               const int64_t *b_rowptr, const int32_t *b_col, int64_t *c_rowptr, int64_t *nnz_c);
+int saena_b200_spgemm_numeric(int M, int K, int N, const int64_t *a_rowptr, const int32_t *a_col, const double *a_val,
+                              const int64_t *b_rowptr, const int32_t *b_col, const double *b_val,
+                              const int64_t *c_rowptr, int32_t *c_col, double *c_val);
+
 /* ---- solvers -----------------------------------------------------------------------------
  * rhs / u are this rank's block (grids[0].A->M entries).  u is overwritten (zero initial
  * guess, as the reference does: saena_object_solve.cpp:2482).  `iters` receives the count

@@ -104,6 +104,8 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_graph_replays.restype = ctypes.c_int64
     L.saena_b200_graph_replays.argtypes = [vp]
     L.saena_b200_set_mapping.argtypes = [vp, i, i, i]
+    L.saena_b200_spgemm_symbolic.argtypes = [i, i, i, vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int64)]
+    L.saena_b200_spgemm_numeric.argtypes = [i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.saena_b200_time_residual_restrict.argtypes = [vp, i, vp, vp, i, ctypes.POINTER(ctypes.c_float),
                                                     ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
     L.saena_b200_autotune_mapping.argtypes = [vp, i, ctypes.c_double, ip]
@@ -123,7 +125,7 @@ EXPORTED_SYMBOLS = [
     "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_find_eig", "saena_b200_p2p_enable", "saena_b200_fault_status", "saena_b200_clear_fault", "saena_b200_set_timeouts", "saena_b200_autotune_halo", "saena_b200_halo_choice", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_smoother", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
-    "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_time_vcycle", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_graph_replays", "saena_b200_set_mapping", "saena_b200_time_residual_restrict", "saena_b200_autotune_mapping", "saena_b200_set_mapping_deferred", "saena_b200_get_mapping",
+    "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_time_vcycle", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_graph_replays", "saena_b200_set_mapping", "saena_b200_spgemm_symbolic", "saena_b200_spgemm_numeric", "saena_b200_time_residual_restrict", "saena_b200_autotune_mapping", "saena_b200_set_mapping_deferred", "saena_b200_get_mapping",
     "saena_b200_operator_bytes",
 ]
 
@@ -173,6 +175,33 @@ def sellp_layout(rowptr: np.ndarray):
     if L.saena_b200_sellp_layout(M, _vp(rp), _vp(perm), _vp(sp)):
         raise RuntimeError("saena_b200_sellp_layout failed")
     return perm[:n_slots], sp
+
+
+def spgemm_csr(M: int, K: int, N: int, a_rowptr, a_col, a_val, b_rowptr, b_col, b_val):
+    """C = A B on the device (saena_b200_spgemm_symbolic / _numeric, csrc/spgemm.cu).  Operands: torch CUDA tensors --
+    int64 row offsets, int32 columns, float64 values, contiguous.  Returns (c_rowptr int64[M + 1], c_col int32, c_val
+    float64), every row with ascending columns.  torch is only the owner of the buffers here: the products are the
+    library's kernels on raw device pointers."""
+    import torch
+    L = load_library()
+    for t, dt in ((a_rowptr, torch.int64), (a_col, torch.int32), (a_val, torch.float64), (b_rowptr, torch.int64),
+                  (b_col, torch.int32), (b_val, torch.float64)):
+        if not (t.is_cuda and t.dtype == dt and t.is_contiguous()):
+            raise ValueError("spgemm_csr: operands must be contiguous CUDA tensors (int64 offsets, int32 columns, float64 values)")
+    dev = a_val.device
+    with torch.cuda.device(dev):
+        torch.cuda.current_stream().synchronize()   # the kernels run on the default stream
+        c_rowptr = torch.empty(M + 1, dtype=torch.int64, device=dev)
+        nnz = ctypes.c_int64(0)
+        if L.saena_b200_spgemm_symbolic(M, K, N, a_rowptr.data_ptr(), a_col.data_ptr(), b_rowptr.data_ptr(), b_col.data_ptr(),
+                                        c_rowptr.data_ptr(), ctypes.byref(nnz)):
+            raise NativeError(L.saena_b200_last_error(None).decode())
+        c_col = torch.empty(nnz.value, dtype=torch.int32, device=dev)
+        c_val = torch.empty(nnz.value, dtype=torch.float64, device=dev)
+        if L.saena_b200_spgemm_numeric(M, K, N, a_rowptr.data_ptr(), a_col.data_ptr(), a_val.data_ptr(), b_rowptr.data_ptr(),
+                                       b_col.data_ptr(), b_val.data_ptr(), c_rowptr.data_ptr(), c_col.data_ptr(), c_val.data_ptr()):
+            raise NativeError(L.saena_b200_last_error(None).decode())
+    return c_rowptr, c_col, c_val
 
 
 class Context:

@@ -34,6 +34,7 @@ plumbing for the setup only; nothing in the solve path imports this module.
 from __future__ import annotations
 
 import math
+import os
 import sys
 import time
 from dataclasses import dataclass
@@ -102,9 +103,40 @@ def _coalesce(n_rows, n_cols, row, col, val) -> _Csr:
     return _Csr(n_rows, n_cols, uk // n_cols, uk % n_cols, out)
 
 
-def _spgemm(A: _Csr, B: _Csr, chunk_products: int = 300_000_000) -> _Csr:
-    """C = A B by expand / sort / compress, in row chunks bounded by the number of products"""
+# "torch" until the device SpGEMM has passed tests/test_zzz_spgemm_gpu.py on a B200 (nothing lands on the bench's
+# default path before it has run on a GPU), "native" from then on
+SPGEMM_DEFAULT = "torch"
+
+
+def _native_spgemm_enabled(dev) -> bool:
+    """SAENA_SETUP_SPGEMM=native: the library's own SpGEMM (csrc/spgemm.cu) does the products on a CUDA
+    device; =torch: the tensor-op route below (the CPU path, and the A/B).  The default is set by SPGEMM_DEFAULT."""
+    return dev.type == "cuda" and os.environ.get("SAENA_SETUP_SPGEMM", SPGEMM_DEFAULT) != "torch"
+
+
+def _spgemm_native(A: _Csr, B: _Csr) -> _Csr:
+    """C = A B with the hand-written device kernels of libsaena_b200.so (saena_b200_spgemm_symbolic / _numeric)"""
+    from . import native
     dev = A.val.device
+
+    def csr_arrays(M: _Csr):
+        rp = torch.zeros(M.n_rows + 1, dtype=torch.int64, device=dev)
+        rp[1:] = torch.cumsum(M.counts(), 0)
+        return rp, M.col.to(torch.int32).contiguous(), M.val.contiguous()
+
+    a_rp, a_col, a_val = csr_arrays(A)
+    b_rp, b_col, b_val = csr_arrays(B)
+    c_rp, c_col, c_val = native.spgemm_csr(A.n_rows, A.n_cols, B.n_cols, a_rp, a_col, a_val, b_rp, b_col, b_val)
+    row = torch.repeat_interleave(torch.arange(A.n_rows, device=dev), c_rp[1:] - c_rp[:-1])
+    return _Csr(A.n_rows, B.n_cols, row, c_col.to(torch.int64), c_val)
+
+
+def _spgemm(A: _Csr, B: _Csr, chunk_products: int = 300_000_000) -> _Csr:
+    """C = A B: the library's device SpGEMM on CUDA; on the CPU (and for SAENA_SETUP_SPGEMM=torch) expand / sort /
+    compress with tensor ops, in row chunks bounded by the number of products"""
+    dev = A.val.device
+    if _native_spgemm_enabled(dev) and A.n_rows < 2 ** 31 and B.n_cols < 2 ** 31 - 1:
+        return _spgemm_native(A, B)
     b_counts = B.counts()
     b_ptr = torch.zeros(B.n_rows + 1, dtype=torch.int64, device=dev)
     b_ptr[1:] = torch.cumsum(b_counts, 0)
@@ -158,7 +190,8 @@ def _galerkin(R: _Csr, A: _Csr, P: _Csr, dense_budget_bytes: float = 48e9) -> _C
     nc = P.n_cols
     dense_bytes = 8.0 * A.n_rows * nc
     avg_prod_per_row = (A.nnz / max(A.n_rows, 1)) * (P.nnz / max(P.n_rows, 1))
-    if A.val.is_cuda and 2 * dense_bytes <= dense_budget_bytes and avg_prod_per_row > 4 * nc:
+    if A.val.is_cuda and not _native_spgemm_enabled(A.val.device) and 2 * dense_bytes <= dense_budget_bytes \
+            and avg_prod_per_row > 4 * nc:
         Pd = torch.zeros(P.n_rows, nc, dtype=torch.float64, device=A.val.device)
         Pd[P.row, P.col] = P.val
         AP = torch.sparse.mm(_to_torch_csr(A), Pd)

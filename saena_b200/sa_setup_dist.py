@@ -409,6 +409,9 @@ def _prefer_dense(comm: Comm, A: DCsr, A_x: _Csr, P: DCsr, P_ext: _Csr, nc: int)
     """Which of the two routes of galerkin_dist is cheaper for the slowest rank.  On the CPU (tests) only
     sa_setup._galerkin's rule on small levels, so that both routes stay exercised."""
     dev = A.val.device
+    from . import sa_setup
+    if sa_setup._native_spgemm_enabled(dev):
+        return False          # the library's device SpGEMM takes every level (same environment on every rank)
     if dev.type != "cuda":
         a_nnz, p_nnz = comm.sum(A.nnz), comm.sum(P.nnz)
         return (a_nnz / max(A.n_rows, 1)) * (p_nnz / max(P.n_rows, 1)) > 4 * nc and A.n_rows <= 20000

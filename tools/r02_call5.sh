@@ -37,6 +37,7 @@ with open("gpurun_out/r02b_allk_raw.csv", "w", newline="") as f:
         w.writerow([r[i] for i in keep])
 print(len(rows) - 2, "launches,", len(keep), "columns kept")
 P
+timeout 600 python tools/setup_time.py 256 > gpurun_out/r02b_setup_time.json 2> gpurun_out/r02b_setup_time.err; cat gpurun_out/r02b_setup_time.json; tail -3 gpurun_out/r02b_setup_time.err
 timeout 400 python tools/fused_restrict_bench.py 256 > gpurun_out/r02b_fused_restrict.jsonl 2> gpurun_out/r02b_fused_restrict.err; cat gpurun_out/r02b_fused_restrict.jsonl
 timeout 400 python tools/profile_fused.py --n 256 --ranks 8 --rank 3 > gpurun_out/r02b_profile_fused_n8r3.jsonl 2> gpurun_out/r02b_profile_fused.err; cat gpurun_out/r02b_profile_fused_n8r3.jsonl | cut -c1-250
 timeout 400 python bench.py --workload unstructured2d --steps 5 --no-cpu-baseline 2> gpurun_out/r02b_bench_unstructured.err | tee gpurun_out/r02b_bench_unstructured.json | cut -c1-300
