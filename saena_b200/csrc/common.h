@@ -236,6 +236,7 @@ struct saena_b200_ctx {
     int64_t graph_replays = 0;
     std::vector<VcycleGraph> graphs;
     bool scale = false;  // saena_object::scale
+    double merge_above = 0.25;  // operator upload: merged layout from this fraction of rows with remote entries
     int apply_mode = 0;  // measurement only: 0 full, 1 local kernels only (no exchange), 2 pack + exchange only
     int64_t launches = 0;
 

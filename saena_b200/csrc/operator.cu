@@ -93,8 +93,11 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
         }
         n_outside_clean_run = M - best;
     }
+    // (ctx->merge_above, default 0.25, SAENA_B200_MERGE_ABOVE: the fraction of rows with remote entries from which the
+    //  split stops paying -- those rows take the boundary-row kernel, the merged operator runs every row on its own
+    //  mapping but cannot start before the ghost values are there)
     op.merged = d->nnz_remote > 0 &&
-                ((int64_t)n_rows_with_remote * 4 >= M ||
+                ((double)n_rows_with_remote >= ctx->merge_above * (double)M ||
                  ((int64_t)n_outside_clean_run * 4 >= M && n_outside_clean_run >= 2 * n_rows_with_remote));
     if (op.merged) {
         const int64_t nl = d->nnz_local, nr = d->nnz_remote, nt = nl + nr;
