@@ -83,6 +83,7 @@ static int init_common(saena_b200_ctx **ctx_out, int device_id, int rank, int nr
     if (const char *hf = getenv("SAENA_B200_HALO_FUSED")) ctx->fused_default = atoi(hf) != 0;
     if (const char *nv = getenv("SAENA_B200_NVTX")) ctx->nvtx = atoi(nv) != 0;
     if (const char *m = getenv("SAENA_B200_MERGE_ABOVE")) ctx->merge_above = atof(m);
+    if (const char *m = getenv("SAENA_B200_MERGED_SPLIT")) ctx->merged_split = atoi(m) != 0;
     if (const char *t = getenv("SAENA_B200_HALO_TIMEOUT_MS")) ctx->halo_timeout_ns = (unsigned long long)(atof(t) * 1e6);
     if (const char *t = getenv("SAENA_B200_SYNC_TIMEOUT_S")) ctx->sync_timeout_s = atof(t);
     if (init_body(ctx, nccl_id)) {

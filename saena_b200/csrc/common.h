@@ -151,6 +151,8 @@ struct DevOperator {
     // after the exchange, with the ordinary kernels.
     bool merged = false;
     double *x_ext = nullptr;  // [n_local_cols + recvSize]
+    int *rowmid = nullptr;    // merged, 32-bit offsets: where the ghost columns of each row start (rows are [local | ghost])
+    double *partial = nullptr;  // [M] local-column sums kept across the wait of the fused kernel (fused_halo.cu)
 
     // halo plan
     int vIndexSize = 0, recvSize = 0;
@@ -236,6 +238,7 @@ struct saena_b200_ctx {
     int64_t graph_replays = 0;
     std::vector<VcycleGraph> graphs;
     bool scale = false;  // saena_object::scale
+    bool merged_split = true;   // fused kernel on merged operators: local columns before the wait (SAENA_B200_MERGED_SPLIT=0: no)
     double merge_above = 0.25;  // operator upload: merged layout from this fraction of rows with remote entries
     int apply_mode = 0;  // measurement only: 0 full, 1 local kernels only (no exchange), 2 pack + exchange only
     int64_t launches = 0;

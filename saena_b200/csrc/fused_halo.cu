@@ -60,6 +60,12 @@ struct FusedArgs {
     const double *x;
     const double *ghost;  // this rank's landing area: 2 x recvSize doubles
     int recvSize;
+    // merged operators on a CSR mapping: rows are stored [local columns | ghost columns], rowmid[i] is where the ghost
+    // part of row i starts.  The local part is summed BEFORE the wait (partial[] keeps it), the ghost part after:
+    // the exchange hides behind the rows' own local work -- the reference's order too (local loop, then remote loop)
+    const int *rowmid;
+    double *partial;
+    int split;
     EpiArgs e;
     // CTA roles: pack | interior rows | rows that wait for ghosts.  The waiting CTAs are at most a
     // chip-full (resident all at once) and stride over n_wait_blocks virtual blocks, so the
@@ -80,6 +86,105 @@ __device__ __forceinline__ void fused_rows(int vb, int lo, int hi, const FusedAr
         spmv_rowgroup_body<MAP, EPI, int>(vb, lo, hi, a.rowptr, a.col, a.val, xs, a.e, nullptr);
     else
         spmv_vec_body<MAP, EPI, int>(vb, lo, hi, a.rowptr, a.col, a.val, xs, a.e, nullptr);
+}
+
+// ---- merged operators, two phases around the wait (PHASE 0: local columns -> partial[], PHASE 1: ghost columns +
+//      partial[] -> epilogue).  The thread that finishes a row is the same in both phases (same vb, same mapping), so
+//      partial[row] is written and read by one thread: no fence between the phases.
+template <int TPR, int EPI, int PHASE>
+__device__ __forceinline__ void
+fused_rowgroup_phase(int vb, const FusedArgs &a, const double *__restrict__ src) {
+    constexpr int ROWS = 256 / TPR;
+    constexpr int WPR = TPR / 32;
+    __shared__ double s_part2[8];
+    const int g = threadIdx.x / TPR, sub = threadIdx.x % TPR;
+    const int row = vb * ROWS + g;
+    double sum = 0.0;
+    if (row < a.M) {
+        const int start = PHASE == 0 ? a.rowptr[row] : a.rowmid[row];
+        const int end = PHASE == 0 ? a.rowmid[row] : a.rowptr[row + 1];
+        for (int k = start + sub; k < end; k += TPR * VEC_UNROLL) {
+            int c[VEC_UNROLL];
+            double v[VEC_UNROLL];
+#pragma unroll
+            for (int q = 0; q < VEC_UNROLL; ++q) {
+                const int kk = k + q * TPR;
+                const bool in = kk < end;
+                c[q] = in ? sb_ld_stream(a.col + kk) : (PHASE == 0 ? 0 : a.n_local);
+                v[q] = in ? sb_ld_stream(a.val + kk) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < VEC_UNROLL; ++q) sum += v[q] * (PHASE == 0 ? __ldg(src + c[q]) : src[c[q] - a.n_local]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (WPR > 1) {
+        if ((threadIdx.x & 31) == 0) s_part2[threadIdx.x >> 5] = sum;
+        __syncthreads();
+        if (sub == 0) {
+            sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) sum += s_part2[g * WPR + w];
+        }
+    }
+    if (sub == 0 && row < a.M) {
+        if (PHASE == 0) a.partial[row] = sum;
+        else sb_epilogue<EPI>(row, a.partial[row] + sum, a.e);
+    }
+    if (WPR > 1) __syncthreads();  // s_part2 is reused by the next virtual block
+}
+
+template <int LANES, int EPI, int PHASE>
+__device__ __forceinline__ void
+fused_vec_phase(int vb, const FusedArgs &a, const double *__restrict__ src) {
+    constexpr int G = 32 / LANES;
+    const int lane = threadIdx.x & 31;
+    const int warp = (vb * 256 + threadIdx.x) >> 5;
+    const int row0 = warp * 32;
+    if (row0 >= a.M) return;
+    const int my_row = row0 + lane;
+    int my_start = 0, my_end = 0;
+    if (my_row < a.M) {
+        my_start = PHASE == 0 ? a.rowptr[my_row] : a.rowmid[my_row];
+        my_end = PHASE == 0 ? a.rowmid[my_row] : a.rowptr[my_row + 1];
+    }
+    double mine = 0.0;
+    const int g = lane / LANES, sub = lane % LANES;
+#pragma unroll
+    for (int t = 0; t < LANES; ++t) {
+        const int srcl = t * G + g;
+        const int start = __shfl_sync(0xffffffffu, my_start, srcl);
+        const int end = __shfl_sync(0xffffffffu, my_end, srcl);
+        double sum = 0.0;
+        for (int k = start + sub; k < end; k += LANES * VEC_UNROLL) {
+            int c[VEC_UNROLL];
+            double v[VEC_UNROLL];
+#pragma unroll
+            for (int q = 0; q < VEC_UNROLL; ++q) {
+                const int kk = k + q * LANES;
+                const bool in = kk < end;
+                c[q] = in ? sb_ld_stream(a.col + kk) : (PHASE == 0 ? 0 : a.n_local);
+                v[q] = in ? sb_ld_stream(a.val + kk) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < VEC_UNROLL; ++q) sum += v[q] * (PHASE == 0 ? __ldg(src + c[q]) : src[c[q] - a.n_local]);
+        }
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const double v = __shfl_sync(0xffffffffu, sum, (lane % G) * LANES);
+        if (lane / G == t) mine = v;
+    }
+    if (my_row < a.M) {
+        if (PHASE == 0) a.partial[my_row] = mine;
+        else sb_epilogue<EPI>(my_row, a.partial[my_row] + mine, a.e);
+    }
+}
+
+template <int MAP, int EPI, int PHASE>
+__device__ __forceinline__ void fused_rows_phase(int vb, const FusedArgs &a, const double *src) {
+    if constexpr (MAP >= 32 && MAP != SB_MAPPING_SELL) fused_rowgroup_phase<MAP, EPI, PHASE>(vb, a, src);
+    else if constexpr (MAP != SB_MAPPING_SELL) fused_vec_phase<MAP, EPI, PHASE>(vb, a, src);
 }
 
 // The mappings whose stand-alone kernels fit 32 registers keep 8 CTAs per SM here too (the role
@@ -109,6 +214,17 @@ fused_halo_spmv_kernel(const __grid_constant__ FusedArgs a) {
         return;
     }
     // ---- rows that read ghost values
+    if constexpr (MERGED && MAP != SB_MAPPING_SELL) {
+        if (a.split) {
+            // local columns first: this is what the exchange hides behind on a merged operator
+            for (int vb = b - a.n_pack; vb < a.n_wait_blocks; vb += a.n_wait) fused_rows_phase<MAP, EPI, 0>(vb, a, a.x);
+            sb_halo_wait_cta(a.h, done);
+            const double *ghost = a.ghost + (size_t)(done & 1ull) * (size_t)a.recvSize;
+            for (int vb = b - a.n_pack; vb < a.n_wait_blocks; vb += a.n_wait) fused_rows_phase<MAP, EPI, 1>(vb, a, ghost);
+            sb_halo_release_cta(a.h, a.n_wait, done);
+            return;
+        }
+    }
     if (a.do_sync) sb_halo_wait_cta(a.h, done);
     if (a.do_compute) {
         const double *ghost = a.ghost + (size_t)(done & 1ull) * (size_t)a.recvSize;
@@ -169,6 +285,8 @@ static int apply_fused_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x
     a.n_brows = op.n_brows; a.bnd_wide = op.avg_nnz_row() >= 48.0;
     a.brow = op.brow; a.brow_ptr = op.brow_ptr; a.bcol = op.bcol; a.bval = op.bval;
     a.x = x; a.ghost = op.ghost_d; a.recvSize = op.recvSize; a.e = e;
+    a.rowmid = op.rowmid; a.partial = op.partial;
+    a.split = mode == 0 && op.merged && !op.use_sell && op.rowmid && op.partial && ctx->merged_split;
     a.do_sync = mode != 1;
     a.do_compute = mode != 2;
     a.vIndexSize = op.vIndexSize; a.vIndex = op.vIndex;

@@ -40,6 +40,7 @@ void sb_free_operator(DevOperator &op) {
     cudaFree(op.sell_ptr); cudaFree(op.sell_col); cudaFree(op.sell_val);
     cudaFree(op.sellp_ptr); cudaFree(op.sellp_perm); cudaFree(op.sellp_col); cudaFree(op.sellp_val);
     cudaFree(op.x_round);
+    cudaFree(op.rowmid); cudaFree(op.partial);
     op = DevOperator();
 }
 
@@ -143,6 +144,12 @@ int sb_upload_operator(saena_b200_ctx *ctx, const saena_b200_operator_desc *d) {
             int *p = nullptr;
             SB_TRY(dev_upload(ctx, &p, rp32.data(), rp32.size()));
             op.rowptr = p;
+            // rows are stored [local columns | ghost columns]: the split point of each row, and the scratch that keeps
+            // the local sums across the fused kernel's wait
+            std::vector<int> mid((size_t)std::max(M, 1));
+            for (int i = 0; i < M; ++i) mid[i] = rp32[i] + d->nnzPerRow_local[i];
+            SB_TRY(dev_upload(ctx, &op.rowmid, mid.data(), (size_t)M));
+            SB_CUDA(cudaMalloc((void **)&op.partial, sizeof(double) * (size_t)std::max(M, 1)));
         }
         SB_TRY(dev_upload(ctx, &op.col, mc.data(), mc.size()));
         SB_TRY(dev_upload(ctx, &op.val, mv.data(), mv.size()));
