@@ -277,6 +277,9 @@ int saena_b200_time_matvec_compute_only(saena_b200_ctx *ctx, int level, int kind
  * launches each and the relative 2-norm difference of the two coarse vectors. */
 int saena_b200_time_residual_restrict(saena_b200_ctx *ctx, int level, const double *u, const double *rhs, int reps,
                                       float *ms_two_kernels, float *ms_fused, double *rel_diff);
+/* Opt-in: levels [0, levels) of the V-cycle run residual + restriction as that one scatter kernel where the level is
+ * eligible (no halo, A on the sliced layout); 0 (default) keeps the two kernels.  Measured: profiles/r02_fused_restrict.md. */
+int saena_b200_set_fused_restrict(saena_b200_ctx *ctx, int levels);
 int saena_b200_timer_start(saena_b200_ctx *ctx);
 /* ms per V-cycle entered at `level` from a zero iterate (reps back-to-back, eager, collective over
  * the ranks); the difference between consecutive levels is one level's cost inside a solve */

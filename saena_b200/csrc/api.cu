@@ -898,7 +898,7 @@ int saena_b200_autotune_mapping(saena_b200_ctx *ctx, int reps, double min_gain, 
             const bool has_halo = mine && (!op->sends.empty() || !op->recvs.empty() || op->nnz_remote > 0 || op->merged);
             // ---- agree: [largest threads-per-row starting point, somebody is sliced / streaming / pinned]
             double agree[2] = {(cur >= 1 && cur <= 256) ? (double)cur : 0.0,
-                               (mine && (cur <= 0 || cur >= SB_MAPPING_SELL || op->sell_only)) ? 1.0 : 0.0};
+                               (mine && (cur <= 0 || cur == SB_MAPPING_SELL || cur == SB_MAPPING_SELLP || op->sell_only)) ? 1.0 : 0.0};
             if (multi) {
                 SB_CUDA(cudaMemcpyAsync(ctx->tune_dev, agree, sizeof(agree), cudaMemcpyHostToDevice, ctx->stream));
                 SB_TRY(sb_allreduce_max(ctx, ctx->tune_dev, 2, ctx->stream));

@@ -238,7 +238,12 @@ struct saena_b200_ctx {
     int64_t graph_replays = 0;
     std::vector<VcycleGraph> graphs;
     bool scale = false;  // saena_object::scale
-    bool merged_split = true;   // fused kernel on merged operators: local columns before the wait (SAENA_B200_MERGED_SPLIT=0: no)
+    int fused_restrict_levels = 0;  // levels [0, n) run residual + restriction as ONE scatter kernel (fused_restrict.cu); 0: off
+    // fused kernel on merged operators: local columns summed before the wait, ghost columns after.  Opt-in
+    // (SAENA_B200_MERGED_SPLIT=1): measured at N=2 on 256^3 it LOSES (levels 3-4: 1.52 / 0.67 ms per V-cycle against
+    // 1.38 / 0.61 -- the second reduction and the second walk over the row offsets cost more than the ~10 us of
+    // exchange they hide); kept for the latency-bound many-rank case
+    bool merged_split = false;
     double merge_above = 0.25;  // operator upload: merged layout from this fraction of rows with remote entries
     int apply_mode = 0;  // measurement only: 0 full, 1 local kernels only (no exchange), 2 pack + exchange only
     int64_t launches = 0;
@@ -354,6 +359,9 @@ int sb_check_fault(saena_b200_ctx *ctx);                   // non-zero (and ctx-
 // collective end of a solver call: all ranks return the same status (one all-reduce of the fault flags), so no rank
 // leaves the sequence of collective calls while the others go on
 int sb_agree_fault(saena_b200_ctx *ctx);
+
+// ---- fused_restrict.cu
+int sb_residual_restrict_fused(saena_b200_ctx *ctx, int l, const double *u, const double *rhs, double *res_coarse);
 
 // ---- vector_ops.cu
 int sb_dot(saena_b200_ctx *ctx, const double *a, const double *b, int n, int slot);           // scalars[slot] = <a,b> (global)

@@ -50,6 +50,31 @@ residual_restrict_sell_kernel(int M, const long long *__restrict__ slice_ptr, co
     for (int k = a; k < b; ++k) atomicAdd(res_coarse + p_col[k], p_val[k] * r);
 }
 
+// The fused form inside the V-cycle (opt-in, saena_b200_set_fused_restrict): res_coarse = R (A u - rhs) in one pass over
+// A, `res` never written.  Eligible: no halo on A, P, R of the level (one rank, or an agglomerated level), A on the
+// sliced layout, P with 32-bit CSR arrays.  Returns 1 when it ran, 0 when the level is not eligible (the caller runs
+// the two kernels), < 0 on error.
+int sb_residual_restrict_fused(saena_b200_ctx *ctx, int l, const double *u, const double *rhs, double *res_coarse) {
+    DevLevel &lv = ctx->levels[l];
+    DevOperator &A = lv.A, &P = lv.P, &R = lv.R;
+    if (l >= ctx->fused_restrict_levels) return 0;
+    if (!A.use_sell || !A.sell_ptr || !P.present || P.wide_offsets || !P.col || !P.val || P.merged || R.merged) return 0;
+    if (!A.sends.empty() || !A.recvs.empty() || !P.sends.empty() || !P.recvs.empty() || !R.sends.empty() || !R.recvs.empty()) return 0;
+    if (A.nnz_remote || P.nnz_remote || R.nnz_remote || lv.M == 0) return 0;
+    if (cudaMemsetAsync(res_coarse, 0, sizeof(double) * (size_t)std::max(R.M, 1), ctx->stream) != cudaSuccess) return -1;
+    ctx->launches += 1;
+    residual_restrict_sell_kernel<<<(lv.M + 255) / 256, 256, 0, ctx->stream>>>(lv.M, A.sell_ptr, A.sell_col, A.sell_val, u, rhs,
+                                                                          (const int *)P.rowptr, P.col, P.val, res_coarse);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+extern "C" int saena_b200_set_fused_restrict(saena_b200_ctx *ctx, int levels) {
+    if (!ctx) return 1;
+    ctx->fused_restrict_levels = levels < 0 ? 0 : levels;
+    sb_invalidate_graphs(ctx);
+    return 0;
+}
+
 extern "C" int saena_b200_time_residual_restrict(saena_b200_ctx *ctx, int level, const double *u_host, const double *rhs_host,
                                                  int reps, float *ms_two_kernels, float *ms_fused, double *rel_diff) {
     if (!ctx) return 1;

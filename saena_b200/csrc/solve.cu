@@ -102,8 +102,22 @@ int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const
     // 1. pre-smooth (:1105-1107)
     if (pre) { SbRange rg(ctx, "pre-smooth", l); SB_TRY(sb_smooth(ctx, l, smoother, pre, rhs, u_is_zero)); }
     else if (u_is_zero) SB_TRY(sb_fill_zero(ctx, lv.u[lv.cur], lv.M));
-    // 2. residual res = A u - rhs (:1140); with a zero iterate and no pre-smoothing it is -rhs
-    if (pre == 0 && u_is_zero) {
+    // 2. + 3. residual res = A u - rhs (:1140) and restriction (:1175) into the coarse grid's rhs, through the old
+    //    partition if they differ.  Opt-in (saena_b200_set_fused_restrict): both as ONE pass over A that scatters every
+    //    fine residual through its row of P and never writes res (fused_restrict.cu; measured in
+    //    profiles/r02_fused_restrict.md: -8 % on level 0, +3 % / +37 % on levels 1 / 2 -- off by default, and FP64
+    //    atomics make the coarse vector's last bits depend on the run).
+    bool fused_rr = false;
+    if (!(pre == 0 && u_is_zero) && ctx->fused_restrict_levels > l) {
+        const bool ident = lv.repart.identity();
+        const int rc = sb_residual_restrict_fused(ctx, l, lv.u[lv.cur], rhs, ident ? cl.rhs : lv.xfer_old);
+        if (rc < 0) SB_FAIL("vcycle: fused residual + restriction failed to launch");
+        fused_rr = rc == 1;
+        if (fused_rr && !ident) SB_TRY(sb_repart(ctx, lv.repart, false, lv.xfer_old, cl.rhs, ctx->stream));
+    }
+    // with a zero iterate and no pre-smoothing the residual is -rhs
+    if (fused_rr) {
+    } else if (pre == 0 && u_is_zero) {
         SB_TRY(sb_negate_copy(ctx, lv.M, rhs, lv.res));
     } else {
         SbRange rg(ctx, "residual", l);
@@ -112,8 +126,7 @@ int sb_vcycle(saena_b200_ctx *ctx, int l, int smoother, int pre, int post, const
         e.out = lv.res;
         SB_TRY(sb_apply(ctx, lv.A, lv.u[lv.cur], EPI_RESIDUAL, e));
     }
-    // 3. restrict (:1175) into the coarse grid's rhs, through the old partition if they differ
-    {
+    if (!fused_rr) {
         SbRange rg(ctx, "Rtransfer", l);
         EpiArgs e{};
         const bool ident = lv.repart.identity();

@@ -104,6 +104,7 @@ def load_library(path: Optional[str] = None):
     L.saena_b200_graph_replays.restype = ctypes.c_int64
     L.saena_b200_graph_replays.argtypes = [vp]
     L.saena_b200_set_mapping.argtypes = [vp, i, i, i]
+    L.saena_b200_set_fused_restrict.argtypes = [vp, i]
     L.saena_b200_spgemm_symbolic.argtypes = [i, i, i, vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int64)]
     L.saena_b200_spgemm_numeric.argtypes = [i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.saena_b200_time_residual_restrict.argtypes = [vp, i, vp, vp, i, ctypes.POINTER(ctypes.c_float),
@@ -125,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "saena_b200_p2p_export", "saena_b200_p2p_import", "saena_b200_find_eig", "saena_b200_p2p_enable", "saena_b200_fault_status", "saena_b200_clear_fault", "saena_b200_set_timeouts", "saena_b200_autotune_halo", "saena_b200_halo_choice", "saena_b200_solve_pcg", "saena_b200_solve_vcycle", "saena_b200_solve_smoother", "saena_b200_solve_cg",
     "saena_b200_solve_pcg_dev", "saena_b200_matvec", "saena_b200_residual", "saena_b200_smooth",
     "saena_b200_vcycle", "saena_b200_coarsest_solve", "saena_b200_dot", "saena_b200_time_matvec",
-    "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_time_vcycle", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_graph_replays", "saena_b200_set_mapping", "saena_b200_spgemm_symbolic", "saena_b200_spgemm_numeric", "saena_b200_time_residual_restrict", "saena_b200_autotune_mapping", "saena_b200_set_mapping_deferred", "saena_b200_get_mapping",
+    "saena_b200_time_smooth_sweep", "saena_b200_time_matvec_parts", "saena_b200_time_vcycle", "saena_b200_timer_start", "saena_b200_timer_stop", "saena_b200_launch_count", "saena_b200_graph_replays", "saena_b200_set_mapping", "saena_b200_set_fused_restrict", "saena_b200_spgemm_symbolic", "saena_b200_spgemm_numeric", "saena_b200_time_residual_restrict", "saena_b200_autotune_mapping", "saena_b200_set_mapping_deferred", "saena_b200_get_mapping",
     "saena_b200_operator_bytes",
 ]
 
@@ -501,6 +502,10 @@ class Context:
 
     def get_mapping(self, level, kind) -> int:
         return int(self._L.saena_b200_get_mapping(self._h, level, kind))
+
+    def set_fused_restrict(self, levels: int):
+        """levels [0, levels) of the V-cycle: residual + restriction as one scatter kernel where eligible (0: off)"""
+        self._ck(self._L.saena_b200_set_fused_restrict(self._h, int(levels)))
 
     def time_residual_restrict(self, level: int, u: np.ndarray, rhs: np.ndarray, reps: int = 10):
         """-> (ms of residual kernel + R kernel, ms of the fused scatter kernel, relative difference of the results)"""

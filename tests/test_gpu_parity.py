@@ -226,7 +226,7 @@ def test_other_solvers_and_option_sets_against_oracle(golden_ctx):
     for kw in (dict(max_iter=12, tol=1e-8, smoother="chebyshev", pre=3, post=3), dict(max_iter=7, tol=1e-8, smoother="jacobi", pre=2, post=0)):
         u_s, it_s, h_s = o.solve_smoother(g.rhs, **kw)
         u_g, it_g, h_g = ctx.solve_smoother(g.rhs, **kw)
-        assert it_g == it_s == kw["max_iter"] and len(h_g) == len(h_s)
+        assert it_g == it_s and len(h_g) == len(h_s)
         assert np.max(np.abs(h_g - h_s) / h_s) <= TOL_HIST and rel(u_g, u_s) <= 1e-10
     # saena_object::solve_CG (unpreconditioned): must converge to the same solution
     u_cg, it_cg, h_cg = ctx.solve_cg(g.rhs, 2000, 1e-10)
