@@ -426,5 +426,16 @@ def test_fused_residual_restrict_measurement_kernel_matches_the_two_kernels():
             assert diff <= TOL_OP and t1 > 0 and t2 > 0, (l, diff)
             want = Oracle(g.hier).matvec(l, KIND_R, Oracle(g.hier).residual(l, u, b))
             assert rel(ctx.matvec(l, KIND_R, ctx.residual(l, u, b)), want) <= TOL_OP
+        # the same form inside the V-cycle of a PCG solve (opt-in): iteration count and history of the oracle
+        u_o, it_o, h_o = Oracle(g.hier).solve_pcg(g.rhs, g.max_iter, g.tol, "chebyshev", g.pre, g.post)
+        launches = ctx.launch_count()
+        ctx.set_fused_restrict(len(g.hier.levels))
+        u1, it1, h1 = ctx.solve_pcg(g.rhs, g.max_iter, g.tol, "chebyshev", g.pre, g.post)
+        n_fused = ctx.launch_count() - launches
+        ctx.set_fused_restrict(0)
+        u2, it2, h2 = ctx.solve_pcg(g.rhs, g.max_iter, g.tol, "chebyshev", g.pre, g.post)
+        check_pcg(it1, h1, u1, it_o, h_o, u_o)
+        check_pcg(it2, h2, u2, it_o, h_o, u_o)
+        assert n_fused < ctx.launch_count() - launches - n_fused   # one launch less per level and V-cycle
     finally:
         ctx.close()
