@@ -244,7 +244,12 @@ struct saena_b200_ctx {
     // 1.38 / 0.61 -- the second reduction and the second walk over the row offsets cost more than the ~10 us of
     // exchange they hide); kept for the latency-bound many-rank case
     bool merged_split = false;
-    double merge_above = 0.25;  // operator upload: merged layout from this fraction of rows with remote entries
+    // operator upload: merged layout from this fraction of rows with remote entries.  0.25 in round 1; measured in
+    // round 2: the rows outside the clean run take the boundary-row kernel at ~1/3 of the interior mapping's rate, so
+    // already 12 % of such rows cost level 1 of the 512^3 hierarchy on 8 GPUs a third of its time (1.459 ms per sweep
+    // against 1.078 ms for the same rows on one GPU), while a merged operator only gives up the ~30 us of overlap;
+    // 256^3 on 4 GPUs: levels 1-2 -3 % / -6 % at 0.08 (profiles/r02_bench_n4_merge_above_0.08.json)
+    double merge_above = 0.08;
     int apply_mode = 0;  // measurement only: 0 full, 1 local kernels only (no exchange), 2 pack + exchange only
     int64_t launches = 0;
 

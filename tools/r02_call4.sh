@@ -20,7 +20,7 @@ for l in open("gpurun_out/r02_bench_512_n8.json"):
         print('roofline', d['roofline'])
         for e in d['levels']: print({k:(round(v,4) if isinstance(v,float) else v) for k,v in e.items()})
 P
-SAENA_BENCH_AGG_SWEEP=2000 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 8 --steps 10 --no-cpu-baseline 2> gpurun_out/r02_bench_n8.err | tee gpurun_out/r02_bench_n8.json | cut -c1-300
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 8 --steps 10 --no-cpu-baseline 2> gpurun_out/r02_bench_n8.err | tee gpurun_out/r02_bench_n8.json | cut -c1-300
 echo "256^3 N=8 bench exit $?"; grep -E "rank|Error|error|FAILED|fallback" gpurun_out/r02_bench_n8.err | tail -8
 python - <<'P'
 import json
