@@ -292,7 +292,7 @@ static int apply_fused_epi(saena_b200_ctx *ctx, DevOperator &op, const double *x
     a.vIndexSize = op.vIndexSize; a.vIndex = op.vIndex;
     a.round_float = !op.use_double;
     a.h = sb_halo_sync_args(ctx, op);
-    a.n_pack = mode == 1 ? 0 : (op.vIndexSize + 255) / 256;
+    a.n_pack = mode == 1 ? 0 : (op.vIndexSize + SB_PACK_PER_CTA - 1) / SB_PACK_PER_CTA;
     if (op.merged) {
         a.n_int = 0;
         a.n_wait_blocks = main_blocks(op, op.M);

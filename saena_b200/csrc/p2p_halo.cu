@@ -176,7 +176,7 @@ int sb_p2p_pack(saena_b200_ctx *ctx, DevOperator &op, const double *x, cudaStrea
     if (op.sends.empty()) return 0;
     if (op.sends.size() > 256) SB_FAIL("peer-memory halo: more than 256 receivers (one spinning thread each)");
     ++ctx->launches;
-    const int blocks = std::max(1, (op.vIndexSize + 255) / 256);
+    const int blocks = std::max(1, (op.vIndexSize + SB_PACK_PER_CTA - 1) / SB_PACK_PER_CTA);
     p2p_pack_kernel<<<blocks, 256, 0, s>>>(sb_halo_sync_args(ctx, op), x, op.vIndex, op.vIndexSize, !op.use_double);
     SB_CUDA(cudaGetLastError());
     return 0;

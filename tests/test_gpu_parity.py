@@ -227,7 +227,11 @@ def test_other_solvers_and_option_sets_against_oracle(golden_ctx):
         u_s, it_s, h_s = o.solve_smoother(g.rhs, **kw)
         u_g, it_g, h_g = ctx.solve_smoother(g.rhs, **kw)
         assert it_g == it_s and len(h_g) == len(h_s)
-        assert np.max(np.abs(h_g - h_s) / h_s) <= TOL_HIST and rel(u_g, u_s) <= 1e-10
+        # (as saena_object::solve above: r = A u - rhs is recomputed every iteration, so near convergence two correct
+        #  evaluations of ||r|| agree only to eps * ||rhs|| / ||r||: 1e-9 while the residual is large, 1e-6 on the tail)
+        err = np.abs(h_g - h_s) / h_s
+        head = h_s > 1e-5 * h_s[0]
+        assert err[head].max() <= TOL_HIST and err.max() <= 1e-6 and rel(u_g, u_s) <= 1e-9, err
     # saena_object::solve_CG (unpreconditioned): must converge to the same solution
     u_cg, it_cg, h_cg = ctx.solve_cg(g.rhs, 2000, 1e-10)
     assert h_cg[-1] / h_cg[0] < 1e-10
