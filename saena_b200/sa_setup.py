@@ -103,15 +103,18 @@ def _coalesce(n_rows, n_cols, row, col, val) -> _Csr:
     return _Csr(n_rows, n_cols, uk // n_cols, uk % n_cols, out)
 
 
-# "torch" until the device SpGEMM has passed tests/test_zzz_spgemm_gpu.py on a B200 (nothing lands on the bench's
-# default path before it has run on a GPU), "native" from then on
-SPGEMM_DEFAULT = "torch"
+# The one-process setup routes its products through the library's device SpGEMM since it passed
+# tests/test_zzz_spgemm_gpu.py on a B200 (scipy, the reference's golden hierarchies, the live reference at 32^3, route
+# equality at 64^3) and built the 256^3 bench hierarchy end to end (profiles/r02_setup_time.json,
+# r02_bench_n1_native_spgemm.json).  The distributed setup keeps the tensor-op route until its own run with the device
+# SpGEMM (SAENA_SETUP_SPGEMM=native asks for it there too).
+SPGEMM_DEFAULT = "native"
 
 
-def _native_spgemm_enabled(dev) -> bool:
+def _native_spgemm_enabled(dev, dist: bool = False) -> bool:
     """SAENA_SETUP_SPGEMM=native: the library's own SpGEMM (csrc/spgemm.cu) does the products on a CUDA
-    device; =torch: the tensor-op route below (the CPU path, and the A/B).  The default is set by SPGEMM_DEFAULT."""
-    return dev.type == "cuda" and os.environ.get("SAENA_SETUP_SPGEMM", SPGEMM_DEFAULT) != "torch"
+    device; =torch: the tensor-op route below (the CPU path, and the A/B)."""
+    return dev.type == "cuda" and os.environ.get("SAENA_SETUP_SPGEMM", "torch" if dist else SPGEMM_DEFAULT) != "torch"
 
 
 def _spgemm_native(A: _Csr, B: _Csr) -> _Csr:
@@ -131,11 +134,11 @@ def _spgemm_native(A: _Csr, B: _Csr) -> _Csr:
     return _Csr(A.n_rows, B.n_cols, row, c_col.to(torch.int64), c_val)
 
 
-def _spgemm(A: _Csr, B: _Csr, chunk_products: int = 300_000_000) -> _Csr:
+def _spgemm(A: _Csr, B: _Csr, chunk_products: int = 300_000_000, dist: bool = False) -> _Csr:
     """C = A B: the library's device SpGEMM on CUDA; on the CPU (and for SAENA_SETUP_SPGEMM=torch) expand / sort /
     compress with tensor ops, in row chunks bounded by the number of products"""
     dev = A.val.device
-    if _native_spgemm_enabled(dev) and A.n_rows < 2 ** 31 and B.n_cols < 2 ** 31 - 1:
+    if _native_spgemm_enabled(dev, dist) and A.n_rows < 2 ** 31 and B.n_cols < 2 ** 31 - 1:
         return _spgemm_native(A, B)
     b_counts = B.counts()
     b_ptr = torch.zeros(B.n_rows + 1, dtype=torch.int64, device=dev)

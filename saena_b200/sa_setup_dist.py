@@ -410,7 +410,7 @@ def _prefer_dense(comm: Comm, A: DCsr, A_x: _Csr, P: DCsr, P_ext: _Csr, nc: int)
     sa_setup._galerkin's rule on small levels, so that both routes stay exercised."""
     dev = A.val.device
     from . import sa_setup
-    if sa_setup._native_spgemm_enabled(dev):
+    if sa_setup._native_spgemm_enabled(dev, dist=True):
         return False          # the library's device SpGEMM takes every level (same environment on every rank)
     if dev.type != "cuda":
         a_nnz, p_nnz = comm.sum(A.nnz), comm.sum(P.nnz)
@@ -442,8 +442,8 @@ def galerkin_dist(comm: Comm, A: DCsr, cm: ColMap, col_ext: torch.Tensor, P: DCs
     uc, inv = torch.unique(P.col, return_inverse=True)                 # coarse rows my P rows reach
     Pt = _transpose(_Csr(A.m, max(int(uc.numel()), 1), P.row, inv, P.val))        # compact coarse rows x my fine rows
     if not dense:
-        AP = _spgemm(A_x, P_ext, chunk)
-        C = _spgemm(Pt, AP, chunk)
+        AP = _spgemm(A_x, P_ext, chunk, dist=True)
+        C = _spgemm(Pt, AP, chunk, dist=True)
         del AP
         return _add_partial_rows(comm, nc, coarse_split, uc[C.row] if C.nnz else C.row, C.col, C.val)
     # dense column blocks: AP[:, c0:c1] = A_x P_ext[:, c0:c1]; partial coarse rows P_local^T AP summed over ranks
