@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 
 from oracle.oracle import Oracle  # noqa: E402
 from saena_b200.hierarchy import partition_hierarchy  # noqa: E402
-from saena_b200.distributed import exchange_nccl_id, halo_exchange_host  # noqa: E402
+from saena_b200.distributed import all_ranks_ok, exchange_nccl_id, halo_exchange_host  # noqa: E402
 from tests.util import GOLDEN, Golden  # noqa: E402
 
 
@@ -28,6 +28,10 @@ def main():
     # the id broadcast used to bootstrap NCCL works over any backend
     ident = exchange_nccl_id(lambda: bytes(range(128)))
     assert ident == bytes(range(128))
+    # the agreement every fallback decision of bench.py rests on: a failure on ANY rank is a failure on every rank
+    assert all_ranks_ok(True) is True
+    assert all_ranks_ok(rank != world - 1) is False
+    assert all_ranks_ok(rank == world - 1) is (world == 1)
     rng = np.random.default_rng(5)
     for l, lv in enumerate(mine.levels):
         A = lv.A

@@ -65,3 +65,30 @@ def test_oracle_find_eig_matches_reference_engine_golden(name):
         assert iters == int(d[f"{name}.L{l}.iters"][0]), (name, l)
         # and it is the bound the setup stored, up to the reference's random start vector
         assert abs(eig - g.hier.levels[l].eig_max) <= 2e-2 * eig
+
+
+def test_oracle_stationary_solvers_match_the_frozen_reference_run():
+    """saena_object::solve and saena_object::solve_smoother as the reference ran them on a hierarchy of its own
+    (tests/golden/poisson12_stationary.npz, made by tests/golden/make_golden_stationary.py): iteration counts equal,
+    histories within 1e-9 while the residual is far from cancellation (both solvers recompute r = A u - rhs every
+    iteration: 1e-6 on the tail), solutions equal"""
+    import os
+
+    import numpy as np
+
+    from saena_b200.hierarchy import hierarchy_from_arrays
+    from tests.util import GOLDEN_DIR, TOL_HIST, rel
+    d = np.load(os.path.join(GOLDEN_DIR, "poisson12_stationary.npz"))
+    h = hierarchy_from_arrays({k[5:]: d[k] for k in d.files if k.startswith("hier.")})
+    o = Oracle(h)
+    cases = {"vcycle": ("solve_vcycle", dict(max_iter=50, tol=1e-8, smoother="chebyshev", pre=3, post=3)),
+             "smoother_cheb": ("solve_smoother", dict(max_iter=12, tol=1e-8, smoother="chebyshev", pre=3, post=3)),
+             "smoother_jacobi": ("solve_smoother", dict(max_iter=7, tol=1e-8, smoother="jacobi", pre=2, post=0))}
+    for name, (fn, kw) in cases.items():
+        u, it, hist = getattr(o, fn)(d["rhs"], **kw)
+        want = d[f"out.{name}.hist"]
+        assert it == int(d[f"out.{name}.iters"][0]) and len(hist) == len(want), name
+        err = np.abs(hist - want) / want
+        head = want > 1e-5 * want[0]
+        assert err[head].max() <= TOL_HIST and err.max() <= 1e-6, (name, err)
+        assert rel(u, d[f"out.{name}.u"]) <= 1e-9, name
