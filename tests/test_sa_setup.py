@@ -132,3 +132,23 @@ def test_nonsymmetric_strength_and_filter_edge_cases():
     P = h.levels[0].P.to_scipy_local().toarray()
     assert P.shape[0] == 6 and np.all(np.abs(P).sum(1) > 0)
     assert h.levels[1].A.M == P.shape[1] < 6
+
+
+@pytest.mark.ref
+def test_setup_reproduces_the_live_reference_at_48_cubed():
+    """one size further up than the goldens and the 32^3 check (6 levels, a 1.17 M-entry level 2): the hierarchy the
+    bench generator builds is the reference's, pattern for pattern, values to 1e-13 -- what ties the bench hierarchy's
+    provenance to the reference at the largest size its own host setup finishes here in seconds (16 s)"""
+    from oracle import ref
+    s = ref.RefSolver.poisson(50)
+    try:
+        href = s.hierarchy()
+        h = build_hierarchy(*poisson3d_coo(48), device="cpu")
+        assert len(h.levels) == len(href.levels) == 6
+        for a, b in zip(h.levels, href.levels):
+            _same_operator(a.A, b.A)
+            if b.P is not None:
+                _same_operator(a.P, b.P)
+                _same_operator(a.R, b.R)
+    finally:
+        s.close()
